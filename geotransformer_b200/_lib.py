@@ -1,0 +1,84 @@
+"""ctypes binding of the C-ABI library ``libgeob200.so`` (declared in ``include/geob200.h``).
+
+The product path has NO fallback: if the library is missing or a call fails, a RuntimeError is raised
+(the reference raises RuntimeError through TORCH_CHECK, ``extensions/common/torch_helper.h:6-35``).
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libgeob200.so')
+_lib = None
+
+c_void_p, c_int64, c_int32, c_float, c_size_t, c_int = (
+    ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_size_t, ctypes.c_int)
+
+# name -> (restype, argtypes); kept in one table so tests can check it against include/geob200.h
+SIGNATURES = {}
+
+
+def _sig(name, restype, *argtypes):
+    SIGNATURES[name] = (restype, list(argtypes))
+
+
+P, I64, I32, F, SZ = c_void_p, c_int64, c_int32, c_float, c_size_t
+_sig('geob200_last_error', ctypes.c_char_p)
+_sig('geob200_grid_subsample_workspace_bytes', SZ, I64, I64)
+_sig('geob200_grid_subsample', c_int, P, I64, P, I64, F, P, P, P, SZ, P)
+_sig('geob200_radius_search_workspace_bytes', SZ, I64, I64, I64)
+_sig('geob200_radius_search', c_int, P, I64, P, I64, P, P, I64, F, I64, P, P, P, P, SZ, P)
+
+
+def lib():
+    """Load (once) and return the C-ABI library; raises RuntimeError if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f'{LIB_PATH} not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                '(there is no CPU fallback for the geotransformer_b200 ops)')
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = handle
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().geob200_last_error().decode(errors='replace')
+        raise RuntimeError(f'{what} failed ({rc}): {msg}')
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(t, name, dtype=None):
+    if not t.is_cuda:
+        raise RuntimeError(f'{name} must be a CUDA tensor (geotransformer_b200 has no CPU path)')
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f'{name} must be {dtype}, got {t.dtype}')
+    if not t.is_contiguous():
+        raise RuntimeError(f'{name} must be contiguous')
+
+
+_WS = {}
+
+
+def workspace(nbytes, device, tag='default'):
+    """Grow-only scratch buffer per (device, tag); ops on one stream reuse it serially."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
+    buf = _WS.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _WS[key] = buf
+    return buf
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()

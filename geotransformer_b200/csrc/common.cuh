@@ -1,0 +1,86 @@
+// Shared helpers for the geob200 CUDA kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace geob200 {
+
+// Error plumbing for the C ABI: every entry point returns 0 on success or a negative code and leaves a
+// human-readable message retrievable with geob200_last_error().
+void set_error(const char* fmt, ...);
+
+#define GEOB_CHECK_CUDA(expr)                                                                   \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            geob200::set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, #expr,            \
+                               cudaGetErrorString(_e));                                         \
+            return -1;                                                                          \
+        }                                                                                       \
+    } while (0)
+
+#define GEOB_CHECK_LAUNCH()                                                                     \
+    do {                                                                                        \
+        cudaError_t _e = cudaGetLastError();                                                    \
+        if (_e != cudaSuccess) {                                                                \
+            geob200::set_error("%s:%d kernel launch failed: %s", __FILE__, __LINE__,            \
+                               cudaGetErrorString(_e));                                         \
+            return -1;                                                                          \
+        }                                                                                       \
+    } while (0)
+
+#define GEOB_REQUIRE(cond, ...)                                                                 \
+    do {                                                                                        \
+        if (!(cond)) {                                                                          \
+            geob200::set_error(__VA_ARGS__);                                                    \
+            return -2;                                                                          \
+        }                                                                                       \
+    } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Bump allocator over a caller-provided workspace.
+struct Arena {
+    char* base;
+    size_t off;
+    size_t cap;
+    __host__ Arena(void* p, size_t bytes) : base(static_cast<char*>(p)), off(0), cap(bytes) {}
+    template <typename T>
+    __host__ T* take(size_t n) {
+        off = align_up(off, 256);
+        T* r = reinterpret_cast<T*>(base + off);
+        off += n * sizeof(T);
+        return r;
+    }
+    __host__ bool ok() const { return off <= cap; }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+static inline int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+}  // namespace geob200
