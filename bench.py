@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""Benchmark of the registration hot path (BASELINE.json metric: point-cloud pairs/sec on 3DMatch-shape synthetic pairs).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload 3dmatch20k]
+
+A step = one pass of the hot path (stack-mode collate -> KPConv-FPN -> geometric transformer -> superpoint matching ->
+Sinkhorn -> local-to-global registration) over one synthetic pair per rank (weak scaling: pair i of rank r is
+synth.make_pair(workload, r + i*W)).  Prints ONE JSON line (see the task contract):
+  value     pairs/s with the raw pair already resident in HBM when the timed region starts
+  e2e       pairs/s through the public API with HOST (pinned) inputs: H2D + collate + forward + D2H of the transform
+  roofline  the dominant kernel (structure-embedding contraction), algorithmic FLOPs / CUDA-event time
+  cpu_baseline  the reference's CPU path on this box's host cores, bounded sample (N=1 only)
+--impl reference times that CPU path alone (oracle port of the forward + the reference's own C++ collate ops).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'point-cloud pairs/sec (3DMatch-shape synth)'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='3dmatch20k')
+    ap.add_argument('--gse-mode', type=int, default=None)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+def dist_env():
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    return rank, world, local
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons DURING the timed region (profiling recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', f'--id={self.index}', f'--query-gpu={q}', '--format=csv,noheader,nounits'],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(',')])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace('.', '').isdigit())
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith('active') for r in self.rows)]
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': float(self.rows[0][1]), 'reasons': reasons}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get('bf16_tflops_sustained', d.get('bf16_tflops')), d.get('hbm_gbs'), 'measured'
+    return 1400.0, 6650.0, 'fallback'
+
+
+def make_inputs(workload, n_pairs, rank, world):
+    from geotransformer_b200.synth import make_pair
+    pairs = []
+    for i in range(n_pairs):
+        p = make_pair(workload, rank + i * world)
+        pairs.append({k: p[k] for k in ('ref_points', 'src_points', 'ref_feats', 'src_feats', 'transform')})
+    return pairs
+
+
+def cpu_reference_pairs_per_s(workload, n_pairs, threads):
+    """The reference's CPU path: its own C++ collate ops (oracle/_ref, kind 'reference') when built, else the plain-C
+    port; the model forward is the torch-CPU restatement (kind 'port').  Returns (pairs/s, seconds, description)."""
+    from geotransformer_b200.config import make_cfg
+    from geotransformer_b200.model import create_model
+    from geotransformer_b200.synth import make_pair, WORKLOADS
+    from geotransformer_b200.weights import synthetic_state_dict
+    from oracle import geo_oracle as G, collate_oracle, ref_ext
+    torch.set_num_threads(threads)
+    cfg = make_cfg(WORKLOADS[workload][0])
+    sd = synthetic_state_dict(create_model(cfg), 7351)
+    impl = ref_ext if ref_ext.available() else collate_oracle
+    limits = cfg.neighbor_limits or [27, 75, 147, 157, 119][:cfg.backbone.num_stages]
+    t_collate = t_fwd = 0.0
+    for i in range(n_pairs):
+        pair = make_pair(workload, 1000 + i)
+        t0 = time.perf_counter()
+        data = G.collate_pair(pair, cfg, limits, impl=impl)
+        t1 = time.perf_counter()
+        with torch.no_grad():
+            G.forward(sd, cfg, data)
+        t2 = time.perf_counter()
+        t_collate += t1 - t0
+        t_fwd += t2 - t1
+    total = t_collate + t_fwd
+    kind = 'reference C++ collate + torch-CPU port of the forward' if impl is ref_ext else 'port'
+    return n_pairs / total, total, f'{n_pairs} pair(s) of {workload}: collate {t_collate:.1f}s + forward {t_fwd:.1f}s ({kind})'
+
+
+def main():
+    args = parse()
+    rank, world, local = dist_env()
+    assert world == args.gpus or world == 1, f'WORLD_SIZE={world} but --gpus {args.gpus}'
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        threads = os.cpu_count() or 1
+        # bounded sample per step: 1 pair of the workload (several seconds to minutes of CPU work)
+        steps = max(1, min(args.steps, 2))
+        warm = min(args.warmup, 0)
+        for _ in range(warm):
+            cpu_reference_pairs_per_s(args.workload, 1, threads)
+        v, secs, desc = cpu_reference_pairs_per_s(args.workload, steps, threads)
+        line = {'metric': METRIC, 'value': v, 'unit': 'pairs/s', 'n_gpus': args.gpus, 'steps': steps, 'warmup': warm,
+                'ms_per_step': 1000.0 * secs / steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'dtype': 'f32', 'data': 'synthetic', 'impl': 'reference',
+                'config': {'workload': args.workload, 'pairs_per_step': 1, 'note': 'CPU path, rank 0 only'},
+                'cpu_baseline': {'value': v, 'unit': 'pairs/s', 'cores': threads, 'kind': 'reference', 'sample': desc},
+                'e2e': {'value': v, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+                'gpu_launches': 0}
+        print(json.dumps(line))
+        return
+
+    assert torch.cuda.is_available(), 'bench.py needs a GPU (the product has no CPU path)'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+
+    from geotransformer_b200 import functional as GF, _lib
+    from geotransformer_b200.config import make_cfg
+    from geotransformer_b200.model import create_model
+    from geotransformer_b200.synth import WORKLOADS
+    from geotransformer_b200.utils.data import registration_collate_fn_stack_mode
+    from geotransformer_b200.weights import synthetic_state_dict
+    from oracle import geo_oracle as G   # registration_error only (metric), not on the timed path
+
+    if args.gse_mode is not None:
+        GF.GSE_MODE = args.gse_mode
+    cfg = make_cfg(WORKLOADS[args.workload][0])
+    limits = cfg.neighbor_limits or [27, 75, 147, 157, 119][:cfg.backbone.num_stages]
+    model = create_model(cfg)
+    model.load_state_dict(synthetic_state_dict(model, 7351), strict=True)
+    model = model.to(dev).eval()
+
+    W, K = args.warmup, args.steps
+    pairs = make_inputs(args.workload, W + K, rank, world)
+    # host staging (pinned) and device-resident copies
+    pinned = [{k: torch.from_numpy(v).pin_memory() for k, v in p.items()} for p in pairs]
+    resident = [{k: v.to(dev) for k, v in p.items()} for p in pinned]
+    h2d_bytes = sum(v.numel() * v.element_size() for v in pinned[0].values())
+
+    def collate(d):
+        return registration_collate_fn_stack_mode([d], cfg.backbone.num_stages, cfg.backbone.init_voxel_size,
+                                                  cfg.backbone.init_radius, limits, device=dev)
+
+    def step_resident(i):
+        return model(collate(resident[i]))['estimated_transform']
+
+    def step_e2e(i, out_host):
+        out = model(collate(pinned[i]))
+        out_host.copy_(out['estimated_transform'], non_blocking=True)     # D2H of the step's result
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n0, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n0, n0 + n):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    out_host = torch.empty((4, 4), dtype=torch.float32).pin_memory()
+    for i in range(W):
+        step_resident(i)
+        step_e2e(i, out_host)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    lib = _lib.lib()
+    l0 = lib.geob200_launch_count()
+    GF.EVENTS = {}
+    ms_res = timed(step_resident, W, K)
+    launches = (lib.geob200_launch_count() - l0)
+    events = GF.EVENTS
+    GF.EVENTS = None
+    results = []
+    ms_e2e = timed(lambda i: results.append(step_e2e(i, out_host)), W, K)
+    sampler.stop_flag = True
+
+    # metric rows (RRE, RTE, nCorr, pair id) gathered with ONE collective
+    rows = []
+    for j, out in enumerate(results):
+        rre, rte = G.registration_error(pairs[W + j]['transform'], out['estimated_transform'].cpu().numpy())
+        rows.append([rre, rte, float(out['ref_corr_points'].shape[0]), float(rank + (W + j) * world)])
+    rows_t = torch.tensor(rows, dtype=torch.float32, device=dev)
+    if world > 1:
+        gathered = [torch.empty_like(rows_t) for _ in range(world)]
+        dist.all_gather(gathered, rows_t)
+        rows_t = torch.cat(gathered, dim=0)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # roofline of the dominant kernel: structure-embedding contraction, 2*N^2*(1+k)*C^2 FLOPs per launch
+    C = cfg.geotransformer.hidden_dim
+    gse = events.get('gse_embed', [])
+    gse_ms = [s.elapsed_time(e) for s, e in gse]
+    n_c = [int(r['ref_points_c'].shape[0]) for r in results] + [int(r['src_points_c'].shape[0]) for r in results]
+    mean_n2 = float(np.mean([n * n for n in n_c])) if n_c else 0.0
+    flops = 2.0 * mean_n2 * 4 * C * C
+    peak_tf, peak_hbm, peak_src = load_peaks()
+    avg_ms = float(np.mean(gse_ms)) if gse_ms else None
+    achieved = flops / (avg_ms * 1e-3) / 1e12 if avg_ms else None
+    mode_name = {0: 'fp32 CUDA cores', 1: 'tcgen05 3xTF32', 2: 'tcgen05 1xTF32'}[GF.GSE_MODE]
+    roofline = {'kernel': 'gse_embed (structure-embedding contraction)', 'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf,
+                'unit': 'TFLOP/s', 'frac': (achieved / peak_tf) if achieved else None, 'traffic': None,
+                'avg_ms_per_launch': avg_ms, 'launches_timed': len(gse_ms), 'flops_per_launch': flops,
+                'share_of_step': (sum(gse_ms) / ms_res) if gse_ms else None, 'mode': mode_name,
+                'peak_source': f'{peak_src} bf16 dense (MEASURED_PEAKS.json); TF32 dense peak is half of it'}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            threads = os.cpu_count() or 1
+            v, secs, desc = cpu_reference_pairs_per_s(args.workload, 1, threads)
+            cpu = {'value': v, 'unit': 'pairs/s', 'cores': threads, 'kind': 'reference' if 'reference' in desc else 'port',
+                   'sample': desc}
+        except Exception as ex:   # the baseline must never take the bench line down
+            cpu = {'value': None, 'unit': 'pairs/s', 'cores': os.cpu_count(), 'kind': 'port', 'sample': f'failed: {ex}'}
+
+    total_pairs = K * world
+    line = {
+        'metric': METRIC, 'value': total_pairs / (ms_res * 1e-3), 'unit': 'pairs/s', 'n_gpus': world, 'steps': K, 'warmup': W,
+        'ms_per_step': ms_res / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic',
+        'config': {'workload': args.workload, 'pairs_per_step_per_gpu': 1, 'points_per_cloud': int(pairs[0]['ref_points'].shape[0]),
+                   'superpoints_per_cloud': int(np.mean(n_c)) if n_c else None, 'sinkhorn_iterations': cfg.model.num_sinkhorn_iterations,
+                   'parallelism': f'pairs sharded over {world} GPU(s), one all_gather of metric rows',
+                   'l2': 'a different pair every step; per-pair working set (~0.5 GB incl. 2x75 MB embeddings) exceeds the 126 MB L2',
+                   'weights': 'random init (synthetic_state_dict seed 7351)'},
+        'e2e': {'value': total_pairs / (ms_e2e * 1e-3), 'unit': 'pairs/s', 'ms_per_step': ms_e2e / K,
+                'h2d_bytes_per_step': int(h2d_bytes), 'd2h_bytes_per_step': 64},
+        'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu, 'clocks': sampler.summary(),
+        'quality': {'median_rre_deg': float(rows_t[:, 0].median()), 'median_rte': float(rows_t[:, 1].median()),
+                    'mean_correspondences': float(rows_t[:, 2].mean()), 'pairs': int(rows_t.shape[0])},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -25,10 +25,37 @@ def _sig(name, restype, *argtypes):
 
 P, I64, I32, F, SZ = c_void_p, c_int64, c_int32, c_float, c_size_t
 _sig('geob200_last_error', ctypes.c_char_p)
+_sig('geob200_launch_count', ctypes.c_uint64)
 _sig('geob200_grid_subsample_workspace_bytes', SZ, I64, I64)
 _sig('geob200_grid_subsample', c_int, P, I64, P, I64, F, P, P, P, SZ, P)
 _sig('geob200_radius_search_workspace_bytes', SZ, I64, I64, I64)
 _sig('geob200_radius_search', c_int, P, I64, P, I64, P, P, I64, F, I64, P, P, P, P, SZ, P)
+
+_sig('geob200_kpconv', c_int, P, P, P, P, I64, I64, I64, P, I64, P, P, I64, I64, F, P, P)
+_sig('geob200_linear', c_int, P, I64, P, P, P, I64, I64, I64, I64, c_int, P)
+_sig('geob200_linear_batched', c_int, P, I64, I64, P, I64, I64, P, I64, P, I64, I64, I64, I64, I64, I64, c_int, P)
+_sig('geob200_group_norm_workspace_bytes', SZ, I64)
+_sig('geob200_group_norm', c_int, P, I64, I64, I64, P, P, F, P, c_int, F, P, P, SZ, P)
+_sig('geob200_maxpool', c_int, P, P, I64, I64, I64, I64, P, P)
+_sig('geob200_upsample_concat', c_int, P, P, I64, I64, P, I64, I64, I64, P, P)
+_sig('geob200_point_to_node_partition', c_int, P, I64, P, I64, I64, P, P, P, P, P, P, P)
+_sig('geob200_gather_rows', c_int, P, I64, I64, P, I64, P, P)
+_sig('geob200_gse_indices', c_int, P, I64, F, F, I64, P, P, P)
+_sig('geob200_gse_embed_workspace_bytes', SZ, I64, I64)
+_sig('geob200_gse_embed', c_int, P, P, I64, I64, P, P, P, P, P, P, P, P, c_int, P, SZ, P)
+_sig('geob200_attention', c_int, P, P, P, P, P, P, I64, I64, I64, I64, P, P)
+_sig('geob200_head_bias', c_int, P, P, I64, I64, I64, P, P)
+_sig('geob200_add_layernorm', c_int, P, P, P, P, I64, I64, F, P, P)
+_sig('geob200_l2_normalize', c_int, P, I64, I64, P, P)
+_sig('geob200_superpoint_matching_workspace_bytes', SZ, I64, I64)
+_sig('geob200_superpoint_matching', c_int, P, P, I64, I64, I64, P, P, I64, c_int, P, P, P, P, P, SZ, P)
+_sig('geob200_gather_patches', c_int, P, I64, P, P, I64, P, I64, P, P, P, P)
+_sig('geob200_patch_scores', c_int, P, I64, P, I64, I64, P, P, I64, I64, P, P)
+_sig('geob200_sinkhorn', c_int, P, P, P, P, I64, I64, I64, F, P, P)
+_sig('geob200_lgr_workspace_bytes', SZ, I64, I64, I64)
+_sig('geob200_local_global_registration', c_int, P, P, P, P, P, I64, I64, I64, I64, F, c_int, F, I64, I64, P, P, P, P, P,
+     P, P, P, P, P, SZ, P)
+_sig('geob200_weighted_procrustes', c_int, P, P, P, I64, I64, F, F, P, P)
 
 
 def lib():

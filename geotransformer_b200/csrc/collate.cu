@@ -17,6 +17,8 @@
 namespace geob200 {
 
 static thread_local char g_err[1024] = "";
+static unsigned long long g_launches = 0;
+void count_launches(int n) { g_launches += (unsigned long long)n; }
 void set_error(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -627,6 +629,7 @@ using namespace geob200;
 extern "C" {
 
 const char* geob200_last_error(void) { return g_err; }
+uint64_t geob200_launch_count(void) { return g_launches; }
 
 size_t geob200_grid_subsample_workspace_bytes(int64_t n_points, int64_t batch) {
     size_t n = (size_t)n_points, b = (size_t)batch;
@@ -699,6 +702,7 @@ int geob200_grid_subsample(const float* points, int64_t n_points, const int64_t*
     gs_order_kernel<<<(unsigned)batch, 1024, 0, st>>>(segs, m_per_cloud, voff, vox_key, vox_bary, cur, nxt, A, lnk,
                                                      bucket_scratch, s_points);
     GEOB_CHECK_LAUNCH();
+    count_launches(11);
     return 0;
 }
 
@@ -777,8 +781,10 @@ int geob200_radius_search(const float* q_points, int64_t n_query, const float* s
         rs_redo_kernel<CAP2><<<num_sms(), 32, CAP2 * 8, st>>>(
             q_points, q_segs, s_segs, clouds, cell_start, sorted, radius, (int)width, (long long)n_support,
             (long long*)out, counts, max_count, overflow_list, overflow_n, (int)batch);
+        count_launches(2);
     }
     GEOB_CHECK_LAUNCH();
+    count_launches(5);
     return 0;
 }
 

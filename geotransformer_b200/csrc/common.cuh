@@ -9,6 +9,8 @@ namespace geob200 {
 // Error plumbing for the C ABI: every entry point returns 0 on success or a negative code and leaves a
 // human-readable message retrievable with geob200_last_error().
 void set_error(const char* fmt, ...);
+// number of kernels launched by this library since load (bench.py reports it as gpu_launches)
+void count_launches(int n);
 
 #define GEOB_CHECK_CUDA(expr)                                                                   \
     do {                                                                                        \

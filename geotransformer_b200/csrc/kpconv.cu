@@ -1,0 +1,552 @@
+// KPConv-FPN backbone kernels: kernel-point convolution, Linear, GroupNorm(+LeakyReLU/+residual), max-pool,
+// nearest-upsample+concat.
+//
+// Reference semantics (all under /root/reference/geotransformer/modules/kpconv):
+//   kpconv.py:79-122        KPConv.forward
+//   modules.py:33-50        GroupNorm over the whole stacked (1,C,N) tensor
+//   modules.py:53-104       UnaryBlock / LastUnaryBlock
+//   functional.py:6-22,54-67 nearest_upsample / maxpool
+// The reference runs these as ~20 eager ATen launches per block with (M,H,K,3)/(M,H,C) intermediates in HBM;
+// here one kernel gathers each neighbour row once, keeps the K=15 kernel-point accumulators in registers,
+// stages the (queries x K*C) tile in shared memory and contracts it with the weights without leaving the SM.
+// Feature tables are L2-resident; the compulsory HBM traffic is the index table + the output.
+#include "common.cuh"
+#include "geob200.h"
+
+namespace geob200 {
+
+constexpr int KP = 15;        // kernel points of every shipped model (config.py: backbone.kernel_size)
+constexpr int KP_PAD = 16;
+constexpr int TQ = 32;        // queries per CTA
+constexpr int CC = 64;        // input-channel chunk staged in shared memory
+
+__device__ __forceinline__ void influence15(const float* __restrict__ kp_s, float rx, float ry, float rz, float inv_dummy,
+                                            float sigma, float* w) {
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+        const float dx = rx - kp_s[3 * k], dy = ry - kp_s[3 * k + 1], dz = rz - kp_s[3 * k + 2];
+        const float sq = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        w[k] = fmaxf(1.0f - sqrtf(sq) / sigma, 0.0f);      // kpconv.py:96-99
+    }
+    (void)inv_dummy;
+}
+
+// First layer of every backbone: Cin == 1 (features are all-ones columns, model input_dim = 1).
+// out[m][c'] = (sum_k (sum_h w[h][k] f[h]) W[k][0][c']) / max(#{h: f[h] > 0}, 1) + bias
+__global__ void __launch_bounds__(256) kpconv_c1_kernel(const float* __restrict__ feats, const float* __restrict__ q_pts,
+                                                        const float* __restrict__ s_pts, const long long* __restrict__ nbr,
+                                                        int H, const float* __restrict__ kp, const float* __restrict__ W,
+                                                        const float* __restrict__ bias, float sigma, int Ns, int M, int Cout,
+                                                        float* __restrict__ out) {
+    __shared__ float kp_s[KP * 3];
+    __shared__ float wk_s[8][KP_PAD];
+    __shared__ float np_s[8];
+    if (threadIdx.x < KP * 3) kp_s[threadIdx.x] = kp[threadIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int m = blockIdx.x * 8 + warp;
+    if (m >= M) return;
+    const float qx = q_pts[3ll * m], qy = q_pts[3ll * m + 1], qz = q_pts[3ll * m + 2];
+    float acc[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) acc[k] = 0.f;
+    int npos = 0;
+    for (int h = lane; h < H; h += 32) {
+        const long long idx = nbr[(long long)m * H + h];
+        if (idx < Ns) {
+            float w[KP];
+            influence15(kp_s, s_pts[3 * idx] - qx, s_pts[3 * idx + 1] - qy, s_pts[3 * idx + 2] - qz, 0.f, sigma, w);
+            const float f = feats[idx];
+            npos += (f > 0.f);
+#pragma unroll
+            for (int k = 0; k < KP; ++k) acc[k] = fmaf(w[k], f, acc[k]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < KP; ++k) acc[k] = warp_sum(acc[k]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) npos += __shfl_xor_sync(0xffffffffu, npos, o);
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < KP; ++k) wk_s[warp][k] = acc[k];
+        np_s[warp] = (float)max(npos, 1);
+    }
+    __syncwarp();
+    for (int c = lane; c < Cout; c += 32) {
+        float o = 0.f;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) o = fmaf(wk_s[warp][k], W[k * Cout + c], o);
+        o = o / np_s[warp];
+        if (bias != nullptr) o += bias[c];
+        out[(long long)m * Cout + c] = o;
+    }
+}
+
+// General KPConv, Cin % 32 == 0 and Cout % 32 == 0 (mid channels 32..512 of the bottleneck blocks).
+// RC = Cout / 32 output columns per thread in the contraction phase.
+template <int RC>
+__global__ void __launch_bounds__(256) kpconv_kernel(const float* __restrict__ feats, const float* __restrict__ q_pts,
+                                                     const float* __restrict__ s_pts, const long long* __restrict__ nbr,
+                                                     int H, const float* __restrict__ kp, const float* __restrict__ W,
+                                                     const float* __restrict__ bias, float sigma, int Ns, int M, int Cin,
+                                                     float* __restrict__ out) {
+    constexpr int Cout = RC * 32;
+    extern __shared__ float smem[];
+    float* wf = smem;                                  // [TQ][KP*CC]  (row stride KP*CC)
+    float* infl = wf + TQ * KP * CC;                   // [8 warps][32][KP_PAD]
+    int* sidx = (int*)(infl + 8 * 32 * KP_PAD);        // [8][32]
+    float* npos_s = (float*)(sidx + 8 * 32);           // [TQ]
+    float* kp_s = npos_s + TQ;                         // [KP*3]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < KP * 3) kp_s[threadIdx.x] = kp[threadIdx.x];
+    __syncthreads();
+    const int m0 = blockIdx.x * TQ;
+
+    float acc_out[4][RC];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int j = 0; j < RC; ++j) acc_out[r][j] = 0.f;
+
+    for (int c0 = 0; c0 < Cin; c0 += CC) {
+        const int cw = min(CC, Cin - c0);             // 32 or 64 channels in this chunk
+        // ---- phase A: one warp per query; acc[k][j] = sum_h infl[h][k] * f[nbr_h][c0 + lane + 32 j]
+        for (int q = warp; q < TQ; q += 8) {
+            const int m = m0 + q;
+            float acc[KP][2];
+#pragma unroll
+            for (int k = 0; k < KP; ++k) { acc[k][0] = 0.f; acc[k][1] = 0.f; }
+            int npos = 0;
+            if (m < M) {
+                const float qx = q_pts[3ll * m], qy = q_pts[3ll * m + 1], qz = q_pts[3ll * m + 2];
+                for (int h0 = 0; h0 < H; h0 += 32) {
+                    const int h = h0 + lane;
+                    long long idx = (h < H) ? nbr[(long long)m * H + h] : (long long)Ns;
+                    float w[KP];
+                    if (idx < Ns) {
+                        influence15(kp_s, s_pts[3 * idx] - qx, s_pts[3 * idx + 1] - qy, s_pts[3 * idx + 2] - qz, 0.f, sigma, w);
+                    } else {
+                        idx = Ns;
+#pragma unroll
+                        for (int k = 0; k < KP; ++k) w[k] = 0.f;
+                    }
+                    float* irow = infl + (warp * 32 + lane) * KP_PAD;
+#pragma unroll
+                    for (int k = 0; k < KP; ++k) irow[k] = w[k];
+                    sidx[warp * 32 + lane] = (int)idx;
+                    __syncwarp();
+                    const int hn = min(32, H - h0);
+                    for (int hh = 0; hh < hn; ++hh) {
+                        const int id = sidx[warp * 32 + hh];
+                        if (id >= Ns) continue;                      // shadow neighbour: zero feature row
+                        const float* frow = feats + (long long)id * Cin;
+                        const float f0 = frow[c0 + lane];
+                        const float f1 = (cw > 32) ? frow[c0 + 32 + lane] : 0.f;
+                        if (c0 == 0) {
+                            // neighbour counts as valid iff the sum of its WHOLE feature row is > 0 (kpconv.py:113-114)
+                            float s = f0 + f1;
+                            for (int c = CC + lane; c < Cin; c += 32) s += frow[c];
+                            s = warp_sum(s);
+                            npos += (s > 0.f);
+                        }
+                        const float4* iv = reinterpret_cast<const float4*>(infl + (warp * 32 + hh) * KP_PAD);
+                        const float4 a0 = iv[0], a1 = iv[1], a2 = iv[2], a3 = iv[3];
+                        const float wv[16] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w,
+                                              a2.x, a2.y, a2.z, a2.w, a3.x, a3.y, a3.z, a3.w};
+#pragma unroll
+                        for (int k = 0; k < KP; ++k) {
+                            acc[k][0] = fmaf(wv[k], f0, acc[k][0]);
+                            acc[k][1] = fmaf(wv[k], f1, acc[k][1]);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            float* wrow = wf + q * (KP * CC);
+#pragma unroll
+            for (int k = 0; k < KP; ++k) {
+                wrow[k * CC + lane] = acc[k][0];
+                wrow[k * CC + 32 + lane] = acc[k][1];
+            }
+            if (c0 == 0 && lane == 0) npos_s[q] = (float)max(npos, 1);
+        }
+        __syncthreads();
+        // ---- phase B: out[TQ x Cout] += wf[TQ x (KP*cw)] . W[k][c0:c0+cw][:]
+        // warp `warp` owns query rows 4*warp .. 4*warp+3 ; lane owns columns lane + 32 j
+        {
+            const float* a0p = wf + (4 * warp + 0) * (KP * CC);
+            const float* a1p = wf + (4 * warp + 1) * (KP * CC);
+            const float* a2p = wf + (4 * warp + 2) * (KP * CC);
+            const float* a3p = wf + (4 * warp + 3) * (KP * CC);
+            for (int k = 0; k < KP; ++k) {
+                const float* wbase = W + ((long long)k * Cin + c0) * Cout + lane;
+                for (int c = 0; c < cw; c += 4) {
+                    const float4 x0 = *reinterpret_cast<const float4*>(a0p + k * CC + c);
+                    const float4 x1 = *reinterpret_cast<const float4*>(a1p + k * CC + c);
+                    const float4 x2 = *reinterpret_cast<const float4*>(a2p + k * CC + c);
+                    const float4 x3 = *reinterpret_cast<const float4*>(a3p + k * CC + c);
+                    float b[4][RC];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                        for (int j = 0; j < RC; ++j) b[u][j] = __ldg(wbase + (long long)(c + u) * Cout + 32 * j);
+#pragma unroll
+                    for (int j = 0; j < RC; ++j) {
+                        acc_out[0][j] = fmaf(x0.x, b[0][j], acc_out[0][j]); acc_out[0][j] = fmaf(x0.y, b[1][j], acc_out[0][j]);
+                        acc_out[0][j] = fmaf(x0.z, b[2][j], acc_out[0][j]); acc_out[0][j] = fmaf(x0.w, b[3][j], acc_out[0][j]);
+                        acc_out[1][j] = fmaf(x1.x, b[0][j], acc_out[1][j]); acc_out[1][j] = fmaf(x1.y, b[1][j], acc_out[1][j]);
+                        acc_out[1][j] = fmaf(x1.z, b[2][j], acc_out[1][j]); acc_out[1][j] = fmaf(x1.w, b[3][j], acc_out[1][j]);
+                        acc_out[2][j] = fmaf(x2.x, b[0][j], acc_out[2][j]); acc_out[2][j] = fmaf(x2.y, b[1][j], acc_out[2][j]);
+                        acc_out[2][j] = fmaf(x2.z, b[2][j], acc_out[2][j]); acc_out[2][j] = fmaf(x2.w, b[3][j], acc_out[2][j]);
+                        acc_out[3][j] = fmaf(x3.x, b[0][j], acc_out[3][j]); acc_out[3][j] = fmaf(x3.y, b[1][j], acc_out[3][j]);
+                        acc_out[3][j] = fmaf(x3.z, b[2][j], acc_out[3][j]); acc_out[3][j] = fmaf(x3.w, b[3][j], acc_out[3][j]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int q = 4 * warp + r;
+        const int m = m0 + q;
+        if (m >= M) continue;
+        const float nn = npos_s[q];
+#pragma unroll
+        for (int j = 0; j < RC; ++j) {
+            const int c = lane + 32 * j;
+            float o = acc_out[r][j] / nn;                          // kpconv.py:116
+            if (bias != nullptr) o += bias[c];
+            out[(long long)m * Cout + c] = o;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// Linear: Y[M,N] = X[M,K] . W[N,K]^T + b  (torch.nn.Linear layout), optional ReLU.  Classic 64x64x16 smem-tiled
+// fp32 SGEMM (the reference's Linears are true fp32: torch default allow_tf32=False).
+// ----------------------------------------------------------------------------------------------------------
+template <int BM, int BN>
+__global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W, int ldw,
+                                                     const float* __restrict__ bias, float* __restrict__ Y, int ldy, int M,
+                                                     int N, int K, int relu, long long sx, long long sw, long long sb,
+                                                     long long sy) {
+    X += sx * blockIdx.z; W += sw * blockIdx.z; Y += sy * blockIdx.z;
+    if (bias != nullptr) bias += sb * blockIdx.z;
+    constexpr int BK = 16;
+    constexpr int TM = BM / 16, TN = BN / 16;
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Bs[BK][BN + 4];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+    const bool vec_ok = ((K & 3) == 0) && ((ldx & 3) == 0) && ((ldw & 3) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
+    for (int k0 = 0; k0 < K; k0 += BK) {
+        // load tiles: BM x BK of X and BN x BK of W, both K-contiguous; 4 floats per thread-load
+        for (int e = threadIdx.x; e < BM * BK / 4; e += 256) {
+            const int r = e / (BK / 4), kq = (e % (BK / 4)) * 4;
+            const int gm = m0 + r, gk = k0 + kq;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gm < M) {
+                if (vec_ok && gk + 3 < K) v = *reinterpret_cast<const float4*>(X + (long long)gm * ldx + gk);
+                else {
+                    if (gk < K) v.x = X[(long long)gm * ldx + gk];
+                    if (gk + 1 < K) v.y = X[(long long)gm * ldx + gk + 1];
+                    if (gk + 2 < K) v.z = X[(long long)gm * ldx + gk + 2];
+                    if (gk + 3 < K) v.w = X[(long long)gm * ldx + gk + 3];
+                }
+            }
+            As[kq][r] = v.x; As[kq + 1][r] = v.y; As[kq + 2][r] = v.z; As[kq + 3][r] = v.w;
+        }
+        for (int e = threadIdx.x; e < BN * BK / 4; e += 256) {
+            const int r = e / (BK / 4), kq = (e % (BK / 4)) * 4;
+            const int gn = n0 + r, gk = k0 + kq;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gn < N) {
+                if (vec_ok && gk + 3 < K) v = *reinterpret_cast<const float4*>(W + (long long)gn * ldw + gk);
+                else {
+                    if (gk < K) v.x = W[(long long)gn * ldw + gk];
+                    if (gk + 1 < K) v.y = W[(long long)gn * ldw + gk + 1];
+                    if (gk + 2 < K) v.z = W[(long long)gn * ldw + gk + 2];
+                    if (gk + 3 < K) v.w = W[(long long)gn * ldw + gk + 3];
+                }
+            }
+            Bs[kq][r] = v.x; Bs[kq + 1][r] = v.y; Bs[kq + 2][r] = v.z; Bs[kq + 3][r] = v.w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float a[TM], b[TN];
+#pragma unroll
+            for (int i = 0; i < TM; ++i) a[i] = As[kk][ty + 16 * i];
+#pragma unroll
+            for (int j = 0; j < TN; ++j) b[j] = Bs[kk][tx + 16 * j];
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const int gm = m0 + ty + 16 * i;
+        if (gm >= M) continue;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int gn = n0 + tx + 16 * j;
+            if (gn >= N) continue;
+            float v = acc[i][j] + (bias != nullptr ? bias[gn] : 0.f);
+            if (relu) v = fmaxf(v, 0.f);
+            Y[(long long)gm * ldy + gn] = v;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// GroupNorm over all rows of the stacked pair (statistics per group = C/G channels x N rows), then affine,
+// optional residual add and LeakyReLU: y = leaky((x-mean)*rstd*gamma+beta + residual).
+// Pass 1 accumulates per-CTA partial (sum, sumsq) in double and the last CTA to finish folds them into
+// mean/rstd (deterministic order) -- no host round trip, one launch.
+// ----------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x, int N, int C, int G, double eps,
+                                                       double* __restrict__ partial,   // [gridDim.x][G][2]
+                                                       unsigned* __restrict__ ticket, float* __restrict__ mean_rstd /*[G][2]*/) {
+    extern __shared__ double sh[];   // [G][2]
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sh[i] = 0.0;
+    __syncthreads();
+    const int cpg = C / G;
+    const int rows_per_blk = (N + gridDim.x - 1) / gridDim.x;
+    const int r0 = blockIdx.x * rows_per_blk, r1 = min(N, r0 + rows_per_blk);
+    // thread t walks channel c = t % C (C <= 256 -> several rows in flight per CTA; C > 256 -> loop)
+    if (C <= 256) {
+        const int rpb = 256 / C;               // rows processed concurrently
+        const int c = threadIdx.x % C, rr = threadIdx.x / C;
+        if (rr < rpb) {
+            double s = 0.0, s2 = 0.0;
+            for (int r = r0 + rr; r < r1; r += rpb) {
+                const double v = (double)x[(long long)r * C + c];
+                s += v; s2 += v * v;
+            }
+            atomicAdd(&sh[2 * (c / cpg)], s);
+            atomicAdd(&sh[2 * (c / cpg) + 1], s2);
+        }
+    } else {
+        for (int c = threadIdx.x; c < C; c += 256) {
+            double s = 0.0, s2 = 0.0;
+            for (int r = r0; r < r1; ++r) {
+                const double v = (double)x[(long long)r * C + c];
+                s += v; s2 += v * v;
+            }
+            atomicAdd(&sh[2 * (c / cpg)], s);
+            atomicAdd(&sh[2 * (c / cpg) + 1], s2);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) partial[(long long)blockIdx.x * 2 * G + i] = sh[i];
+    __threadfence();
+    __shared__ unsigned last;
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (last) {
+        for (int g = threadIdx.x; g < G; g += blockDim.x) {
+            double s = 0.0, s2 = 0.0;
+            for (unsigned b = 0; b < gridDim.x; ++b) {
+                s += partial[(long long)b * 2 * G + 2 * g];
+                s2 += partial[(long long)b * 2 * G + 2 * g + 1];
+            }
+            const double cnt = (double)cpg * (double)N;
+            const double mean = s / cnt;
+            double var = s2 / cnt - mean * mean;
+            if (var < 0.0) var = 0.0;
+            mean_rstd[2 * g] = (float)mean;
+            mean_rstd[2 * g + 1] = (float)(1.0 / sqrt(var + eps));
+        }
+        if (threadIdx.x == 0) *ticket = 0u;   // self-reset for the next launch on this stream
+    }
+}
+
+__global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean_rstd,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       const float* __restrict__ residual, float* __restrict__ y,
+                                                       long long total4, int C, int cpg, int leaky, float slope) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total4) return;
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    const int c = (int)((i * 4) % C);
+    float in[4] = {v.x, v.y, v.z, v.w}, o[4];
+    float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (residual != nullptr) rv = reinterpret_cast<const float4*>(residual)[i];
+    const float rs[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int g = (c + u) / cpg;
+        float t = (in[u] - mean_rstd[2 * g]) * mean_rstd[2 * g + 1] * gamma[c + u] + beta[c + u];
+        t += rs[u];
+        if (leaky) t = t > 0.f ? t : t * slope;
+        o[u] = t;
+    }
+    reinterpret_cast<float4*>(y)[i] = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+// max over neighbour rows (shadow row = zeros), functional.py:54-67.  One warp per output row.
+__global__ void __launch_bounds__(256) maxpool_kernel(const float* __restrict__ x, const long long* __restrict__ nbr, int H,
+                                                      int Ns, int M, int C, float* __restrict__ y) {
+    const int lane = threadIdx.x & 31;
+    const int m = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (m >= M) return;
+    for (int c = lane; c < C; c += 32) {
+        float best = -INFINITY;
+        for (int h = 0; h < H; ++h) {
+            const long long idx = nbr[(long long)m * H + h];
+            const float v = (idx < Ns) ? x[idx * C + c] : 0.f;
+            best = fmaxf(best, v);
+        }
+        y[(long long)m * C + c] = best;
+    }
+}
+
+// y[m] = [ x_pad[up[m][0]] | skip[m] ]   (functional.py:6-22 followed by torch.cat in backbone.py)
+__global__ void __launch_bounds__(256) upsample_concat_kernel(const float* __restrict__ x, const long long* __restrict__ up,
+                                                              int up_stride, int Ns, const float* __restrict__ skip, int M,
+                                                              int C1, int C2, float* __restrict__ y) {
+    const int lane = threadIdx.x & 31;
+    const int m = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (m >= M) return;
+    const long long idx = up[(long long)m * up_stride];
+    float* yr = y + (long long)m * (C1 + C2);
+    for (int c = lane; c < C1; c += 32) yr[c] = (idx < Ns) ? x[idx * C1 + c] : 0.f;
+    if (skip != nullptr)
+        for (int c = lane; c < C2; c += 32) yr[C1 + c] = skip[(long long)m * C2 + c];
+}
+
+}  // namespace geob200
+
+using namespace geob200;
+
+extern "C" {
+
+int geob200_kpconv(const float* s_feats, const float* q_points, const float* s_points, const int64_t* neighbors,
+                   int64_t n_query, int64_t n_support, int64_t n_neighbors, const float* kernel_points, int64_t n_kernel,
+                   const float* weights, const float* bias, int64_t c_in, int64_t c_out, float sigma, float* out,
+                   void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    GEOB_REQUIRE(n_kernel == KP, "kpconv: kernel_size %lld unsupported (all shipped models use 15)", (long long)n_kernel);
+    GEOB_REQUIRE(n_query > 0 && n_support > 0 && n_neighbors > 0, "kpconv: empty input");
+    if (c_in == 1) {
+        kpconv_c1_kernel<<<(unsigned)((n_query + 7) / 8), 256, 0, st>>>(s_feats, q_points, s_points, (const long long*)neighbors,
+                                                                       (int)n_neighbors, kernel_points, weights, bias, sigma,
+                                                                       (int)n_support, (int)n_query, (int)c_out, out);
+        GEOB_CHECK_LAUNCH();
+        count_launches(1);
+        return 0;
+    }
+    GEOB_REQUIRE(c_in % 32 == 0 && c_out % 32 == 0 && c_out <= 512,
+                 "kpconv: channel counts (%lld -> %lld) must be multiples of 32, c_out <= 512", (long long)c_in, (long long)c_out);
+    const size_t smem = sizeof(float) * (TQ * KP * CC + 8 * 32 * KP_PAD + TQ + KP * 3 + 3) + sizeof(int) * 8 * 32;
+    const unsigned grid = (unsigned)((n_query + TQ - 1) / TQ);
+#define LAUNCH_KP(RCV)                                                                                              \
+    {                                                                                                               \
+        static bool set = false;                                                                                    \
+        if (!set) {                                                                                                 \
+            GEOB_CHECK_CUDA(cudaFuncSetAttribute(kpconv_kernel<RCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            set = true;                                                                                             \
+        }                                                                                                           \
+        kpconv_kernel<RCV><<<grid, 256, smem, st>>>(s_feats, q_points, s_points, (const long long*)neighbors,       \
+                                                    (int)n_neighbors, kernel_points, weights, bias, sigma,         \
+                                                    (int)n_support, (int)n_query, (int)c_in, out);                 \
+    }
+    switch (c_out / 32) {
+        case 1: LAUNCH_KP(1) break;
+        case 2: LAUNCH_KP(2) break;
+        case 4: LAUNCH_KP(4) break;
+        case 8: LAUNCH_KP(8) break;
+        case 16: LAUNCH_KP(16) break;
+        default: GEOB_REQUIRE(false, "kpconv: c_out %lld unsupported (32,64,128,256,512)", (long long)c_out);
+    }
+#undef LAUNCH_KP
+    GEOB_CHECK_LAUNCH();
+    count_launches(1);
+    return 0;
+}
+
+int geob200_linear_batched(const float* x, int64_t ldx, int64_t stride_x, const float* weight, int64_t ldw, int64_t stride_w,
+                           const float* bias, int64_t stride_b, float* y, int64_t ldy, int64_t stride_y, int64_t m, int64_t n,
+                           int64_t k, int64_t batch, int relu, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    GEOB_REQUIRE(m > 0 && n > 0 && k > 0 && batch > 0, "linear: empty problem");
+    const unsigned z = (unsigned)batch;
+    if (m <= 1024 && n <= 64) {
+        dim3 grid((unsigned)((n + 31) / 32), (unsigned)((m + 31) / 32), z);
+        linear_kernel<32, 32><<<grid, 256, 0, st>>>(x, (int)ldx, weight, (int)ldw, bias, y, (int)ldy, (int)m, (int)n, (int)k, relu,
+                                                    stride_x, stride_w, stride_b, stride_y);
+    } else if (m * n * batch <= 148ll * 64 * 64 * 2) {
+        dim3 grid((unsigned)((n + 31) / 32), (unsigned)((m + 63) / 64), z);
+        linear_kernel<64, 32><<<grid, 256, 0, st>>>(x, (int)ldx, weight, (int)ldw, bias, y, (int)ldy, (int)m, (int)n, (int)k, relu,
+                                                    stride_x, stride_w, stride_b, stride_y);
+    } else {
+        dim3 grid((unsigned)((n + 63) / 64), (unsigned)((m + 63) / 64), z);
+        linear_kernel<64, 64><<<grid, 256, 0, st>>>(x, (int)ldx, weight, (int)ldw, bias, y, (int)ldy, (int)m, (int)n, (int)k, relu,
+                                                    stride_x, stride_w, stride_b, stride_y);
+    }
+    GEOB_CHECK_LAUNCH();
+    count_launches(1);
+    return 0;
+}
+
+int geob200_linear(const float* x, int64_t ldx, const float* weight, const float* bias, float* y, int64_t ldy, int64_t m,
+                   int64_t n, int64_t k, int relu, void* stream) {
+    return geob200_linear_batched(x, ldx, 0, weight, k, 0, bias, 0, y, ldy, 0, m, n, k, 1, relu, stream);
+}
+
+size_t geob200_group_norm_workspace_bytes(int64_t groups) { return (size_t)(296 * 2 * groups * 8 + 2 * groups * 4 + 256 + 1024); }
+
+int geob200_group_norm(const float* x, int64_t n_rows, int64_t channels, int64_t groups, const float* gamma,
+                       const float* beta, float eps, const float* residual, int leaky, float slope, float* y,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    GEOB_REQUIRE(n_rows > 0 && channels > 0 && groups > 0 && channels % groups == 0, "group_norm: bad shape");
+    GEOB_REQUIRE(channels % 4 == 0, "group_norm: channels must be a multiple of 4");
+    GEOB_REQUIRE(workspace_bytes >= geob200_group_norm_workspace_bytes(groups), "group_norm: workspace too small");
+    Arena ar(workspace, workspace_bytes);
+    unsigned* ticket = ar.take<unsigned>(64);           // must be zero on first use: caller provides zeroed ws once
+    float* mean_rstd = ar.take<float>(2 * groups);
+    double* partial = ar.take<double>(296 * 2 * groups);
+    int nblk = (int)((n_rows + 127) / 128);
+    if (nblk > 296) nblk = 296;
+    if (nblk < 1) nblk = 1;
+    gn_stats_kernel<<<nblk, 256, sizeof(double) * 2 * groups, st>>>(x, (int)n_rows, (int)channels, (int)groups, (double)eps,
+                                                                    partial, ticket, mean_rstd);
+    const long long total4 = n_rows * channels / 4;
+    gn_apply_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(x, mean_rstd, gamma, beta, residual, y, total4,
+                                                                     (int)channels, (int)(channels / groups), leaky, slope);
+    GEOB_CHECK_LAUNCH();
+    count_launches(2);
+    return 0;
+}
+
+int geob200_maxpool(const float* x, const int64_t* neighbors, int64_t n_query, int64_t n_support, int64_t n_neighbors,
+                    int64_t channels, float* y, void* stream) {
+    maxpool_kernel<<<(unsigned)((n_query + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, (const long long*)neighbors, (int)n_neighbors,
+                                                                                  (int)n_support, (int)n_query, (int)channels, y);
+    GEOB_CHECK_LAUNCH();
+    count_launches(1);
+    return 0;
+}
+
+int geob200_upsample_concat(const float* x, const int64_t* up_indices, int64_t up_stride, int64_t n_support,
+                            const float* skip, int64_t n_query, int64_t c1, int64_t c2, float* y, void* stream) {
+    upsample_concat_kernel<<<(unsigned)((n_query + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+        x, (const long long*)up_indices, (int)up_stride, (int)n_support, skip, (int)n_query, (int)c1, (int)c2, y);
+    GEOB_CHECK_LAUNCH();
+    count_launches(1);
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,339 @@
+"""Thin torch-tensor wrappers over the C ABI (``include/geob200.h``).
+
+PyTorch is used here only for device memory and the current stream; every computation is a hand-written
+sm_100a kernel inside ``libgeob200.so``.  All functions require CUDA tensors and raise ``RuntimeError`` otherwise
+(there is no CPU path in the product).
+"""
+import math
+
+import torch
+
+from . import _lib as L
+
+_f32, _i64, _u8, _i32 = torch.float32, torch.int64, torch.uint8, torch.int32
+
+# tensor-core mode of the structure-embedding contraction (see geob200_gse_embed): 0 fp32, 1 3xTF32, 2 1xTF32
+GSE_MODE = 0
+
+# Optional per-op CUDA-event timing on the launching stream (bench.py sets EVENTS = {} to collect
+# {op name: [(start_event, end_event), ...]}; None = off, zero overhead).
+EVENTS = None
+
+
+class _timed:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if EVENTS is not None:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.e = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+        return self
+
+    def __exit__(self, *a):
+        if EVENTS is not None:
+            self.e.record()
+            EVENTS.setdefault(self.name, []).append((self.s, self.e))
+        return False
+
+
+def _f(t, name):
+    L.require_cuda(t, name, _f32)
+    return t
+
+
+def _detach(t):
+    return t.detach() if t is not None and t.requires_grad else t
+
+
+_GN_WS = {}
+
+
+def _gn_workspace(device, groups):
+    key = (device.index, groups)
+    ws = _GN_WS.get(key)
+    if ws is None:
+        ws = torch.zeros(L.lib().geob200_group_norm_workspace_bytes(groups), dtype=_u8, device=device)
+        _GN_WS[key] = ws
+    return ws
+
+
+# ------------------------------------------------------------------------------------------------ backbone
+
+def kpconv(s_feats, q_points, s_points, neighbor_indices, kernel_points, weights, bias, sigma):
+    s_feats, weights, bias = _detach(s_feats), _detach(weights), _detach(bias)
+    _f(s_feats, 's_feats'); _f(q_points, 'q_points'); _f(s_points, 's_points')
+    L.require_cuda(neighbor_indices, 'neighbor_indices', _i64)
+    m, h = neighbor_indices.shape
+    ns = s_points.shape[0]
+    k, cin, cout = weights.shape
+    out = torch.empty((m, cout), dtype=_f32, device=s_feats.device)
+    L.check(L.lib().geob200_kpconv(s_feats.data_ptr(), q_points.data_ptr(), s_points.data_ptr(),
+                                   neighbor_indices.data_ptr(), m, ns, h, kernel_points.data_ptr(), k,
+                                   weights.data_ptr(), L.ptr(bias), cin, cout, float(sigma), out.data_ptr(),
+                                   L.stream_ptr()), 'kpconv')
+    return out
+
+
+def linear(x, weight, bias=None, relu=False, out=None):
+    """y = x @ weight.T + bias; x may be a column slice of a wider row-major tensor (stride(1) == 1)."""
+    x, weight, bias = _detach(x), _detach(weight), _detach(bias)
+    if not x.is_cuda or x.dtype != _f32 or x.stride(1) != 1:
+        raise RuntimeError('linear: x must be a float32 CUDA tensor with unit inner stride')
+    L.require_cuda(weight, 'weight', _f32)
+    m, k = x.shape
+    n = weight.shape[0]
+    if out is None:
+        out = torch.empty((m, n), dtype=_f32, device=x.device)
+    L.check(L.lib().geob200_linear(x.data_ptr(), x.stride(0), weight.data_ptr(), L.ptr(bias), out.data_ptr(),
+                                   out.stride(0), m, n, k, int(relu), L.stream_ptr()), 'linear')
+    return out
+
+
+def group_norm(x, weight, bias, groups, eps=1e-5, negative_slope=None, residual=None):
+    x, weight, bias = _detach(x), _detach(weight), _detach(bias)
+    _f(x, 'x')
+    n, c = x.shape
+    ws = _gn_workspace(x.device, groups)
+    y = torch.empty_like(x)
+    L.check(L.lib().geob200_group_norm(x.data_ptr(), n, c, groups, weight.data_ptr(), bias.data_ptr(), float(eps),
+                                       L.ptr(residual), int(negative_slope is not None),
+                                       float(negative_slope or 0.0), y.data_ptr(), ws.data_ptr(), ws.numel(),
+                                       L.stream_ptr()), 'group_norm')
+    return y
+
+
+def maxpool(x, neighbor_indices):
+    x = _detach(x)
+    _f(x, 'x'); L.require_cuda(neighbor_indices, 'neighbor_indices', _i64)
+    m, h = neighbor_indices.shape
+    y = torch.empty((m, x.shape[1]), dtype=_f32, device=x.device)
+    L.check(L.lib().geob200_maxpool(x.data_ptr(), neighbor_indices.data_ptr(), m, x.shape[0], h, x.shape[1],
+                                    y.data_ptr(), L.stream_ptr()), 'maxpool')
+    return y
+
+
+def upsample_concat(x, upsample_indices, skip=None):
+    """[nearest_upsample(x, upsample_indices) | skip]; ``upsample_indices`` (M, H) -- only column 0 is used."""
+    x = _detach(x)
+    _f(x, 'x')
+    if not upsample_indices.is_cuda or upsample_indices.dtype != _i64:
+        raise RuntimeError('upsample_indices must be an int64 CUDA tensor')
+    m = upsample_indices.shape[0]
+    stride = upsample_indices.stride(0) if upsample_indices.ndim == 2 else 1
+    c1 = x.shape[1]
+    c2 = 0 if skip is None else skip.shape[1]
+    y = torch.empty((m, c1 + c2), dtype=_f32, device=x.device)
+    L.check(L.lib().geob200_upsample_concat(x.data_ptr(), upsample_indices.data_ptr(), stride, x.shape[0],
+                                            L.ptr(skip), m, c1, c2, y.data_ptr(), L.stream_ptr()), 'upsample_concat')
+    return y
+
+
+def nearest_upsample(x, upsample_indices):
+    return upsample_concat(x, upsample_indices, None)
+
+
+# ------------------------------------------------------------------------------------------------ partition
+
+def point_to_node_partition(points, nodes, point_limit, return_count=False):
+    _f(points, 'points'); _f(nodes, 'nodes')
+    n, m = points.shape[0], nodes.shape[0]
+    dev = points.device
+    p2n = torch.empty((n,), dtype=_i64, device=dev)
+    node_masks = torch.empty((m,), dtype=torch.bool, device=dev)
+    node_sizes = torch.empty((m,), dtype=_i32, device=dev)
+    knn = torch.empty((m, point_limit), dtype=_i64, device=dev)
+    knn_masks = torch.empty((m, point_limit), dtype=torch.bool, device=dev)
+    status = torch.empty((1,), dtype=_i32, device=dev)
+    L.check(L.lib().geob200_point_to_node_partition(points.data_ptr(), n, nodes.data_ptr(), m, point_limit,
+                                                    p2n.data_ptr(), node_masks.data_ptr(), node_sizes.data_ptr(),
+                                                    knn.data_ptr(), knn_masks.data_ptr(), status.data_ptr(),
+                                                    L.stream_ptr()), 'point_to_node_partition')
+    if return_count:
+        return p2n, node_sizes.long(), node_masks, knn, knn_masks
+    return p2n, node_masks, knn, knn_masks
+
+
+def gather_rows(table, indices):
+    """index_select on a zero-padded table: rows with index >= len(table) come back as zeros."""
+    table = _detach(table)
+    _f(table, 'table'); L.require_cuda(indices, 'indices', _i64)
+    c = table.shape[1]
+    out = torch.empty((*indices.shape, c), dtype=_f32, device=table.device)
+    L.check(L.lib().geob200_gather_rows(table.data_ptr(), table.shape[0], c, indices.data_ptr(), indices.numel(),
+                                        out.data_ptr(), L.stream_ptr()), 'gather_rows')
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ transformer
+
+def gse_indices(points, sigma_d, sigma_a, angle_k):
+    _f(points, 'points')
+    n = points.shape[0]
+    d = torch.empty((n, n), dtype=_f32, device=points.device)
+    a = torch.empty((n, n, angle_k), dtype=_f32, device=points.device)
+    factor_a = 180.0 / (sigma_a * math.pi)
+    L.check(L.lib().geob200_gse_indices(points.data_ptr(), n, float(sigma_d), float(factor_a), angle_k, d.data_ptr(),
+                                        a.data_ptr(), L.stream_ptr()), 'gse_indices')
+    return d, a
+
+
+def gse_embed(d_indices, a_indices, div_term, wd, wa, bd, ba, wd_t, wa_t, mode=None):
+    n = d_indices.shape[0]
+    c = wd.shape[0]
+    mode = GSE_MODE if mode is None else mode
+    lib = L.lib()
+    ws = L.workspace(lib.geob200_gse_embed_workspace_bytes(n, c), d_indices.device, 'gse')
+    emb = torch.empty((n, n, c), dtype=_f32, device=d_indices.device)
+    with _timed('gse_embed'):
+        L.check(lib.geob200_gse_embed(d_indices.data_ptr(), a_indices.data_ptr(), n, c, div_term.data_ptr(),
+                                      wd_t.data_ptr(), wa_t.data_ptr(), wd.data_ptr(), wa.data_ptr(), bd.data_ptr(),
+                                      ba.data_ptr(), emb.data_ptr(), int(mode), ws.data_ptr(), ws.numel(), L.stream_ptr()),
+                'gse_embed')
+    return emb
+
+
+def attention(q, k, v, heads, qp=None, qb=None, embed=None):
+    n, c = q.shape
+    m = k.shape[0]
+    out = torch.empty((n, c), dtype=_f32, device=q.device)
+    L.check(L.lib().geob200_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), L.ptr(qp), L.ptr(qb), L.ptr(embed), n, m,
+                                      c, heads, out.data_ptr(), L.stream_ptr()), 'attention')
+    return out
+
+
+def head_project(q, wp_t, bp, heads):
+    """qp[n,h,:] = Wp[h*d:(h+1)*d, :]^T q[n,h*d:(h+1)*d]  and  qb[n,h] = q_h . bp_h   (proj_p moved onto q)."""
+    n, c = q.shape
+    d = c // heads
+    qp = torch.empty((n, heads, c), dtype=_f32, device=q.device)
+    qb = torch.empty((n, heads), dtype=_f32, device=q.device)
+    lib = L.lib()
+    # batched over heads: x = q[:, h*d:(h+1)*d] (ldx=c, stride d), W' = wp_t[:, h*d:(h+1)*d] (ldw=c, stride d),
+    # y = qp[:, h, :] (ldy=heads*c, stride c)
+    L.check(lib.geob200_linear_batched(q.data_ptr(), c, d, wp_t.data_ptr(), c, d, None, 0, qp.data_ptr(), heads * c, c,
+                                       n, c, d, heads, 0, L.stream_ptr()), 'head_project')
+    L.check(lib.geob200_head_bias(q.data_ptr(), bp.data_ptr(), n, c, heads, qb.data_ptr(), L.stream_ptr()), 'head_bias')
+    return qp, qb
+
+
+def add_layernorm(a, b, weight, bias, eps=1e-5):
+    weight, bias = _detach(weight), _detach(bias)
+    n, c = a.shape
+    y = torch.empty_like(a)
+    L.check(L.lib().geob200_add_layernorm(a.data_ptr(), L.ptr(b), weight.data_ptr(), bias.data_ptr(), n, c, float(eps),
+                                          y.data_ptr(), L.stream_ptr()), 'add_layernorm')
+    return y
+
+
+def l2_normalize(x):
+    _f(x, 'x')
+    y = torch.empty_like(x)
+    L.check(L.lib().geob200_l2_normalize(x.data_ptr(), x.shape[0], x.shape[1], y.data_ptr(), L.stream_ptr()), 'l2_normalize')
+    return y
+
+
+# ------------------------------------------------------------------------------------------------ matching
+
+def superpoint_matching(ref_feats, src_feats, ref_masks, src_masks, num_correspondences, dual_normalization=True):
+    _f(ref_feats, 'ref_feats'); _f(src_feats, 'src_feats')
+    dev = ref_feats.device
+    nr, ns, c = ref_feats.shape[0], src_feats.shape[0], ref_feats.shape[1]
+    if ref_masks is None:
+        ref_masks = torch.ones((nr,), dtype=torch.bool, device=dev)
+    if src_masks is None:
+        src_masks = torch.ones((ns,), dtype=torch.bool, device=dev)
+    lib = L.lib()
+    ws = L.workspace(lib.geob200_superpoint_matching_workspace_bytes(nr, ns), dev)
+    k = int(num_correspondences)
+    ri = torch.empty((k,), dtype=_i64, device=dev)
+    si = torch.empty((k,), dtype=_i64, device=dev)
+    sc = torch.empty((k,), dtype=_f32, device=dev)
+    cnt = torch.empty((1,), dtype=_i32, device=dev)
+    L.check(lib.geob200_superpoint_matching(ref_feats.data_ptr(), src_feats.data_ptr(), nr, ns, c, ref_masks.data_ptr(),
+                                            src_masks.data_ptr(), k, int(dual_normalization), ri.data_ptr(),
+                                            si.data_ptr(), sc.data_ptr(), cnt.data_ptr(), ws.data_ptr(), ws.numel(),
+                                            L.stream_ptr()), 'superpoint_matching')
+    if nr * ns < k:                      # only then can fewer than k correspondences exist
+        kk = int(cnt.item())
+        return ri[:kk], si[:kk], sc[:kk]
+    return ri, si, sc
+
+
+def gather_patches(corr_indices, node_knn_indices, node_knn_masks, points):
+    p, k = corr_indices.shape[0], node_knn_indices.shape[1]
+    dev = points.device
+    idx = torch.empty((p, k), dtype=_i64, device=dev)
+    msk = torch.empty((p, k), dtype=torch.bool, device=dev)
+    pts = torch.empty((p, k, 3), dtype=_f32, device=dev)
+    L.check(L.lib().geob200_gather_patches(corr_indices.data_ptr(), p, node_knn_indices.data_ptr(),
+                                           node_knn_masks.data_ptr(), k, points.data_ptr(), points.shape[0],
+                                           idx.data_ptr(), msk.data_ptr(), pts.data_ptr(), L.stream_ptr()), 'gather_patches')
+    return idx, msk, pts
+
+
+def patch_scores(ref_feats, src_feats, ref_knn_indices, src_knn_indices):
+    ref_feats, src_feats = _detach(ref_feats), _detach(src_feats)
+    p, k = ref_knn_indices.shape
+    out = torch.empty((p, k, k), dtype=_f32, device=ref_feats.device)
+    L.check(L.lib().geob200_patch_scores(ref_feats.data_ptr(), ref_feats.shape[0], src_feats.data_ptr(),
+                                         src_feats.shape[0], ref_feats.shape[1], ref_knn_indices.data_ptr(),
+                                         src_knn_indices.data_ptr(), p, k, out.data_ptr(), L.stream_ptr()), 'patch_scores')
+    return out
+
+
+def sinkhorn(scores, row_masks, col_masks, alpha, num_iterations, inf=1e12):
+    scores, alpha = _detach(scores), _detach(alpha)
+    _f(scores, 'scores')
+    p, k, k2 = scores.shape
+    if k != k2:
+        raise RuntimeError('sinkhorn: the B200 kernel handles square patch score matrices')
+    dev = scores.device
+    if row_masks is None:
+        row_masks = torch.ones((p, k), dtype=torch.bool, device=dev)
+    if col_masks is None:
+        col_masks = torch.ones((p, k), dtype=torch.bool, device=dev)
+    out = torch.empty((p, k + 1, k + 1), dtype=_f32, device=dev)
+    L.check(L.lib().geob200_sinkhorn(scores.data_ptr(), row_masks.data_ptr(), col_masks.data_ptr(), alpha.data_ptr(), p, k,
+                                     int(num_iterations), float(inf), out.data_ptr(), L.stream_ptr()), 'sinkhorn')
+    return out
+
+
+def local_global_registration(ref_knn_points, src_knn_points, ref_knn_masks, src_knn_masks, score_mat, k, acceptance_radius,
+                              mutual, confidence_threshold, correspondence_threshold, num_refinement_steps,
+                              return_details=False):
+    p, kk = ref_knn_masks.shape
+    ld = score_mat.shape[1]
+    dev = score_mat.device
+    lib = L.lib()
+    cap = p * kk * k * (1 if mutual else 2)
+    ref_c = torch.empty((cap, 3), dtype=_f32, device=dev)
+    src_c = torch.empty((cap, 3), dtype=_f32, device=dev)
+    sc = torch.empty((cap,), dtype=_f32, device=dev)
+    cp = torch.empty((cap,), dtype=_i32, device=dev)
+    n = torch.empty((1,), dtype=_i32, device=dev)
+    T = torch.empty((4, 4), dtype=_f32, device=dev)
+    pT = torch.empty((p, 4, 4), dtype=_f32, device=dev)
+    pin = torch.empty((p,), dtype=_i32, device=dev)
+    best = torch.empty((1,), dtype=_i32, device=dev)
+    ws = L.workspace(lib.geob200_lgr_workspace_bytes(p, kk, k), dev)
+    L.check(lib.geob200_local_global_registration(
+        ref_knn_points.data_ptr(), src_knn_points.data_ptr(), ref_knn_masks.data_ptr(), src_knn_masks.data_ptr(),
+        score_mat.data_ptr(), p, kk, ld, k, float(acceptance_radius), int(mutual), float(confidence_threshold),
+        int(correspondence_threshold), int(num_refinement_steps), ref_c.data_ptr(), src_c.data_ptr(), sc.data_ptr(),
+        cp.data_ptr(), n.data_ptr(), T.data_ptr(), pT.data_ptr(), pin.data_ptr(), best.data_ptr(), ws.data_ptr(),
+        ws.numel(), L.stream_ptr()), 'local_global_registration')
+    c = int(n.item())    # the one D2H of the stage: the number of correspondences sizes the returned tensors
+    if return_details:
+        return ref_c[:c], src_c[:c], sc[:c], T, dict(corr_patch=cp[:c], patch_transforms=pT, patch_inliers=pin, best=best)
+    return ref_c[:c], src_c[:c], sc[:c], T
+
+
+def weighted_procrustes(src_points, ref_points, weights=None, weight_thresh=0.0, eps=1e-5):
+    b, n = src_points.shape[0], src_points.shape[1]
+    T = torch.empty((b, 4, 4), dtype=_f32, device=src_points.device)
+    L.check(L.lib().geob200_weighted_procrustes(src_points.data_ptr(), ref_points.data_ptr(), L.ptr(weights), b, n,
+                                                float(weight_thresh), float(eps), T.data_ptr(), L.stream_ptr()),
+            'weighted_procrustes')
+    return T

@@ -1,0 +1,99 @@
+"""GeoTransformer registration model (inference forward) on the B200 path.
+
+Reference: ``experiments/*/model.py:18-217``.  Same attribute names (``backbone``, ``transformer``,
+``coarse_matching``, ``fine_matching``, ``optimal_transport``) and hence the same ``state_dict`` keys; same
+``forward(data_dict) -> output_dict`` contract.  ``gt_node_corr_*`` (needs the ground-truth transform, feeds only
+the training target and the PIR metric) is SURVEY.md section 8f "next" #1 and is not produced.
+"""
+import torch
+import torch.nn as nn
+
+from . import functional as GF
+from .backbone import KPConvFPN
+from .modules.geotransformer import GeometricTransformer, SuperPointMatching, LocalGlobalRegistration
+from .modules.sinkhorn import LearnableLogOptimalTransport
+
+
+class GeoTransformer(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = cfg
+        self.num_points_in_patch = cfg.model.num_points_in_patch
+        self.matching_radius = cfg.model.ground_truth_matching_radius
+        self.fine_level = cfg.model.fine_level            # 1 for 3DMatch/KITTI (model.py:77,80), 0 for ModelNet
+        b = cfg.backbone
+        self.backbone = KPConvFPN(b.input_dim, b.output_dim, b.init_dim, b.kernel_size, b.init_radius, b.init_sigma,
+                                  b.group_norm, num_stages=b.num_stages,
+                                  finest_decoder=2 if self.fine_level == 1 else 1)
+        g = cfg.geotransformer
+        self.transformer = GeometricTransformer(g.input_dim, g.output_dim, g.hidden_dim, g.num_heads, g.blocks, g.sigma_d,
+                                                g.sigma_a, g.angle_k, reduction_a=g.reduction_a)
+        self.coarse_matching = SuperPointMatching(cfg.coarse_matching.num_correspondences,
+                                                  cfg.coarse_matching.dual_normalization)
+        f = cfg.fine_matching
+        self.fine_matching = LocalGlobalRegistration(
+            f.topk, f.acceptance_radius, mutual=f.mutual, confidence_threshold=f.confidence_threshold,
+            use_dustbin=f.use_dustbin, use_global_score=f.use_global_score,
+            correspondence_threshold=f.correspondence_threshold, correspondence_limit=f.correspondence_limit,
+            num_refinement_steps=f.num_refinement_steps)
+        self.optimal_transport = LearnableLogOptimalTransport(cfg.model.num_sinkhorn_iterations)
+
+    @torch.no_grad()
+    def forward(self, data_dict, taps=None):
+        out = {}
+        feats = data_dict['features']
+        lens = data_dict['lengths']
+        fl = self.fine_level
+        # lengths are needed on the host to slice ref/src (the reference does three .item() syncs, model.py:76-78);
+        # the collate keeps host copies so no sync happens here
+        lens_h = data_dict.get('lengths_host')
+        if lens_h is None:
+            lens_h = [l.tolist() for l in lens]
+        nc, nf, n0 = int(lens_h[-1][0]), int(lens_h[fl][0]), int(lens_h[0][0])
+        points_c, points_f, points = data_dict['points'][-1], data_dict['points'][fl], data_dict['points'][0]
+        ref_c, src_c = points_c[:nc], points_c[nc:]
+        ref_f, src_f = points_f[:nf], points_f[nf:]
+        out.update(ref_points_c=ref_c, src_points_c=src_c, ref_points_f=ref_f, src_points_f=src_f,
+                   ref_points=points[:n0], src_points=points[n0:])
+
+        K = self.num_points_in_patch
+        _, ref_node_masks, ref_knn_idx, ref_knn_masks = GF.point_to_node_partition(ref_f, ref_c, K)
+        _, src_node_masks, src_knn_idx, src_knn_masks = GF.point_to_node_partition(src_f, src_c, K)
+        if taps is not None:
+            taps.update(ref_node_masks=ref_node_masks, src_node_masks=src_node_masks, ref_node_knn_indices=ref_knn_idx,
+                        src_node_knn_indices=src_knn_idx, ref_node_knn_masks=ref_knn_masks, src_node_knn_masks=src_knn_masks)
+
+        feats_list = self.backbone(feats, data_dict)
+        feats_c, feats_f = feats_list[-1], feats_list[0]
+        if taps is not None:
+            taps['feats_c'], taps['feats_f'] = feats_c, feats_f
+
+        ref_fc, src_fc = self.transformer(ref_c, src_c, feats_c[:nc], feats_c[nc:])
+        ref_fc_n, src_fc_n = GF.l2_normalize(ref_fc), GF.l2_normalize(src_fc)
+        ref_ff, src_ff = feats_f[:nf], feats_f[nf:]
+        out.update(ref_feats_c=ref_fc_n, src_feats_c=src_fc_n, ref_feats_f=ref_ff, src_feats_f=src_ff)
+
+        ref_corr, src_corr, node_scores = self.coarse_matching(ref_fc_n, src_fc_n, ref_node_masks, src_node_masks)
+        forced = data_dict.get('forced_node_corr')       # test hook: teacher-forced coarse correspondences
+        if forced is not None:
+            ref_corr, src_corr, node_scores = forced
+        out.update(ref_node_corr_indices=ref_corr, src_node_corr_indices=src_corr, node_corr_scores=node_scores)
+
+        rk_idx, rk_masks, rk_pts = GF.gather_patches(ref_corr, ref_knn_idx, ref_knn_masks, ref_f)
+        sk_idx, sk_masks, sk_pts = GF.gather_patches(src_corr, src_knn_idx, src_knn_masks, src_f)
+        out.update(ref_node_corr_knn_points=rk_pts, src_node_corr_knn_points=sk_pts, ref_node_corr_knn_masks=rk_masks,
+                   src_node_corr_knn_masks=sk_masks)
+
+        scores = GF.patch_scores(ref_ff, src_ff, rk_idx, sk_idx)
+        if taps is not None:
+            taps['matching_scores_raw'] = scores
+        scores = self.optimal_transport(scores, rk_masks, sk_masks)
+        out['matching_scores'] = scores
+
+        rc, sc, cs, T = self.fine_matching(rk_pts, sk_pts, rk_masks, sk_masks, scores, node_scores)
+        out.update(ref_corr_points=rc, src_corr_points=sc, corr_scores=cs, estimated_transform=T)
+        return out
+
+
+def create_model(cfg):
+    return GeoTransformer(cfg)

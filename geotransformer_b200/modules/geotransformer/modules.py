@@ -1,0 +1,107 @@
+"""``geotransformer.modules.geotransformer`` on the B200 path: same class names, constructor/forward signatures and
+``state_dict`` keys as the reference (``geotransformer/modules/geotransformer/{geotransformer.py:9-155,
+superpoint_matching.py:7-50, local_global_registration.py:11-235}``)."""
+import torch
+import torch.nn as nn
+
+from ... import functional as GF
+from ..transformer.modules import SinusoidalPositionalEmbedding, RPEConditionalTransformer, _WeightCache
+
+
+class GeometricStructureEmbedding(nn.Module):
+    """reference ``geotransformer.py:9-72``."""
+
+    def __init__(self, hidden_dim, sigma_d, sigma_a, angle_k, reduction_a='max'):
+        super().__init__()
+        if reduction_a != 'max':
+            raise NotImplementedError("only reduction_a='max' (every shipped config) is implemented")
+        self.sigma_d, self.sigma_a, self.angle_k, self.reduction_a = sigma_d, sigma_a, angle_k, reduction_a
+        self.embedding = SinusoidalPositionalEmbedding(hidden_dim)
+        self.proj_d = nn.Linear(hidden_dim, hidden_dim)
+        self.proj_a = nn.Linear(hidden_dim, hidden_dim)
+        self._cache = _WeightCache()
+
+    @torch.no_grad()
+    def get_embedding_indices(self, points):
+        """points (B=1, N, 3) or (N, 3) -> d_indices (.., N, N), a_indices (.., N, N, k)."""
+        squeeze = points.ndim == 3
+        pts = points[0] if squeeze else points
+        d, a = GF.gse_indices(pts.contiguous(), self.sigma_d, self.sigma_a, self.angle_k)
+        return (d.unsqueeze(0), a.unsqueeze(0)) if squeeze else (d, a)
+
+    def forward(self, points):
+        squeeze = points.ndim == 3
+        if squeeze and points.shape[0] != 1:
+            raise NotImplementedError('one cloud per call (the reference model always passes B=1)')
+        pts = (points[0] if squeeze else points).contiguous()
+        d, a = GF.gse_indices(pts, self.sigma_d, self.sigma_a, self.angle_k)
+        wd_t = self._cache.get('wd_t', self.proj_d.weight, lambda w: w.t().contiguous())
+        wa_t = self._cache.get('wa_t', self.proj_a.weight, lambda w: w.t().contiguous())
+        emb = GF.gse_embed(d, a, self.embedding.div_term, self.proj_d.weight.detach(), self.proj_a.weight.detach(),
+                           self.proj_d.bias.detach(), self.proj_a.bias.detach(), wd_t, wa_t)
+        return emb.unsqueeze(0) if squeeze else emb
+
+
+class GeometricTransformer(nn.Module):
+    """reference ``geotransformer.py:75-155``."""
+
+    def __init__(self, input_dim, output_dim, hidden_dim, num_heads, blocks, sigma_d, sigma_a, angle_k, dropout=None,
+                 activation_fn='ReLU', reduction_a='max'):
+        super().__init__()
+        self.embedding = GeometricStructureEmbedding(hidden_dim, sigma_d, sigma_a, angle_k, reduction_a=reduction_a)
+        self.in_proj = nn.Linear(input_dim, hidden_dim)
+        self.transformer = RPEConditionalTransformer(blocks, hidden_dim, num_heads, dropout=dropout,
+                                                     activation_fn=activation_fn)
+        self.out_proj = nn.Linear(hidden_dim, output_dim)
+
+    def forward(self, ref_points, src_points, ref_feats, src_feats, ref_masks=None, src_masks=None):
+        if ref_masks is not None or src_masks is not None:
+            raise NotImplementedError('masks are None on the inference path (EXP*/model.py:135-140)')
+        batched = ref_points.ndim == 3
+        if batched:
+            ref_points, src_points, ref_feats, src_feats = ref_points[0], src_points[0], ref_feats[0], src_feats[0]
+        ref_emb = self.embedding(ref_points)
+        src_emb = self.embedding(src_points)
+        rf = GF.linear(ref_feats, self.in_proj.weight, self.in_proj.bias)
+        sf = GF.linear(src_feats, self.in_proj.weight, self.in_proj.bias)
+        rf, sf = self.transformer(rf, sf, ref_emb, src_emb)
+        rf = GF.linear(rf, self.out_proj.weight, self.out_proj.bias)
+        sf = GF.linear(sf, self.out_proj.weight, self.out_proj.bias)
+        if batched:
+            return rf.unsqueeze(0), sf.unsqueeze(0)
+        return rf, sf
+
+
+class SuperPointMatching(nn.Module):
+    """reference ``superpoint_matching.py:7-50``."""
+
+    def __init__(self, num_correspondences, dual_normalization=True):
+        super().__init__()
+        self.num_correspondences, self.dual_normalization = num_correspondences, dual_normalization
+
+    def forward(self, ref_feats, src_feats, ref_masks=None, src_masks=None):
+        return GF.superpoint_matching(ref_feats, src_feats, ref_masks, src_masks, self.num_correspondences,
+                                      self.dual_normalization)
+
+
+class LocalGlobalRegistration(nn.Module):
+    """reference ``local_global_registration.py:11-235``."""
+
+    def __init__(self, k, acceptance_radius, mutual=True, confidence_threshold=0.05, use_dustbin=False,
+                 use_global_score=False, correspondence_threshold=3, correspondence_limit=None, num_refinement_steps=5):
+        super().__init__()
+        if use_dustbin or use_global_score or correspondence_limit is not None:
+            raise NotImplementedError('use_dustbin / use_global_score / correspondence_limit are off in every shipped config')
+        self.k, self.acceptance_radius, self.mutual = k, acceptance_radius, mutual
+        self.confidence_threshold, self.use_dustbin, self.use_global_score = confidence_threshold, use_dustbin, use_global_score
+        self.correspondence_threshold, self.correspondence_limit = correspondence_threshold, correspondence_limit
+        self.num_refinement_steps = num_refinement_steps
+
+    def forward(self, ref_knn_points, src_knn_points, ref_knn_masks, src_knn_masks, score_mat, global_scores,
+                return_details=False):
+        """score_mat: (B, K, K) or (B, K+1, K+1) log-assignment (a dustbin row/column is ignored in place, so the
+        caller does not need to slice -- a slice is accepted too, it is made contiguous)."""
+        return GF.local_global_registration(ref_knn_points.contiguous(), src_knn_points.contiguous(), ref_knn_masks.contiguous(),
+                                            src_knn_masks.contiguous(), score_mat.contiguous(), self.k, self.acceptance_radius,
+                                            self.mutual, self.confidence_threshold, self.correspondence_threshold,
+                                            self.num_refinement_steps, return_details=return_details)

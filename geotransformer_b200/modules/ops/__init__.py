@@ -1,0 +1,39 @@
+"""Op surface of ``geotransformer.modules.ops`` (reference ``modules/ops/__init__.py:1-21``) on the B200 path."""
+import torch
+
+from ... import ext as _ext
+from ... import functional as GF
+
+
+def grid_subsample(points, lengths, voxel_size):
+    """reference ``modules/ops/grid_subsample.py:7-22``."""
+    s_points, s_lengths = _ext.grid_subsampling(points, lengths, voxel_size)
+    return s_points, s_lengths
+
+
+def radius_search(q_points, s_points, q_lengths, s_lengths, radius, neighbor_limit):
+    """reference ``modules/ops/radius_search.py:7-27``; returns a CONTIGUOUS (N, min(limit, max_count)) table (the
+    reference returns a strided view that ``to_cuda`` later densifies, ``utils/torch.py:113-123``)."""
+    return _ext.radius_neighbors(q_points, s_points, q_lengths, s_lengths, radius, neighbor_limit=max(int(neighbor_limit), 0))
+
+
+def point_to_node_partition(points, nodes, point_limit, return_count=False):
+    """reference ``modules/ops/pointcloud_partition.py:60-107``."""
+    return GF.point_to_node_partition(points, nodes, point_limit, return_count)
+
+
+def index_select(data, index, dim):
+    """reference ``modules/ops/index_select.py:4-31`` (pure indexing; dim 0 on float tables uses the gather kernel)."""
+    if dim == 0 and data.is_cuda and data.dtype == torch.float32 and data.ndim == 2 and data.is_contiguous():
+        return GF.gather_rows(data, index.contiguous())
+    out = data.index_select(dim, index.reshape(-1))
+    if index.ndim > 1:
+        out = out.view(*data.shape[:dim], *index.shape, *data.shape[dim:][1:])
+    return out
+
+
+def apply_transform(points, transform):
+    """reference ``modules/ops/transformation.py:7-60`` (points only): Q = P R^T + t."""
+    if transform.ndim == 2:
+        return torch.matmul(points.reshape(-1, 3), transform[:3, :3].t()).reshape(points.shape) + transform[:3, 3]
+    return torch.matmul(points, transform[:, :3, :3].transpose(-1, -2)) + transform[:, None, :3, 3]

@@ -1,0 +1,68 @@
+"""Stack-mode collate on the GPU (reference ``geotransformer/utils/data.py:13-77,139-189``).
+
+The reference runs this on CPU inside DataLoader worker processes (single-threaded C++ ops); CUDA cannot be used in
+forked workers, so here the raw pair is moved to the device and collated in the main process on the current stream
+(the reference already has the switch for handing raw pairs through: ``precompute_data=False``, ``data.py:181-186``).
+"""
+import numpy as np
+import torch
+
+from ..modules.ops import grid_subsample, radius_search
+
+
+def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, neighbor_limits):
+    """reference ``utils/data.py:13-77``.  ``lengths`` may live on the host or the device; host copies of every level's
+    lengths are returned under ``lengths_host`` so that later stages need no device->host sync."""
+    assert num_stages == len(neighbor_limits)
+    points_list, lengths_list, lengths_host = [], [], []
+    for i in range(num_stages):
+        if i > 0:
+            points, lengths = grid_subsample(points, lengths_host[-1], voxel_size=voxel_size)
+        lengths_h = lengths.cpu() if lengths.is_cuda else lengths
+        points_list.append(points)
+        lengths_host.append(lengths_h)
+        lengths_list.append(lengths_h.to(points.device))
+        voxel_size *= 2
+
+    neighbors_list, subsampling_list, upsampling_list = [], [], []
+    for i in range(num_stages):
+        cur_points, cur_lengths = points_list[i], lengths_host[i]
+        neighbors_list.append(radius_search(cur_points, cur_points, cur_lengths, cur_lengths, radius, neighbor_limits[i]))
+        if i < num_stages - 1:
+            sub_points, sub_lengths = points_list[i + 1], lengths_host[i + 1]
+            subsampling_list.append(radius_search(sub_points, cur_points, sub_lengths, cur_lengths, radius, neighbor_limits[i]))
+            upsampling_list.append(radius_search(cur_points, sub_points, cur_lengths, sub_lengths, radius * 2,
+                                                 neighbor_limits[i + 1]))
+        radius *= 2
+    return {'points': points_list, 'lengths': lengths_list, 'lengths_host': [l.tolist() for l in lengths_host],
+            'neighbors': neighbors_list, 'subsampling': subsampling_list, 'upsampling': upsampling_list}
+
+
+def registration_collate_fn_stack_mode(data_dicts, num_stages, voxel_size, search_radius, neighbor_limits,
+                                       precompute_data=True, device='cuda'):
+    """reference ``utils/data.py:139-189``: points are stacked ``[ref_1..ref_B, src_1..src_B]``."""
+    batch_size = len(data_dicts)
+    collated = {}
+    for d in data_dicts:
+        for key, value in d.items():
+            if isinstance(value, np.ndarray):
+                value = torch.from_numpy(value)
+            collated.setdefault(key, []).append(value)
+    feats = torch.cat(collated.pop('ref_feats') + collated.pop('src_feats'), dim=0)
+    points_list = collated.pop('ref_points') + collated.pop('src_points')
+    lengths = torch.LongTensor([p.shape[0] for p in points_list])
+    points = torch.cat(points_list, dim=0)
+    if batch_size == 1:
+        for key, value in collated.items():
+            collated[key] = value[0]
+    # one H2D per tensor from pinned staging; the reference does this later in to_cuda (utils/torch.py:113-123)
+    collated = {k: (v.to(device, non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in collated.items()}
+    collated['features'] = feats.to(device, non_blocking=True)
+    points = points.to(device, non_blocking=True)
+    if precompute_data:
+        collated.update(precompute_data_stack_mode(points, lengths, num_stages, voxel_size, search_radius, neighbor_limits))
+    else:
+        collated['points'] = points
+        collated['lengths'] = lengths
+    collated['batch_size'] = batch_size
+    return collated

@@ -20,6 +20,8 @@ extern "C" {
 #endif
 
 const char* geob200_last_error(void);
+/* number of CUDA kernels this library has launched since it was loaded (bench.py: gpu_launches) */
+uint64_t geob200_launch_count(void);
 
 /* ---- collate -------------------------------------------------------------------------------------------- */
 
@@ -43,6 +45,123 @@ int geob200_radius_search(const float* q_points, int64_t n_query, const float* s
                           const int64_t* q_lengths_h, const int64_t* s_lengths_h, int64_t batch, float radius,
                           int64_t width, int64_t* out, int32_t* counts, int32_t* max_count, void* workspace,
                           size_t workspace_bytes, void* stream);
+
+/* ---- KPConv-FPN backbone --------------------------------------------------------------------------------- */
+
+/* KPConv.forward (reference geotransformer/modules/kpconv/kpconv.py:79-122), fused gather -> kernel-point
+ * influence -> contraction -> neighbour-count normalisation -> bias.  neighbors (n_query, n_neighbors) int64 with
+ * sentinel n_support; kernel_points (15,3); weights (15, c_in, c_out); bias may be NULL.
+ * c_in == 1, or c_in, c_out multiples of 32 with c_out <= 512. */
+int geob200_kpconv(const float* s_feats, const float* q_points, const float* s_points, const int64_t* neighbors,
+                   int64_t n_query, int64_t n_support, int64_t n_neighbors, const float* kernel_points, int64_t n_kernel,
+                   const float* weights, const float* bias, int64_t c_in, int64_t c_out, float sigma, float* out,
+                   void* stream);
+
+/* nn.Linear: y[m,n] = x[m,k] . weight[n,k]^T + bias (UnaryBlock.mlp, modules.py:78; every transformer Linear).
+ * ldx / ldy are row strides in floats (inputs may be column slices). */
+int geob200_linear(const float* x, int64_t ldx, const float* weight, const float* bias, float* y, int64_t ldy, int64_t m,
+                   int64_t n, int64_t k, int relu, void* stream);
+int geob200_linear_batched(const float* x, int64_t ldx, int64_t stride_x, const float* weight, int64_t ldw, int64_t stride_w,
+                           const float* bias, int64_t stride_b, float* y, int64_t ldy, int64_t stride_y, int64_t m, int64_t n,
+                           int64_t k, int64_t batch, int relu, void* stream);
+
+/* GroupNorm over all n_rows of the stacked pair (modules.py:33-50) + optional residual add + optional LeakyReLU:
+ * y = leaky((x - mean_g) * rstd_g * gamma + beta + residual).  The first 256 bytes of the workspace must be zero
+ * on first use (launch ticket; the kernel restores it). */
+size_t geob200_group_norm_workspace_bytes(int64_t groups);
+int geob200_group_norm(const float* x, int64_t n_rows, int64_t channels, int64_t groups, const float* gamma,
+                       const float* beta, float eps, const float* residual, int leaky, float slope, float* y,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* maxpool over neighbour rows with a zero shadow row (functional.py:54-67) */
+int geob200_maxpool(const float* x, const int64_t* neighbors, int64_t n_query, int64_t n_support, int64_t n_neighbors,
+                    int64_t channels, float* y, void* stream);
+
+/* y[m] = [ x_pad[up_indices[m*up_stride]] | skip[m] ]: nearest_upsample (functional.py:6-22) fused with the
+ * torch.cat of the decoder (backbone.py:75-76).  skip may be NULL (c2 = 0). */
+int geob200_upsample_concat(const float* x, const int64_t* up_indices, int64_t up_stride, int64_t n_support,
+                            const float* skip, int64_t n_query, int64_t c1, int64_t c2, float* y, void* stream);
+
+/* ---- point-to-node grouping ------------------------------------------------------------------------------ */
+
+/* point_to_node_partition (reference geotransformer/modules/ops/pointcloud_partition.py:60-107).
+ * node_masks / node_knn_masks are uint8 (torch.bool); node_sizes int32; status != 0 if a node owns > 4096 points. */
+int geob200_point_to_node_partition(const float* points, int64_t n_points, const float* nodes, int64_t n_nodes,
+                                    int64_t point_limit, int64_t* point_to_node, uint8_t* node_masks, int32_t* node_sizes,
+                                    int64_t* node_knn_indices, uint8_t* node_knn_masks, int32_t* status, void* stream);
+
+/* out[r] = indices[r] < n_rows ? table[indices[r]] : 0  (index_select on a zero-padded table, ops/index_select.py) */
+int geob200_gather_rows(const float* table, int64_t n_rows, int64_t channels, const int64_t* indices, int64_t n_indices,
+                        float* out, void* stream);
+
+/* ---- geometric transformer -------------------------------------------------------------------------------- */
+
+/* GeometricStructureEmbedding.get_embedding_indices (geotransformer.py:27-55) for one cloud:
+ * d_indices (n,n) = sqrt(pairwise_distance)/sigma_d, a_indices (n,n,3) = atan2(|ref x anc|, ref.anc) * factor_a */
+int geob200_gse_indices(const float* points, int64_t n, float sigma_d, float factor_a, int64_t angle_k, float* d_indices,
+                        float* a_indices, void* stream);
+
+/* GeometricStructureEmbedding.forward (geotransformer.py:57-72) given the indices: sinusoid -> proj_d / proj_a ->
+ * max over k -> sum, fused.  wd/wa are the nn.Linear weights (out,in); wd_t/wa_t their transposes (in,out).
+ * mode 0: fp32 CUDA cores; 1: tcgen05 3xTF32; 2: tcgen05 1xTF32. */
+size_t geob200_gse_embed_workspace_bytes(int64_t n, int64_t channels);
+int geob200_gse_embed(const float* d_indices, const float* a_indices, int64_t n, int64_t channels, const float* div_term,
+                      const float* wd_t, const float* wa_t, const float* wd, const float* wa, const float* bd, const float* ba,
+                      float* embeddings, int mode, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Fused multi-head attention: softmax((q.k + qp.E + qb)/sqrt(d)) v  (rpe_transformer.py:51-70 with proj_p moved onto
+ * q; vanilla_transformer.py:50-68 when qp = qb = embed = NULL).  q (n_query,C), k,v (n_key,C), qp (n_query,H,C),
+ * qb (n_query,H), embed (n_query,n_key,C). */
+int geob200_attention(const float* q, const float* k, const float* v, const float* qp, const float* qb, const float* embed,
+                      int64_t n_query, int64_t n_key, int64_t channels, int64_t heads, float* out, void* stream);
+int geob200_head_bias(const float* q, const float* bias_p, int64_t n, int64_t channels, int64_t heads, float* qb, void* stream);
+/* y = LayerNorm(a + b) (b may be NULL) */
+int geob200_add_layernorm(const float* a, const float* b, const float* gamma, const float* beta, int64_t n, int64_t channels,
+                          float eps, float* y, void* stream);
+/* F.normalize(x, p=2, dim=1) */
+int geob200_l2_normalize(const float* x, int64_t n, int64_t channels, float* y, void* stream);
+
+/* ---- matching ---------------------------------------------------------------------------------------------- */
+
+/* SuperPointMatching.forward (superpoint_matching.py:13-50); num_out (device int32) = number of rows written. */
+size_t geob200_superpoint_matching_workspace_bytes(int64_t n_ref, int64_t n_src);
+int geob200_superpoint_matching(const float* ref_feats, const float* src_feats, int64_t n_ref, int64_t n_src, int64_t channels,
+                                const uint8_t* ref_masks, const uint8_t* src_masks, int64_t num_correspondences, int dual,
+                                int64_t* ref_corr_indices, int64_t* src_corr_indices, float* corr_scores, int32_t* num_out,
+                                void* workspace, size_t workspace_bytes, void* stream);
+
+/* patch gathers of model.py:169-174: indices/masks/points of the k points of each selected superpoint */
+int geob200_gather_patches(const int64_t* corr_indices, int64_t n_corr, const int64_t* node_knn_indices,
+                           const uint8_t* node_knn_masks, int64_t k, const float* points, int64_t n_points,
+                           int64_t* out_indices, uint8_t* out_masks, float* out_points, void* stream);
+
+/* matching_scores = einsum('bnd,bmd->bnm') / sqrt(C) over zero-padded feature tables (model.py:176-188) */
+int geob200_patch_scores(const float* ref_feats, int64_t n_ref, const float* src_feats, int64_t n_src, int64_t channels,
+                         const int64_t* ref_knn_indices, const int64_t* src_knn_indices, int64_t n_patches, int64_t k,
+                         float* scores, void* stream);
+
+/* LearnableLogOptimalTransport.forward (learnable_sinkhorn.py:20-66): out (n_patches, k+1, k+1) */
+int geob200_sinkhorn(const float* scores, const uint8_t* row_masks, const uint8_t* col_masks, const float* alpha,
+                     int64_t n_patches, int64_t k, int64_t num_iterations, float inf, float* out, void* stream);
+
+/* ---- local-to-global registration -------------------------------------------------------------------------- */
+
+/* LocalGlobalRegistration.forward (local_global_registration.py:196-235), use_dustbin=False, use_global_score=False,
+ * correspondence_limit=None.  log_scores (P, score_ld, score_ld) with score_ld = k or k+1 (dustbin row/col ignored).
+ * Correspondence outputs have capacity P*k*topk rows; num_corr (device int32) = rows written, in (patch,i,j) order.
+ * patch_transforms (P,4,4), patch_inliers (P, -1 = patch below correspondence_threshold), best_patch may be NULL. */
+size_t geob200_lgr_workspace_bytes(int64_t n_patches, int64_t k, int64_t topk);
+int geob200_local_global_registration(const float* ref_knn_points, const float* src_knn_points, const uint8_t* ref_knn_masks,
+                                      const uint8_t* src_knn_masks, const float* log_scores, int64_t n_patches, int64_t k,
+                                      int64_t score_ld, int64_t topk, float acceptance_radius, int mutual,
+                                      float confidence_threshold, int64_t correspondence_threshold, int64_t num_refinement_steps,
+                                      float* ref_corr_points, float* src_corr_points, float* corr_scores, int32_t* corr_patch,
+                                      int32_t* num_corr, float* estimated_transform, float* patch_transforms, int32_t* patch_inliers,
+                                      int32_t* best_patch, void* workspace, size_t workspace_bytes, void* stream);
+
+/* weighted_procrustes (modules/registration/procrustes.py:6-73): transforms (batch,4,4); weights may be NULL */
+int geob200_weighted_procrustes(const float* src_points, const float* ref_points, const float* weights, int64_t batch,
+                                int64_t n, float weight_thresh, float eps, float* transforms, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,127 @@
+"""TEST INFRASTRUCTURE ONLY -- generates the committed fixtures under tests/golden/ by running the REAL reference
+(imported from /root/reference through oracle/ref_harness.py, CPU) and checks the restatement oracle/geo_oracle.py
+against it.  Run in the build container:   python -m oracle.make_golden
+
+Fixtures (compressed npz, a few MB in total):
+  tests/golden/<workload>.npz        reference outputs at the stage boundaries of SURVEY.md section 8a for the
+                                     deterministic pair synth.make_pair(workload, 0) and the deterministic weights
+                                     weights.synthetic_state_dict(model, 7351)
+The big tensors are stored as strided row samples + float64 checksums (row index arrays are stored alongside).
+"""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from geotransformer_b200.config import make_cfg                     # noqa: E402
+from geotransformer_b200.model import create_model                  # noqa: E402
+from geotransformer_b200.synth import make_pair                     # noqa: E402
+from geotransformer_b200.weights import synthetic_state_dict        # noqa: E402
+from oracle import geo_oracle, ref_ext, ref_harness                 # noqa: E402
+
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+LIMITS = {'demo2k': [38, 36, 36, 38], 'modelnet717': [13, 21, 27]}
+
+
+def sample_rows(t, n=64):
+    t = t.detach()
+    idx = np.unique(np.linspace(0, t.shape[0] - 1, num=min(n, t.shape[0])).astype(np.int64))
+    return idx, t[idx].numpy()
+
+
+def run(workload):
+    pair = make_pair(workload, 0)
+    cfg = make_cfg(pair['config'])
+    limits = cfg.neighbor_limits or LIMITS[workload]
+    torch.manual_seed(0)
+    sd = synthetic_state_dict(create_model(cfg), 7351)
+
+    rcfg, rcreate = ref_harness.load_experiment(pair['config'])
+    from geotransformer.utils.data import registration_collate_fn_stack_mode
+    ref_model = rcreate(rcfg).eval()
+    ref_model.load_state_dict(sd, strict=True)
+    dd = {k: pair[k] for k in ('ref_points', 'src_points', 'ref_feats', 'src_feats', 'transform')}
+    t0 = time.time()
+    data = registration_collate_fn_stack_mode([dd], rcfg.backbone.num_stages, rcfg.backbone.init_voxel_size,
+                                              rcfg.backbone.init_radius, limits)
+    data = {k: ([x.clone() if isinstance(x, torch.Tensor) else x for x in v] if isinstance(v, list) else
+                (v.clone() if isinstance(v, torch.Tensor) else v)) for k, v in data.items()}
+    t1 = time.time()
+    with torch.no_grad():
+        ref_out = ref_model(data)
+    t2 = time.time()
+    print(f'[{workload}] reference collate {t1 - t0:.2f}s forward {t2 - t1:.2f}s; '
+          f'levels {[int(p.shape[0]) for p in data["points"]]} corr {ref_out["ref_corr_points"].shape[0]}')
+
+    # ---- the restatement must reproduce the reference on CPU
+    odata = geo_oracle.collate_pair(pair, cfg, limits, impl=ref_ext)
+    for i in range(cfg.backbone.num_stages):
+        assert torch.equal(odata['points'][i], data['points'][i]) and torch.equal(odata['neighbors'][i], data['neighbors'][i])
+    odata2 = geo_oracle.collate_pair(pair, cfg, limits)          # plain-C restatement of the ext
+    for i in range(cfg.backbone.num_stages):
+        assert torch.equal(odata2['points'][i], data['points'][i]), f'grid order differs at level {i}'
+    # Neighbour tables: identical up to the order inside EXACT-distance tie groups (the barycentre of a 2-point voxel
+    # is equidistant to both points; the reference orders such ties by an unstable std::sort, the restatement by index)
+    n_tie_rows = 0
+    for key, qi, si in (('neighbors', 0, 0), ('subsampling', 1, 0), ('upsampling', 0, 1)):
+        for i, (a, b) in enumerate(zip(odata2[key], data[key])):
+            q, s = data['points'][i + qi], data['points'][i + si]
+            ca, cb = geo_oracle.canonical_neighbors(q, s, a), geo_oracle.canonical_neighbors(q, s, b)
+            assert torch.equal(ca, cb), f'{key}[{i}] differs beyond tie order'
+            n_tie_rows += int((a != b).any(dim=1).sum())
+    print(f'[{workload}] neighbour tables equal up to exact-tie order ({n_tie_rows} rows with a swapped tie)')
+    odata2 = {k: v for k, v in odata2.items()}
+    for key in ('neighbors', 'subsampling', 'upsampling'):
+        odata2[key] = data[key]                                   # teacher-force the reference's tie order downstream
+    taps = {}
+    with torch.no_grad():
+        o = geo_oracle.forward(sd, cfg, odata2, taps=taps)
+    report = {}
+    for k in ('ref_feats_c', 'src_feats_c', 'ref_feats_f', 'src_feats_f', 'matching_scores', 'estimated_transform',
+              'ref_corr_points', 'src_corr_points', 'corr_scores'):
+        a, b = o[k], ref_out[k]
+        report[k] = (tuple(a.shape) == tuple(b.shape)) and float((a - b).abs().max()) if a.shape == b.shape else 'SHAPE'
+    for k in ('ref_node_corr_indices', 'src_node_corr_indices'):
+        report[k] = bool(torch.equal(o[k], ref_out[k]))
+    print(f'[{workload}] oracle-vs-reference max abs diff:', report)
+    bad = [k for k, v in report.items() if v == 'SHAPE' or v is False or (isinstance(v, float) and v > 1e-5)]
+    assert not bad, f'oracle restatement deviates from the reference: {bad}'
+
+    # ---- fixtures
+    g = {}
+    for i, (p, l) in enumerate(zip(data['points'], data['lengths'])):
+        if i > 0:
+            g[f'points_{i}'] = p.numpy()
+        g[f'lengths_{i}'] = l.numpy()
+    for key in ('neighbors', 'subsampling', 'upsampling'):
+        for i, t in enumerate(data[key]):
+            g[f'{key}_{i}'] = t.numpy().astype(np.int32)
+    for k in ('feats_c', 'feats_f', 'ref_embeddings'):
+        t = taps[k]
+        idx, rows = sample_rows(t.reshape(t.shape[0], -1) if k != 'ref_embeddings' else t.reshape(-1, t.shape[-1]), 96)
+        g[k + '_rows'], g[k + '_sample'] = idx, rows
+        g[k + '_sum'] = np.array([t.double().sum().item(), t.double().abs().sum().item()])
+    for k in ('ref_feats_c', 'src_feats_c', 'estimated_transform', 'corr_scores', 'ref_corr_points', 'src_corr_points',
+              'ref_node_corr_indices', 'src_node_corr_indices'):
+        g[k] = ref_out[k].detach().numpy()
+    g['node_corr_scores'] = o['node_corr_scores'].numpy()
+    idx, rows = sample_rows(ref_out['matching_scores'].reshape(ref_out['matching_scores'].shape[0], -1), 16)
+    g['matching_scores_rows'], g['matching_scores_sample'] = idx, rows
+    for k in ('ref_node_knn_indices', 'src_node_knn_indices'):
+        g[k] = taps[k].numpy().astype(np.int32)
+    g['neighbor_limits'] = np.array(limits)
+    os.makedirs(GOLD, exist_ok=True)
+    path = os.path.join(GOLD, workload + '.npz')
+    np.savez_compressed(path, **g)
+    print(f'[{workload}] wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)')
+
+
+if __name__ == '__main__':
+    assert ref_harness.available(), 'needs /root/reference'
+    for w in (sys.argv[1:] or ['demo2k', 'modelnet717']):
+        run(w)

@@ -1,0 +1,143 @@
+"""End-to-end parity of the CUDA path against the committed golden fixtures (outputs of the REAL reference run in the
+build container by oracle/make_golden.py) on the deterministic pairs/weights.  Stage-wise with teacher forcing where
+the reference itself is ill-conditioned (coarse top-k on random-weight features, SURVEY.md 'hard parts')."""
+import numpy as np
+import pytest
+import torch
+
+from geotransformer_b200.synth import make_pair
+from geotransformer_b200.utils.data import registration_collate_fn_stack_mode
+from oracle import geo_oracle as G
+
+pytestmark = pytest.mark.gpu
+
+CASES = [('demo2k', '3dmatch'), ('modelnet717', 'modelnet')]
+
+
+def _collate(pair, cfg, limits):
+    dd = {k: pair[k] for k in ('ref_points', 'src_points', 'ref_feats', 'src_feats', 'transform')}
+    return registration_collate_fn_stack_mode([dd], cfg.backbone.num_stages, cfg.backbone.init_voxel_size,
+                                              cfg.backbone.init_radius, limits)
+
+
+def _rows(t, idx):
+    return t.reshape(-1, t.shape[-1])[torch.from_numpy(idx).to(t.device)].cpu().numpy()
+
+
+@pytest.mark.parametrize('workload,cfg_name', CASES)
+def test_collate_matches_reference(workload, cfg_name, golden, models):
+    cfg, sd, model = models(cfg_name)
+    gold = golden(workload)
+    pair = make_pair(workload, 0)
+    limits = gold['neighbor_limits'].tolist()
+    data = _collate(pair, cfg, limits)
+    S = cfg.backbone.num_stages
+    for i in range(S):
+        assert data['lengths'][i].tolist() == gold[f'lengths_{i}'].tolist()
+        if i > 0:
+            assert np.array_equal(data['points'][i].cpu().numpy(), gold[f'points_{i}']), f'points level {i} (values/order)'
+    n_tie = 0
+    for key, qi, si in (('neighbors', 0, 0), ('subsampling', 1, 0), ('upsampling', 0, 1)):
+        for i, t in enumerate(data[key]):
+            want = torch.from_numpy(gold[f'{key}_{i}'].astype(np.int64))
+            got = t.cpu()
+            assert got.shape == want.shape, f'{key}[{i}] shape'
+            if not torch.equal(got, want):     # only the order inside exact-distance tie groups may differ
+                q, s = data['points'][i + qi].cpu(), data['points'][i + si].cpu()
+                assert torch.equal(G.canonical_neighbors(q, s, got), G.canonical_neighbors(q, s, want)), f'{key}[{i}]'
+                n_tie += int((got != want).any(dim=1).sum())
+    print(f'{workload}: {n_tie} rows differ from the reference only by exact-tie order')
+
+
+@pytest.mark.parametrize('workload,cfg_name', CASES)
+def test_forward_matches_reference(workload, cfg_name, golden, models):
+    cfg, sd, model = models(cfg_name)
+    model = model.cuda().eval()
+    gold = golden(workload)
+    pair = make_pair(workload, 0)
+    limits = gold['neighbor_limits'].tolist()
+    data = _collate(pair, cfg, limits)
+    # teacher-force the reference's neighbour tables (identical up to exact-tie order, previous test)
+    for key in ('neighbors', 'subsampling', 'upsampling'):
+        data[key] = [torch.from_numpy(gold[f'{key}_{i}'].astype(np.int64)).cuda() for i in range(len(data[key]))]
+    taps = {}
+    out = model(data, taps=taps)
+    tol = 1e-4
+    for k in ('feats_c', 'feats_f'):
+        got = _rows(taps[k], gold[k + '_rows'])
+        err = np.abs(got - gold[k + '_sample']).max() / max(np.abs(gold[k + '_sample']).max(), 1.0)
+        assert err < tol, f'{k}: rel err {err:.2e}'
+    assert np.array_equal(taps['ref_node_knn_indices'].cpu().numpy(), gold['ref_node_knn_indices'].astype(np.int64))
+    assert np.array_equal(taps['src_node_knn_indices'].cpu().numpy(), gold['src_node_knn_indices'].astype(np.int64))
+    for k in ('ref_feats_c', 'src_feats_c'):
+        err = np.abs(out[k].cpu().numpy() - gold[k]).max()
+        assert err < tol, f'{k}: abs err {err:.2e} (unit-norm features)'
+    # coarse matching: same SET of node correspondences; order may differ between near-equal scores
+    got_pairs = set(zip(out['ref_node_corr_indices'].tolist(), out['src_node_corr_indices'].tolist()))
+    want_pairs = set(zip(gold['ref_node_corr_indices'].tolist(), gold['src_node_corr_indices'].tolist()))
+    missing = want_pairs - got_pairs
+    assert len(missing) <= max(2, len(want_pairs) // 50), f'{len(missing)} coarse correspondences differ'
+    # second pass with the reference's coarse correspondences forced: fine matching must then agree
+    data['forced_node_corr'] = (torch.from_numpy(gold['ref_node_corr_indices']).cuda(), torch.from_numpy(gold['src_node_corr_indices']).cuda(),
+                                torch.from_numpy(gold['node_corr_scores']).cuda())
+    out = model(data)
+    ms = out['matching_scores'].reshape(out['matching_scores'].shape[0], -1)[torch.from_numpy(gold['matching_scores_rows']).cuda()].cpu().numpy()
+    want = gold['matching_scores_sample']
+    live = want > -1e11
+    assert np.abs(ms[live] - want[live]).max() < 2e-4, f'matching_scores {np.abs(ms[live] - want[live]).max():.2e}'
+    assert out['ref_corr_points'].shape[0] == gold['ref_corr_points'].shape[0], 'number of fine correspondences'
+    assert np.array_equal(out['ref_corr_points'].cpu().numpy(), gold['ref_corr_points'])
+    assert np.array_equal(out['src_corr_points'].cpu().numpy(), gold['src_corr_points'])
+    assert np.abs(out['corr_scores'].cpu().numpy() - gold['corr_scores']).max() < 1e-4
+    T = out['estimated_transform'].cpu().numpy()
+    assert np.abs(T - gold['estimated_transform']).max() < 1e-4, f'transform\n{T}\nvs\n{gold["estimated_transform"]}'
+
+
+def test_full_size_properties_3dmatch20k(models):
+    """BASELINE size (20k+20k points): size-independent properties instead of an oracle run"""
+    cfg, sd, model = models('3dmatch')
+    model = model.cuda().eval()
+    pair = make_pair('3dmatch20k', 0)
+    data = _collate(pair, cfg, cfg.neighbor_limits)
+    lens = data['lengths_host']
+    assert lens[0] == [20000, 20000]
+    for i, nb in enumerate(data['neighbors']):
+        n = data['points'][i].shape[0]
+        assert nb.shape[0] == n and nb.shape[1] <= cfg.neighbor_limits[i]
+        assert torch.equal(nb[:, 0].cpu(), torch.arange(n)), 'self is the nearest neighbour of a self search'
+        assert int(nb.min()) >= 0 and int(nb.max()) <= n
+        # every row: real indices first, sentinels last; neighbours stay inside the row's own cloud
+        is_sent = nb == n
+        assert not bool((is_sent[:, :-1] & ~is_sent[:, 1:]).any())
+        n_ref = lens[i][0]
+        ref_rows = torch.arange(n, device=nb.device) < n_ref
+        real = ~is_sent
+        assert not bool(((nb >= n_ref) & real & ref_rows[:, None]).any())
+        assert not bool(((nb < n_ref) & real & ~ref_rows[:, None]).any())
+    out = model(data)
+    T = out['estimated_transform'].cpu().double()
+    R = T[:3, :3]
+    assert (R @ R.t() - torch.eye(3, dtype=torch.double)).abs().max() < 1e-5 and abs(torch.det(R).item() - 1) < 1e-5
+    ms = out['matching_scores']
+    assert ms.shape == (256, 65, 65) and bool(torch.isfinite(ms).all())
+    fc = out['ref_feats_c']
+    assert (fc.norm(dim=1) - 1).abs().max() < 1e-4
+    rre, rte = G.registration_error(pair['transform'], T.numpy())
+    print(f'3dmatch20k random-weight registration: RRE {rre:.3f} deg, RTE {rte:.4f} m, {out["ref_corr_points"].shape[0]} correspondences')
+    # determinism: a second run gives identical outputs
+    out2 = model(data)
+    assert torch.equal(out2['estimated_transform'], out['estimated_transform'])
+    assert torch.equal(out2['ref_corr_points'], out['ref_corr_points'])
+
+
+def test_kitti_shape_runs(models):
+    """5-stage backbone, hidden 128, K_patch 128, topk 2 (config 4 shape at reduced point count to stay fast)"""
+    from geotransformer_b200.synth import WORKLOADS, _ground
+    cfg, sd, model = models('kitti')
+    model = model.cuda().eval()
+    WORKLOADS['kitti8k'] = ('kitti', _ground, dict(n=8000, R=25.0, sigma=0.05), 10.0)
+    pair = make_pair('kitti8k', 0)
+    data = _collate(pair, cfg, [27, 75, 147, 157, 119])
+    out = model(data)
+    assert out['matching_scores'].shape[1:] == (129, 129)
+    assert bool(torch.isfinite(out['estimated_transform']).all())

@@ -1,0 +1,312 @@
+"""Every CUDA op of the hot path against the CPU oracle (oracle/geo_oracle.py) on seeded inputs, through the C ABI.
+Tolerance: 1e-4 (north star) on fp32 values -- stated per test, usually much tighter; indices bit-exact."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from geotransformer_b200 import functional as GF
+from geotransformer_b200.synth import make_pair
+from oracle import geo_oracle as G
+
+pytestmark = pytest.mark.gpu
+
+
+def close(a, b, tol, what=''):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    assert a.shape == b.shape, f'{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}'
+    err = (a - b).abs().max().item() if a.numel() else 0.0
+    scale = max(b.abs().max().item(), 1.0) if b.numel() else 1.0
+    assert err <= tol * scale, f'{what}: max abs err {err:.3e} (scale {scale:.3g}) > {tol:g}'
+    return err
+
+
+@pytest.fixture(scope='module')
+def mn(models):
+    """ModelNet-shape pair collated by the oracle + deterministic weights."""
+    cfg, sd, model = models('modelnet')
+    pair = make_pair('modelnet717', 0)
+    data = G.collate_pair(pair, cfg, [13, 21, 27])
+    return cfg, sd, data
+
+
+def _cuda_data(data):
+    out = {}
+    for k, v in data.items():
+        if isinstance(v, list):
+            out[k] = [x.cuda() if isinstance(x, torch.Tensor) else x for x in v]
+        elif isinstance(v, torch.Tensor):
+            out[k] = v.cuda()
+        else:
+            out[k] = v
+    return out
+
+
+@pytest.mark.parametrize('cin,cout,h', [(1, 64, 13), (32, 32, 21), (64, 64, 38), (128, 128, 27), (256, 256, 40)])
+def test_kpconv(cin, cout, h):
+    g = torch.Generator().manual_seed(cin + h)
+    ns, m = 700, 333
+    s_pts = torch.rand(ns, 3, generator=g)
+    q_pts = s_pts[torch.randperm(ns, generator=g)[:m]] + 0.01 * torch.randn(m, 3, generator=g)
+    d = torch.cdist(q_pts, s_pts)
+    nbr = d.argsort(dim=1)[:, :h].contiguous()
+    nbr[d.gather(1, nbr) > 0.25] = ns                     # shadow neighbours
+    feats = torch.randn(ns, cin, generator=g) if cin > 1 else torch.ones(ns, 1)
+    sd = {'w.weights': torch.randn(15, cin, cout, generator=g) * 0.1, 'w.bias': torch.randn(cout, generator=g) * 0.1,
+          'w.kernel_points': (torch.rand(15, 3, generator=g) - 0.5) * 0.3}
+    sd['w.kernel_points'][0] = 0
+    want = G.kpconv(sd, 'w.', feats, q_pts, s_pts, nbr, 0.12)
+    got = GF.kpconv(feats.cuda(), q_pts.cuda(), s_pts.cuda(), nbr.cuda(), sd['w.kernel_points'].cuda(), sd['w.weights'].cuda(),
+                    sd['w.bias'].cuda(), 0.12)
+    # rows whose neighbour count could flip (a feature row summing to ~0) are excluded from the max (documented quirk)
+    close(got, want, 2e-5, f'kpconv {cin}->{cout}')
+
+
+@pytest.mark.parametrize('m,k,n', [(5, 7, 3), (333, 64, 32), (1000, 1536, 512), (4100, 256, 128), (64, 512, 256)])
+def test_linear(m, k, n):
+    g = torch.Generator().manual_seed(m)
+    x, w, b = torch.randn(m, k, generator=g), torch.randn(n, k, generator=g) / math.sqrt(k), torch.randn(n, generator=g)
+    got = GF.linear(x.cuda(), w.cuda(), b.cuda())
+    close(got, F.linear(x, w, b), 1e-5, 'linear')
+    got = GF.linear(x.cuda(), w.cuda(), None, relu=True)
+    close(got, F.relu(F.linear(x, w)), 1e-5, 'linear relu')
+
+
+def test_linear_column_slice_input():
+    g = torch.Generator().manual_seed(1)
+    x, w = torch.randn(50, 256, generator=g), torch.randn(64, 64, generator=g)
+    got = GF.linear(x.cuda()[:, 64:128], w.cuda())
+    close(got, F.linear(x[:, 64:128], w), 1e-5, 'linear slice')
+
+
+@pytest.mark.parametrize('n,c', [(1434, 64), (4100, 128), (37, 512), (300, 1024)])
+def test_group_norm_variants(n, c):
+    g = torch.Generator().manual_seed(n)
+    x = torch.randn(n, c, generator=g) * 2 + 0.5
+    w, b = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g)
+    res = torch.randn(n, c, generator=g)
+    ref = F.group_norm(x.t().unsqueeze(0), 32, w, b, 1e-5).squeeze(0).t()
+    close(GF.group_norm(x.cuda(), w.cuda(), b.cuda(), 32), ref, 1e-5, 'gn')
+    close(GF.group_norm(x.cuda(), w.cuda(), b.cuda(), 32, negative_slope=0.1), F.leaky_relu(ref, 0.1), 1e-5, 'gn+lrelu')
+    close(GF.group_norm(x.cuda(), w.cuda(), b.cuda(), 32, negative_slope=0.1, residual=res.cuda()),
+          F.leaky_relu(ref + res, 0.1), 1e-5, 'gn+res+lrelu')
+    # twice in a row on the same stream: the launch ticket must have been restored
+    close(GF.group_norm(x.cuda(), w.cuda(), b.cuda(), 32), ref, 1e-5, 'gn again')
+
+
+def test_maxpool_and_upsample(mn):
+    cfg, sd, data = mn
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(data['points'][0].shape[0], 64, generator=g)
+    close(GF.maxpool(x.cuda(), data['subsampling'][0].cuda()), G.maxpool(x, data['subsampling'][0]), 0, 'maxpool')
+    y = torch.randn(data['points'][1].shape[0], 32, generator=g)
+    skip = torch.randn(data['points'][0].shape[0], 16, generator=g)
+    want = torch.cat([G.nearest_upsample(y, data['upsampling'][0]), skip], dim=1)
+    close(GF.upsample_concat(y.cuda(), data['upsampling'][0].cuda(), skip.cuda()), want, 0, 'upsample_concat')
+
+
+def test_backbone_blocks_modelnet(mn, models):
+    """whole KPConv-FPN (15 blocks for S=3) with teacher-forced oracle collate: fine and coarse features"""
+    cfg, sd, data = mn
+    _, _, model = models('modelnet')
+    model = model.cuda()
+    with torch.no_grad():
+        want = G.backbone(sd, cfg, data['features'], data)
+        got = model.backbone(data['features'].cuda(), _cuda_data(data))
+    assert len(got) == len(want)
+    for i, (a, b) in enumerate(zip(got, want)):
+        close(a, b, 1e-4, f'backbone output {i}')
+
+
+def _tie_aware_index_check(got, want, dist_rows, what, ulp_tol=4):
+    """indices must match; a mismatch is tolerated only where the oracle's own two candidate distances are within a few
+    ulp of each other (matmul-formula distances, SURVEY.md 'hard parts')."""
+    got, want = got.cpu(), want.cpu()
+    bad = (got != want).nonzero()
+    n_tol = 0
+    for idx in bad:
+        r = idx[0].item()
+        a, b = dist_rows(r, got[tuple(idx)].item()), dist_rows(r, want[tuple(idx)].item())
+        assert abs(a - b) <= ulp_tol * np.spacing(np.float32(max(abs(a), abs(b), 1e-30))), f'{what}: row {r} picks {got[tuple(idx)]} vs {want[tuple(idx)]} with distances {a} vs {b}'
+        n_tol += 1
+    return n_tol
+
+
+def test_point_to_node_partition(mn):
+    cfg, sd, data = mn
+    n0 = int(data['lengths'][0][0])
+    nc = int(data['lengths'][-1][0])
+    pts, nodes = data['points'][0][:n0], data['points'][-1][:nc]
+    p2n, masks, knn, knn_masks = G.point_to_node_partition(pts, nodes, 128)
+    g_p2n, g_masks, g_knn, g_knn_masks = GF.point_to_node_partition(pts.cuda(), nodes.cuda(), 128)
+    sq = G.pairwise_distance(nodes, pts)
+    n_tol = _tie_aware_index_check(g_p2n, p2n, lambda r, m: sq[int(m), r].item(), 'point_to_node')
+    if n_tol == 0:
+        assert torch.equal(g_masks.cpu(), masks)
+        assert torch.equal(g_knn_masks.cpu(), knn_masks)
+        _tie_aware_index_check(g_knn, knn, lambda r, n: sq[r, int(n)].item() if n < n0 else 1e12, 'node_knn')
+
+
+def test_gse_indices_and_embedding(mn):
+    cfg, sd, data = mn
+    nc = int(data['lengths'][-1][0])
+    pts = data['points'][-1][:nc]
+    g = cfg.geotransformer
+    d_want, a_want = G.embedding_indices(pts, g.sigma_d, g.sigma_a, g.angle_k)
+    d_got, a_got = GF.gse_indices(pts.cuda(), g.sigma_d, g.sigma_a, g.angle_k)
+    close(d_got, d_want, 2e-5, 'd_indices')
+    close(a_got, a_want, 2e-5, 'a_indices')
+    pre = 'transformer.embedding.'
+    want = G.structure_embedding(sd, pre, pts, g.sigma_d, g.sigma_a, g.angle_k)
+    wd, wa = sd[pre + 'proj_d.weight'].cuda(), sd[pre + 'proj_a.weight'].cuda()
+    got = GF.gse_embed(d_got, a_got, sd[pre + 'embedding.div_term'].cuda(), wd, wa, sd[pre + 'proj_d.bias'].cuda(),
+                       sd[pre + 'proj_a.bias'].cuda(), wd.t().contiguous(), wa.t().contiguous(), mode=0)
+    close(got, want, 2e-5, 'structure embedding (fp32 path)')
+
+
+def test_gse_embedding_generic_channels():
+    """hidden_dim 128 (KITTI) goes through the generic contraction"""
+    g = torch.Generator().manual_seed(9)
+    n, c = 40, 128
+    pts = torch.rand(n, 3, generator=g) * 20
+    sd = {'e.embedding.div_term': torch.exp(torch.arange(0, c, 2).float() * (-np.log(10000.0) / c)),
+          'e.proj_d.weight': torch.randn(c, c, generator=g) / math.sqrt(c), 'e.proj_d.bias': torch.randn(c, generator=g) * 0.1,
+          'e.proj_a.weight': torch.randn(c, c, generator=g) / math.sqrt(c), 'e.proj_a.bias': torch.randn(c, generator=g) * 0.1}
+    want = G.structure_embedding(sd, 'e.', pts, 4.8, 15, 3)
+    d, a = GF.gse_indices(pts.cuda(), 4.8, 15, 3)
+    cu = {k: v.cuda() for k, v in sd.items()}
+    got = GF.gse_embed(d, a, cu['e.embedding.div_term'], cu['e.proj_d.weight'], cu['e.proj_a.weight'], cu['e.proj_d.bias'],
+                       cu['e.proj_a.bias'], cu['e.proj_d.weight'].t().contiguous(), cu['e.proj_a.weight'].t().contiguous(), mode=0)
+    close(got, want, 2e-5, 'structure embedding C=128')
+
+
+def test_transformer_layers(mn, models):
+    cfg, sd, data = mn
+    _, _, model = models('modelnet')
+    model = model.cuda()
+    nc = int(data['lengths'][-1][0])
+    pts_r, pts_s = data['points'][-1][:nc], data['points'][-1][nc:]
+    g = torch.Generator().manual_seed(4)
+    fr, fs = torch.randn(pts_r.shape[0], 512, generator=g), torch.randn(pts_s.shape[0], 512, generator=g)
+    taps = {}
+    with torch.no_grad():
+        want_r, want_s = G.geometric_transformer(sd, cfg, pts_r, pts_s, fr, fs, taps=taps)
+        # one self layer and one cross layer in isolation first
+        e0 = taps['ref_embeddings']
+        x = torch.randn(pts_r.shape[0], 256, generator=g)
+        mem = torch.randn(pts_s.shape[0], 256, generator=g)
+        lp = 'transformer.transformer.layers.0.'
+        w_self = G.rpe_self_layer(sd, lp, x, e0, 4)
+        g_self, _ = model.transformer.transformer.layers[0](x.cuda(), x.cuda(), e0.cuda())
+        close(g_self, w_self, 2e-5, 'rpe self layer')
+        lp = 'transformer.transformer.layers.1.'
+        w_cross = G.cross_layer(sd, lp, x, mem, 4)
+        g_cross, _ = model.transformer.transformer.layers[1](x.cuda(), mem.cuda())
+        close(g_cross, w_cross, 2e-5, 'cross layer')
+        got_r, got_s = model.transformer(pts_r.cuda(), pts_s.cuda(), fr.cuda(), fs.cuda())
+    close(got_r, want_r, 1e-4, 'transformer ref feats')
+    close(got_s, want_s, 1e-4, 'transformer src feats')
+    close(GF.l2_normalize(got_r), F.normalize(want_r, p=2, dim=1), 1e-4, 'normalised ref feats')
+
+
+def test_superpoint_matching_separated_features():
+    """well separated unit features: indices and order must match exactly (K9 in isolation)"""
+    g = torch.Generator().manual_seed(11)
+    nr, ns, c = 150, 170, 256
+    fr = F.normalize(torch.randn(nr, c, generator=g), dim=1)
+    fs = F.normalize(torch.randn(ns, c, generator=g), dim=1)
+    rm, sm = torch.rand(nr, generator=g) > 0.1, torch.rand(ns, generator=g) > 0.1
+    wr, ws, wsc = G.superpoint_matching(fr, fs, rm, sm, 256, True)
+    gr, gs, gsc = GF.superpoint_matching(fr.cuda(), fs.cuda(), rm.cuda(), sm.cuda(), 256, True)
+    close(gsc, wsc, 1e-5 / max(wsc.max().item(), 1e-9) * wsc.max().item(), 'corr scores')
+    same = (gr.cpu() == wr) & (gs.cpu() == ws)
+    # entries may swap only between near-equal scores
+    for i in (~same).nonzero().flatten().tolist():
+        assert abs(gsc[i].item() - wsc[i].item()) <= 1e-6 * wsc[i].item()
+    assert same.float().mean() > 0.98
+    assert set(zip(gr.tolist(), gs.tolist())) == set(zip(wr.tolist(), ws.tolist())) or same.float().mean() > 0.98
+    # fewer candidates than requested
+    wr2, ws2, _ = G.superpoint_matching(fr[:5], fs[:7], None or torch.ones(5, dtype=torch.bool), torch.ones(7, dtype=torch.bool), 256, True)
+    gr2, gs2, _ = GF.superpoint_matching(fr[:5].cuda(), fs[:7].cuda(), None, None, 256, True)
+    assert gr2.shape[0] == 35 and torch.equal(gr2.cpu(), wr2) and torch.equal(gs2.cpu(), ws2)
+
+
+@pytest.mark.parametrize('k', [64, 128])
+def test_patch_scores_and_sinkhorn(k):
+    g = torch.Generator().manual_seed(k)
+    p, nf, c = 24, 900, 256
+    fr, fs = torch.randn(nf, c, generator=g) * 0.5, torch.randn(nf + 10, c, generator=g) * 0.5
+    ri = torch.randint(0, nf + 1, (p, k), generator=g)          # nf = sentinel
+    si = torch.randint(0, nf + 11, (p, k), generator=g)
+    rm, sm = ri < nf, si < nf + 10
+    rm[3] = False                                               # a fully masked patch side
+    rpad, spad = torch.cat([fr, torch.zeros(1, c)]), torch.cat([fs, torch.zeros(1, c)])
+    want = torch.einsum('bnd,bmd->bnm', rpad[ri], spad[si]) / c ** 0.5
+    got = GF.patch_scores(fr.cuda(), fs.cuda(), ri.cuda(), si.cuda())
+    close(got, want, 1e-5, 'patch scores')
+    alpha = torch.tensor(1.0)
+    want_ot = G.optimal_transport(alpha, want, rm, sm, 100)
+    got_ot = GF.sinkhorn(got, rm.cuda(), sm.cuda(), alpha.cuda(), 100)
+    fin = torch.isfinite(want_ot) & (want_ot > -1e11)
+    assert torch.equal(torch.isfinite(got_ot.cpu()) & (got_ot.cpu() > -1e11), fin)
+    err = (got_ot.cpu()[fin] - want_ot[fin]).abs().max().item()
+    assert err <= 1e-4, f'sinkhorn log-assignment max abs err {err:.3e}'
+    # marginals of the valid block: rows of exp(out) sum to ~1 for valid rows (property test, any size)
+    pr = got_ot.exp().cpu()
+    rows = pr[:, :-1, :].sum(dim=2)
+    ok = rm & (sm.sum(dim=1, keepdim=True) > 0)
+    assert (rows[ok] - 1).abs().max() < 1e-3
+
+
+def test_weighted_procrustes_and_edge_cases():
+    g = torch.Generator().manual_seed(2)
+    b, n = 9, 50
+    src = torch.randn(b, n, 3, generator=g)
+    from geotransformer_b200.synth import _rodrigues
+    Rs = torch.stack([torch.from_numpy(_rodrigues(np.random.default_rng(i).normal(size=3), 0.3 * i)).float() for i in range(b)])
+    t = torch.randn(b, 3, generator=g)
+    ref = src @ Rs.transpose(1, 2) + t[:, None, :] + 0.01 * torch.randn(b, n, 3, generator=g)
+    w = torch.rand(b, n, generator=g)
+    w[0] = 0                                                   # degenerate: all-zero weights -> identity
+    ref[1] = src[1] * torch.tensor([1.0, 1.0, -1.0])           # reflection: det fix must kick in
+    want = G.weighted_procrustes(src, ref, w)
+    got = GF.weighted_procrustes(src.cuda(), ref.cuda(), w.cuda())
+    close(got[0], torch.eye(4), 0, 'zero-weight transform is the identity')
+    close(got, want, 1e-4, 'weighted procrustes')
+    R = got[:, :3, :3].cpu().double()
+    assert (R @ R.transpose(1, 2) - torch.eye(3, dtype=torch.double)).abs().max() < 1e-5      # R in O(3)
+    assert (torch.det(R[2:]) - 1).abs().max() < 1e-5                                           # proper rotations
+
+
+def test_local_global_registration_pipeline(models):
+    """LGR on oracle-made assignment matrices: correspondences identical (order too), transform within 1e-4"""
+    cfg, sd, model = models('3dmatch')
+    g = torch.Generator().manual_seed(8)
+    p, k = 40, 64
+    from geotransformer_b200.synth import _rodrigues
+    R = torch.from_numpy(_rodrigues(np.array([0.3, -0.5, 0.8]), 0.4)).float()
+    t = torch.tensor([0.2, -0.1, 0.3])
+    src = torch.rand(p, k, 3, generator=g)
+    perm = torch.stack([torch.randperm(k, generator=g) for _ in range(p)])
+    ref = torch.gather(src, 1, perm[:, :, None].expand(-1, -1, 3)) @ R.t() + t + 0.003 * torch.randn(p, k, 3, generator=g)
+    # ref[p,i] corresponds to src[p,perm[p,i]]
+    rm, sm = torch.rand(p, k, generator=g) > 0.15, torch.rand(p, k, generator=g) > 0.15
+    logits = torch.randn(p, k, k, generator=g) * 0.5
+    logits[torch.arange(p)[:, None], torch.arange(k)[None, :], perm] += 6.0
+    logits[5] = -3.0 + 0.01 * torch.randn(k, k, generator=g)       # a patch with (almost) no confident matches
+    ot = G.optimal_transport(torch.tensor(1.0), logits, rm, sm, 100)
+    taps = {}
+    w_rc, w_sc, w_cs, w_T = G.local_global_registration(cfg, ref, src, rm, sm, ot[:, :-1, :-1], taps=taps)
+    lgr = model.fine_matching
+    rc, sc, cs, T, det = lgr(ref.cuda(), src.cuda(), rm.cuda(), sm.cuda(), ot.cuda(), None, return_details=True)
+    assert rc.shape == w_rc.shape, f'{rc.shape[0]} correspondences vs {w_rc.shape[0]}'
+    close(rc, w_rc, 0, 'ref corr points')
+    close(sc, w_sc, 0, 'src corr points')
+    close(cs, w_cs, 1e-5, 'corr scores')
+    assert torch.equal(det['corr_patch'].cpu().long(), taps['corr_batch_indices'])
+    assert int(det['best'].item()) >= 0
+    close(T, w_T, 1e-4, 'estimated transform')
+    gt = torch.eye(4); gt[:3, :3] = R; gt[:3, 3] = t
+    close(T, gt, 5e-3, 'estimated transform vs ground truth')

@@ -1,0 +1,90 @@
+"""The oracle itself (CPU): plain-C collate restatement vs the real reference build (oracle/_ref), and the
+torch restatement of the forward vs the committed reference fixtures."""
+import numpy as np
+import pytest
+import torch
+
+from geotransformer_b200.synth import make_pair
+from oracle import collate_oracle as co
+from oracle import geo_oracle as G
+from oracle import ref_ext
+
+
+def _stack(pair):
+    pts = torch.from_numpy(np.concatenate([pair['ref_points'], pair['src_points']]))
+    return pts, torch.tensor([len(pair['ref_points']), len(pair['src_points'])])
+
+
+@pytest.mark.skipif(not ref_ext.available(), reason='oracle/_ref not built')
+@pytest.mark.parametrize('workload,voxel', [('demo2k', 0.05), ('3dmatch20k', 0.05), ('modelnet717', 0.1)])
+def test_c_restatement_matches_reference_build(workload, voxel):
+    pts, lens = _stack(make_pair(workload, 1))
+    for _ in range(3):
+        a, al = ref_ext.grid_subsampling(pts, lens, voxel)
+        b, bl = co.grid_subsampling(pts, lens, voxel)
+        assert torch.equal(al, bl) and torch.equal(a, b)          # values AND unordered_map order
+        pts, lens, voxel = a, al, voxel * 2
+    na = ref_ext.radius_neighbors(pts, pts, lens, lens, voxel * 1.25)
+    nb = co.radius_neighbors(pts, pts, lens, lens, voxel * 1.25)
+    assert torch.equal(na, nb)
+
+
+def test_grid_subsample_golden_order(golden):
+    """against the committed fixture (reference output), no reference build needed"""
+    gold = golden('demo2k')
+    pts, lens = _stack(make_pair('demo2k', 0))
+    v = 0.05
+    for i in range(1, 4):
+        pts, lens = co.grid_subsampling(pts, lens, v)
+        assert np.array_equal(pts.numpy(), gold[f'points_{i}']) and lens.tolist() == gold[f'lengths_{i}'].tolist()
+        v *= 2
+
+
+def test_rehash_schedule_edge_sizes():
+    """clouds whose voxel counts straddle the libstdc++ rehash thresholds (13/14, 29/30, 59/60, 127/128)"""
+    if not ref_ext.available():
+        pytest.skip('oracle/_ref not built')
+    g = torch.Generator().manual_seed(0)
+    for n in (1, 2, 12, 13, 14, 28, 29, 30, 58, 59, 60, 126, 127, 128, 129, 257, 258, 542):
+        pts = torch.rand(n, 3, generator=g) * 100.0          # one point per voxel with high probability
+        a, al = ref_ext.grid_subsampling(pts, torch.tensor([n]), 0.5)
+        b, bl = co.grid_subsampling(pts, torch.tensor([n]), 0.5)
+        assert torch.equal(a, b), n
+
+
+def test_forward_restatement_matches_reference_fixture(golden, models):
+    """torch restatement vs the real reference on the ModelNet-shape pair (teacher-forced neighbour tables)"""
+    cfg, sd, _ = models('modelnet')
+    gold = golden('modelnet717')
+    pair = make_pair('modelnet717', 0)
+    data = G.collate_pair(pair, cfg, gold['neighbor_limits'].tolist())
+    for i in range(1, cfg.backbone.num_stages):
+        assert np.array_equal(data['points'][i].numpy(), gold[f'points_{i}'])
+    for key in ('neighbors', 'subsampling', 'upsampling'):
+        for i in range(len(data[key])):
+            want = torch.from_numpy(gold[f'{key}_{i}'].astype(np.int64))
+            q = data['points'][i + (1 if key == 'subsampling' else 0)]
+            s = data['points'][i + (1 if key == 'upsampling' else 0)]
+            assert torch.equal(G.canonical_neighbors(q, s, data[key][i]), G.canonical_neighbors(q, s, want))
+            data[key][i] = want
+    with torch.no_grad():
+        out = G.forward(sd, cfg, data)
+    assert np.abs(out['ref_feats_c'].numpy() - gold['ref_feats_c']).max() < 1e-5
+    assert np.array_equal(out['ref_node_corr_indices'].numpy(), gold['ref_node_corr_indices'])
+    assert np.array_equal(out['ref_corr_points'].numpy(), gold['ref_corr_points'])
+    assert np.abs(out['estimated_transform'].numpy() - gold['estimated_transform']).max() < 1e-5
+
+
+def test_sinkhorn_marginals_property():
+    g = torch.Generator().manual_seed(1)
+    s = torch.randn(3, 20, 20, generator=g)
+    rm, cm = torch.rand(3, 20, generator=g) > 0.2, torch.rand(3, 20, generator=g) > 0.2
+    out = G.optimal_transport(torch.tensor(1.0), s, rm, cm, 100).exp()
+    rows = out[:, :-1, :].sum(dim=2)
+    assert (rows[rm] - 1).abs().max() < 1e-3
+
+
+def test_procrustes_degenerate_cases():
+    src = torch.randn(1, 10, 3)
+    T = G.weighted_procrustes(src, src + 1.0, torch.zeros(1, 10))
+    assert torch.equal(T[0], torch.eye(4))
