@@ -94,6 +94,13 @@ def make_inputs(workload, n_pairs, rank, world):
     return pairs
 
 
+def cpu_threads():
+    """Intra-op threads for the CPU reference path.  Measured on the B200 host (128 vCPU): the forward of one demo-size
+    pair takes 1.3 s with 1 thread, 0.1 s with 16, 0.5 s with 64 and 116 s with 128 (oversubscription on the thousands of
+    tiny ATen ops) -- so the baseline uses min(cores, 16), the fastest setting, and reports that number as `cores`."""
+    return max(1, min(os.cpu_count() or 1, 16))
+
+
 def cpu_reference_pairs_per_s(workload, n_pairs, threads):
     """The reference's CPU path: its own C++ collate ops (oracle/_ref, kind 'reference') when built, else the plain-C
     port; the model forward is the torch-CPU restatement (kind 'port').  Returns (pairs/s, seconds, description)."""
@@ -131,7 +138,7 @@ def main():
     if args.impl == 'reference':
         if rank != 0:
             return
-        threads = os.cpu_count() or 1
+        threads = cpu_threads()
         # bounded sample per step: 1 pair of the workload (several seconds to minutes of CPU work)
         steps = max(1, min(args.steps, 2))
         warm = min(args.warmup, 0)
@@ -263,7 +270,7 @@ def main():
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            threads = os.cpu_count() or 1
+            threads = cpu_threads()
             v, secs, desc = cpu_reference_pairs_per_s(args.workload, 1, threads)
             cpu = {'value': v, 'unit': 'pairs/s', 'cores': threads, 'kind': 'reference' if 'reference' in desc else 'port',
                    'sample': desc}

@@ -80,7 +80,8 @@ __global__ void __launch_bounds__(256) gse_indices_kernel(const float* __restric
             const float cy = __fsub_rn(__fmul_rn(rz[k], ax), __fmul_rn(rx[k], az));
             const float cz = __fsub_rn(__fmul_rn(rx[k], ay), __fmul_rn(ry[k], ax));
             const float sinv = sqrtf(sqnorm3g(cx, cy, cz));
-            const float cosv = __fadd_rn(__fadd_rn(__fmul_rn(rx[k], ax), __fmul_rn(ry[k], ay)), __fmul_rn(rz[k], az));
+            // accumulate from +0 like torch.sum: a sum of negative zeros (j == i) must give +0 so that atan2(0, 0) = 0, not pi
+            const float cosv = __fadd_rn(__fadd_rn(__fadd_rn(0.0f, __fmul_rn(rx[k], ax)), __fmul_rn(ry[k], ay)), __fmul_rn(rz[k], az));
             a_idx[((long long)i * N + j) * KA + k] = atan2f(sinv, cosv) * factor_a;
         }
     }
