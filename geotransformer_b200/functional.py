@@ -13,7 +13,7 @@ from . import _lib as L
 _f32, _i64, _u8, _i32 = torch.float32, torch.int64, torch.uint8, torch.int32
 
 # tensor-core mode of the structure-embedding contraction (see geob200_gse_embed): 0 fp32, 1 3xTF32, 2 1xTF32
-GSE_MODE = 0
+GSE_MODE = 1
 
 # Optional per-op CUDA-event timing on the launching stream (bench.py sets EVENTS = {} to collect
 # {op name: [(start_event, end_event), ...]}; None = off, zero overhead).
@@ -183,6 +183,8 @@ def gse_embed(d_indices, a_indices, div_term, wd, wa, bd, ba, wd_t, wa_t, mode=N
     n = d_indices.shape[0]
     c = wd.shape[0]
     mode = GSE_MODE if mode is None else mode
+    if c != 256:
+        mode = 0                     # the tcgen05 contraction is specialised for hidden_dim 256 (3DMatch / ModelNet)
     lib = L.lib()
     ws = L.workspace(lib.geob200_gse_embed_workspace_bytes(n, c), d_indices.device, 'gse')
     emb = torch.empty((n, n, c), dtype=_f32, device=d_indices.device)

@@ -166,6 +166,25 @@ def test_gse_indices_and_embedding(mn):
     close(got, want, 2e-5, 'structure embedding (fp32 path)')
 
 
+@pytest.mark.parametrize('n', [7, 100, 271])
+def test_gse_embedding_tensor_core_modes(n):
+    """tcgen05 contraction: 3xTF32 (default) must be fp32-accurate, 1xTF32 within TF32 rounding; vs the oracle"""
+    g = torch.Generator().manual_seed(n)
+    c = 256
+    pts = torch.rand(n, 3, generator=g) * 2.0
+    sd = {'e.embedding.div_term': torch.exp(torch.arange(0, c, 2).float() * (-np.log(10000.0) / c)),
+          'e.proj_d.weight': torch.randn(c, c, generator=g) / math.sqrt(c), 'e.proj_d.bias': torch.randn(c, generator=g) * 0.1,
+          'e.proj_a.weight': torch.randn(c, c, generator=g) / math.sqrt(c), 'e.proj_a.bias': torch.randn(c, generator=g) * 0.1}
+    want = G.structure_embedding(sd, 'e.', pts, 0.2, 15, 3)
+    d, a = GF.gse_indices(pts.cuda(), 0.2, 15, 3)
+    cu = {k: v.cuda() for k, v in sd.items()}
+    args = (d, a, cu['e.embedding.div_term'], cu['e.proj_d.weight'], cu['e.proj_a.weight'], cu['e.proj_d.bias'], cu['e.proj_a.bias'],
+            cu['e.proj_d.weight'].t().contiguous(), cu['e.proj_a.weight'].t().contiguous())
+    close(GF.gse_embed(*args, mode=1), want, 2e-5, 'structure embedding 3xTF32')
+    close(GF.gse_embed(*args, mode=2), want, 2e-3, 'structure embedding 1xTF32')
+    close(GF.gse_embed(*args, mode=0), want, 2e-5, 'structure embedding fp32')
+
+
 def test_gse_embedding_generic_channels():
     """hidden_dim 128 (KITTI) goes through the generic contraction"""
     g = torch.Generator().manual_seed(9)
