@@ -4,8 +4,8 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload 3dmatch20k]
 
 A step = one pass of the hot path (stack-mode collate -> KPConv-FPN -> geometric transformer -> superpoint matching ->
-Sinkhorn -> local-to-global registration) over one synthetic pair per rank (weak scaling: pair i of rank r is
-synth.make_pair(workload, r + i*W)).  Prints ONE JSON line (see the task contract):
+Sinkhorn -> local-to-global registration) over a batch of --streams synthetic pairs per rank, processed concurrently by
+geotransformer_b200.engine.RegistrationEngine (weak scaling: pair i of rank r is synth.make_pair(workload, r + i*W)).  Prints ONE JSON line (see the task contract):
   value     pairs/s with the raw pair already resident in HBM when the timed region starts
   e2e       pairs/s through the public API with HOST (pinned) inputs: H2D + collate + forward + D2H of the transform
   roofline  the dominant kernel (structure-embedding contraction), algorithmic FLOPs / CUDA-event time
@@ -37,6 +37,7 @@ def parse():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='3dmatch20k')
     ap.add_argument('--gse-mode', type=int, default=None)
+    ap.add_argument('--streams', type=int, default=2, help='pairs in flight per GPU (one CUDA stream + host thread each)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     return ap.parse_args()
 
@@ -178,36 +179,29 @@ def main():
     model.load_state_dict(synthetic_state_dict(model, 7351), strict=True)
     model = model.to(dev).eval()
 
-    W, K = args.warmup, args.steps
-    pairs = make_inputs(args.workload, W + K, rank, world)
+    from geotransformer_b200.engine import RegistrationEngine
+    W, K, S = args.warmup, args.steps, max(1, args.streams)
+    pairs = make_inputs(args.workload, (W + K) * S, rank, world)
     # host staging (pinned) and device-resident copies
     pinned = [{k: torch.from_numpy(v).pin_memory() for k, v in p.items()} for p in pairs]
     resident = [{k: v.to(dev) for k, v in p.items()} for p in pinned]
-    h2d_bytes = sum(v.numel() * v.element_size() for v in pinned[0].values())
-
-    def collate(d):
-        return registration_collate_fn_stack_mode([d], cfg.backbone.num_stages, cfg.backbone.init_voxel_size,
-                                                  cfg.backbone.init_radius, limits, device=dev)
-
-    def step_resident(i):
-        return model(collate(resident[i]))['estimated_transform']
-
-    def step_e2e(i, out_host):
-        out = model(collate(pinned[i]))
-        out_host.copy_(out['estimated_transform'], non_blocking=True)     # D2H of the step's result
-        return out
+    h2d_bytes = sum(v.numel() * v.element_size() for v in pinned[0].values()) * S
+    engine = RegistrationEngine(model, cfg, limits, num_streams=S, device=dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, n0, n):
+    def timed(source, n0, n, sink=None):
+        """n steps of S pairs each; CUDA events on the current stream, which the engine's streams fork from / join into"""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(n0, n0 + n):
-            fn(i)
+            res = engine.register(source[i * S:(i + 1) * S], start_event=e0 if i == n0 else None)
+            if sink is not None:
+                sink.extend(res)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -217,29 +211,28 @@ def main():
             ms = float(t.item())
         return ms
 
-    out_host = torch.empty((4, 4), dtype=torch.float32).pin_memory()
-    for i in range(W):
-        step_resident(i)
-        step_e2e(i, out_host)
+    timed(resident, 0, W)
+    timed(pinned, 0, W)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     lib = _lib.lib()
     l0 = lib.geob200_launch_count()
     GF.EVENTS = {}
-    ms_res = timed(step_resident, W, K)
+    ms_res = timed(resident, W, K)
     launches = (lib.geob200_launch_count() - l0)
     events = GF.EVENTS
     GF.EVENTS = None
     results = []
-    ms_e2e = timed(lambda i: results.append(step_e2e(i, out_host)), W, K)
+    ms_e2e = timed(pinned, W, K, sink=results)
     sampler.stop_flag = True
+    engine.close()
 
     # metric rows (RRE, RTE, nCorr, pair id) gathered with ONE collective
     rows = []
     for j, out in enumerate(results):
-        rre, rte = G.registration_error(pairs[W + j]['transform'], out['estimated_transform'].cpu().numpy())
-        rows.append([rre, rte, float(out['ref_corr_points'].shape[0]), float(rank + (W + j) * world)])
+        rre, rte = G.registration_error(pairs[W * S + j]['transform'], out['estimated_transform'].numpy())
+        rows.append([rre, rte, float(out['num_corr']), float(rank + (W * S + j) * world)])
     rows_t = torch.tensor(rows, dtype=torch.float32, device=dev)
     if world > 1:
         gathered = [torch.empty_like(rows_t) for _ in range(world)]
@@ -254,7 +247,7 @@ def main():
     C = cfg.geotransformer.hidden_dim
     gse = events.get('gse_embed', [])
     gse_ms = [s.elapsed_time(e) for s, e in gse]
-    n_c = [int(r['ref_points_c'].shape[0]) for r in results] + [int(r['src_points_c'].shape[0]) for r in results]
+    n_c = [r['num_superpoints'][0] for r in results] + [r['num_superpoints'][1] for r in results]
     mean_n2 = float(np.mean([n * n for n in n_c])) if n_c else 0.0
     flops = 2.0 * mean_n2 * 4 * C * C
     peak_tf, peak_hbm, peak_src = load_peaks()
@@ -264,7 +257,7 @@ def main():
     roofline = {'kernel': 'gse_embed (structure-embedding contraction)', 'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf,
                 'unit': 'TFLOP/s', 'frac': (achieved / peak_tf) if achieved else None, 'traffic': None,
                 'avg_ms_per_launch': avg_ms, 'launches_timed': len(gse_ms), 'flops_per_launch': flops,
-                'share_of_step': (sum(gse_ms) / ms_res) if gse_ms else None, 'mode': mode_name,
+                'share_of_gpu_time': (sum(gse_ms) / (ms_res * S)) if gse_ms else None, 'mode': mode_name,
                 'peak_source': f'{peak_src} bf16 dense (MEASURED_PEAKS.json); TF32 dense peak is half of it'}
 
     cpu = None
@@ -277,18 +270,18 @@ def main():
         except Exception as ex:   # the baseline must never take the bench line down
             cpu = {'value': None, 'unit': 'pairs/s', 'cores': os.cpu_count(), 'kind': 'port', 'sample': f'failed: {ex}'}
 
-    total_pairs = K * world
+    total_pairs = K * S * world
     line = {
         'metric': METRIC, 'value': total_pairs / (ms_res * 1e-3), 'unit': 'pairs/s', 'n_gpus': world, 'steps': K, 'warmup': W,
         'ms_per_step': ms_res / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic',
-        'config': {'workload': args.workload, 'pairs_per_step_per_gpu': 1, 'points_per_cloud': int(pairs[0]['ref_points'].shape[0]),
+        'config': {'workload': args.workload, 'pairs_per_step_per_gpu': S, 'streams': S, 'points_per_cloud': int(pairs[0]['ref_points'].shape[0]),
                    'superpoints_per_cloud': int(np.mean(n_c)) if n_c else None, 'sinkhorn_iterations': cfg.model.num_sinkhorn_iterations,
                    'parallelism': f'pairs sharded over {world} GPU(s), one all_gather of metric rows',
                    'l2': 'a different pair every step; per-pair working set (~0.5 GB incl. 2x75 MB embeddings) exceeds the 126 MB L2',
                    'weights': 'random init (synthetic_state_dict seed 7351)'},
         'e2e': {'value': total_pairs / (ms_e2e * 1e-3), 'unit': 'pairs/s', 'ms_per_step': ms_e2e / K,
-                'h2d_bytes_per_step': int(h2d_bytes), 'd2h_bytes_per_step': 64},
+                'h2d_bytes_per_step': int(h2d_bytes), 'd2h_bytes_per_step': 64 * S},
         'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu, 'clocks': sampler.summary(),
         'quality': {'median_rre_deg': float(rows_t[:, 0].median()), 'median_rte': float(rows_t[:, 1].median()),
                     'mean_correspondences': float(rows_t[:, 2].mean()), 'pairs': int(rows_t.shape[0])},

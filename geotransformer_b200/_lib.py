@@ -31,7 +31,8 @@ _sig('geob200_grid_subsample', c_int, P, I64, P, I64, F, P, P, P, SZ, P)
 _sig('geob200_radius_search_workspace_bytes', SZ, I64, I64, I64)
 _sig('geob200_radius_search', c_int, P, I64, P, I64, P, P, I64, F, I64, P, P, P, P, SZ, P)
 
-_sig('geob200_kpconv', c_int, P, P, P, P, I64, I64, I64, P, I64, P, P, I64, I64, F, P, P)
+_sig('geob200_kpconv_workspace_bytes', SZ, I64)
+_sig('geob200_kpconv', c_int, P, P, P, P, I64, I64, I64, P, I64, P, P, I64, I64, F, P, P, SZ, P)
 _sig('geob200_linear', c_int, P, I64, P, P, P, I64, I64, I64, I64, c_int, P)
 _sig('geob200_linear_batched', c_int, P, I64, I64, P, I64, I64, P, I64, P, I64, I64, I64, I64, I64, I64, c_int, P)
 _sig('geob200_group_norm_workspace_bytes', SZ, I64)
@@ -43,8 +44,8 @@ _sig('geob200_gather_rows', c_int, P, I64, I64, P, I64, P, P)
 _sig('geob200_gse_indices', c_int, P, I64, F, F, I64, P, P, P)
 _sig('geob200_gse_embed_workspace_bytes', SZ, I64, I64)
 _sig('geob200_gse_embed', c_int, P, P, I64, I64, P, P, P, P, P, P, P, P, c_int, P, SZ, P)
-_sig('geob200_attention', c_int, P, P, P, P, P, P, I64, I64, I64, I64, P, P)
-_sig('geob200_head_bias', c_int, P, P, I64, I64, I64, P, P)
+_sig('geob200_attention', c_int, P, I64, P, I64, P, I64, P, P, P, I64, I64, I64, I64, P, I64, P)
+_sig('geob200_head_bias', c_int, P, I64, P, I64, I64, I64, P, P)
 _sig('geob200_add_layernorm', c_int, P, P, P, P, I64, I64, F, P, P)
 _sig('geob200_l2_normalize', c_int, P, I64, I64, P, P)
 _sig('geob200_superpoint_matching_workspace_bytes', SZ, I64, I64)
@@ -98,8 +99,9 @@ _WS = {}
 
 
 def workspace(nbytes, device, tag='default'):
-    """Grow-only scratch buffer per (device, tag); ops on one stream reuse it serially."""
-    key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
+    """Grow-only scratch buffer per (device, current stream, tag): ops on one stream reuse it serially, concurrent streams
+    (RegistrationEngine runs several pairs at once) never share scratch."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), stream_ptr(), tag)
     buf = _WS.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)

@@ -14,65 +14,98 @@
 
 namespace geob200 {
 
-// R query rows per CTA.  C = channels (multiple of 32, <= 256 handled by 256 threads), H heads (divides 32).
-template <int R>
-__global__ void __launch_bounds__(256) attention_kernel(const float* __restrict__ q, const float* __restrict__ k,
-                                                        const float* __restrict__ v, const float* __restrict__ qp,
+// R = 2 query rows per CTA (key/value rows fetched once for both).  Keys are spread over LANES: lane <-> key m, so
+// every dot product over channels is a private register accumulation (no shuffles); q / qp are warp-broadcast
+// shared-memory reads.  Each lane handles KPT = 2 keys per pass to halve the shared-memory traffic per FMA.
+// q, k, v may be column slices of wider row-major buffers (row strides ldq, ldk, ldv in floats).
+// C multiple of 4 and <= 256 (one thread per channel in the P.V phase), H <= 8 heads.
+constexpr int ATT_R = 2;
+constexpr int ATT_KPT = 2;
+constexpr int ATT_MAXH = 8;
+
+__global__ void __launch_bounds__(256) attention_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk,
+                                                        const float* __restrict__ v, int ldv, const float* __restrict__ qp,
                                                         const float* __restrict__ qb, const float* __restrict__ E, int N, int M,
-                                                        int C, int H, float inv_scale_div, float* __restrict__ out) {
+                                                        int C, int H, float div, float* __restrict__ out, int ldo) {
     extern __shared__ float sm[];
-    float* q_s = sm;                       // [R][C]
-    float* qp_s = q_s + R * C;             // [R][H][C]
-    float* sc = qp_s + R * H * C;          // [R][H][M]
-    const int n0 = blockIdx.x * R;
+    float* q_s = sm;                            // [R][C]
+    float* qp_s = q_s + ATT_R * C;              // [R][H][C]
+    float* sc = qp_s + ATT_R * H * C;           // [R][H][M]
+    const int n0 = blockIdx.x * ATT_R;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int cpl = C / 32;                // contiguous channels per lane
-    const int lph = 32 / H;                // lanes per head
-    for (int t = threadIdx.x; t < R * C; t += blockDim.x) {
+    const int d = C / H;
+    for (int t = threadIdx.x; t < ATT_R * C; t += blockDim.x) {
         const int r = t / C, n = n0 + r;
-        q_s[t] = (n < N) ? q[(long long)n * C + (t % C)] : 0.f;
+        q_s[t] = (n < N) ? q[(long long)n * ldq + (t % C)] : 0.f;
     }
     if (qp != nullptr)
-        for (int t = threadIdx.x; t < R * H * C; t += blockDim.x) {
+        for (int t = threadIdx.x; t < ATT_R * H * C; t += blockDim.x) {
             const int r = t / (H * C), n = n0 + r;
             qp_s[t] = (n < N) ? qp[(long long)n * H * C + (t % (H * C))] : 0.f;
         }
     __syncthreads();
-    const int my_head = lane / lph;
-    for (int m = warp; m < M; m += 8) {
-        float kv[8];
-#pragma unroll 8
-        for (int u = 0; u < 8; ++u) kv[u] = (u < cpl) ? k[(long long)m * C + lane * cpl + u] : 0.f;
+    const bool has_e = (E != nullptr);
+    const int r1ok = (n0 + 1 < N) ? 1 : 0;
+    for (int mb = warp * 32 * ATT_KPT; mb < M; mb += 8 * 32 * ATT_KPT) {
+        int mk[ATT_KPT];
+        bool ok[ATT_KPT];
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int n = n0 + r;
-            float se = 0.f;
-#pragma unroll 8
-            for (int u = 0; u < 8; ++u)
-                if (u < cpl) se = fmaf(q_s[r * C + lane * cpl + u], kv[u], se);
-            for (int o = lph >> 1; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);   // per-head q.k
-            float tot = se;
-            if (E != nullptr && n < N) {
-                const float* erow = E + ((long long)n * M + m) * C + lane * cpl;
-                float ev[8];
-#pragma unroll 8
-                for (int u = 0; u < 8; ++u) ev[u] = (u < cpl) ? erow[u] : 0.f;
-                for (int h = 0; h < H; ++h) {
-                    float sp = 0.f;
-                    const float* w = qp_s + (r * H + h) * C + lane * cpl;
-#pragma unroll 8
-                    for (int u = 0; u < 8; ++u)
-                        if (u < cpl) sp = fmaf(w[u], ev[u], sp);
-                    sp = warp_sum(sp);
-                    if (h == my_head) tot += sp + qb[(long long)n * H + h];
+        for (int u = 0; u < ATT_KPT; ++u) { mk[u] = mb + u * 32 + lane; ok[u] = mk[u] < M; if (!ok[u]) mk[u] = M - 1; }
+        for (int h = 0; h < H; ++h) {
+            float aq[ATT_KPT][ATT_R], ae[ATT_KPT][ATT_R];
+#pragma unroll
+            for (int u = 0; u < ATT_KPT; ++u)
+#pragma unroll
+                for (int r = 0; r < ATT_R; ++r) { aq[u][r] = 0.f; ae[u][r] = 0.f; }
+            // q . k over this head's channels
+            for (int c = h * d; c < (h + 1) * d; c += 4) {
+                const float4 q0 = *reinterpret_cast<const float4*>(q_s + c);
+                const float4 q1 = *reinterpret_cast<const float4*>(q_s + C + c);
+#pragma unroll
+                for (int u = 0; u < ATT_KPT; ++u) {
+                    const float4 kv = *reinterpret_cast<const float4*>(k + (long long)mk[u] * ldk + c);
+                    aq[u][0] = fmaf(kv.x, q0.x, fmaf(kv.y, q0.y, fmaf(kv.z, q0.z, fmaf(kv.w, q0.w, aq[u][0]))));
+                    aq[u][1] = fmaf(kv.x, q1.x, fmaf(kv.y, q1.y, fmaf(kv.z, q1.z, fmaf(kv.w, q1.w, aq[u][1]))));
                 }
             }
-            if ((lane % lph) == 0) sc[(r * H + my_head) * M + m] = tot / inv_scale_div;
+            // (Wp_h^T q_h) . E[n, m, :] over ALL channels
+            if (has_e) {
+                const float* w0 = qp_s + (0 * H + h) * C;
+                const float* w1 = qp_s + (1 * H + h) * C;
+                const float* e00 = E + ((long long)n0 * M + mk[0]) * C;
+                const float* e01 = E + ((long long)n0 * M + mk[1]) * C;
+                const float* e10 = E + ((long long)(n0 + r1ok) * M + mk[0]) * C;
+                const float* e11 = E + ((long long)(n0 + r1ok) * M + mk[1]) * C;
+#pragma unroll 4
+                for (int c = 0; c < C; c += 4) {
+                    const float4 a0 = *reinterpret_cast<const float4*>(w0 + c);
+                    const float4 a1 = *reinterpret_cast<const float4*>(w1 + c);
+                    const float4 x00 = __ldg(reinterpret_cast<const float4*>(e00 + c));
+                    const float4 x01 = __ldg(reinterpret_cast<const float4*>(e01 + c));
+                    const float4 x10 = __ldg(reinterpret_cast<const float4*>(e10 + c));
+                    const float4 x11 = __ldg(reinterpret_cast<const float4*>(e11 + c));
+                    ae[0][0] = fmaf(x00.x, a0.x, fmaf(x00.y, a0.y, fmaf(x00.z, a0.z, fmaf(x00.w, a0.w, ae[0][0]))));
+                    ae[1][0] = fmaf(x01.x, a0.x, fmaf(x01.y, a0.y, fmaf(x01.z, a0.z, fmaf(x01.w, a0.w, ae[1][0]))));
+                    ae[0][1] = fmaf(x10.x, a1.x, fmaf(x10.y, a1.y, fmaf(x10.z, a1.z, fmaf(x10.w, a1.w, ae[0][1]))));
+                    ae[1][1] = fmaf(x11.x, a1.x, fmaf(x11.y, a1.y, fmaf(x11.z, a1.z, fmaf(x11.w, a1.w, ae[1][1]))));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < ATT_KPT; ++u)
+                if (ok[u]) {
+#pragma unroll
+                    for (int r = 0; r < ATT_R; ++r) {
+                        const int n = n0 + r;
+                        float tot = aq[u][r];
+                        if (has_e && n < N) tot += ae[u][r] + qb[(long long)n * H + h];
+                        sc[(r * H + h) * M + mk[u]] = tot / div;
+                    }
+                }
         }
     }
     __syncthreads();
     // softmax over m, one warp per (row, head)
-    for (int rh = warp; rh < R * H; rh += 8) {
+    for (int rh = warp; rh < ATT_R * H; rh += 8) {
         float* s = sc + rh * M;
         float mx = -INFINITY;
         for (int m = lane; m < M; m += 32) mx = fmaxf(mx, s[m]);
@@ -87,31 +120,39 @@ __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict_
         for (int m = lane; m < M; m += 32) s[m] = s[m] / sum;
     }
     __syncthreads();
-    // out[n][c] = sum_m P[h(c)][m] v[m][c]
+    // out[n][c] = sum_m P[h(c)][m] v[m][c]   (4 partial sums per thread for memory-level parallelism)
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const int h = c / (C / H);
-        float acc[R];
+        const int h = c / d;
+        const float* p0 = sc + (0 * H + h) * M;
+        const float* p1 = sc + (1 * H + h) * M;
+        float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+        int m = 0;
+        for (; m + 3 < M; m += 4) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) acc[r] = 0.f;
-        for (int m = 0; m < M; ++m) {
-            const float vv = v[(long long)m * C + c];
-#pragma unroll
-            for (int r = 0; r < R; ++r) acc[r] = fmaf(sc[(r * H + h) * M + m], vv, acc[r]);
+            for (int u = 0; u < 4; ++u) {
+                const float vv = v[(long long)(m + u) * ldv + c];
+                a0[u] = fmaf(p0[m + u], vv, a0[u]);
+                a1[u] = fmaf(p1[m + u], vv, a1[u]);
+            }
         }
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-            if (n0 + r < N) out[(long long)(n0 + r) * C + c] = acc[r];
+        for (; m < M; ++m) {
+            const float vv = v[(long long)m * ldv + c];
+            a0[0] = fmaf(p0[m], vv, a0[0]);
+            a1[0] = fmaf(p1[m], vv, a1[0]);
+        }
+        if (n0 < N) out[(long long)n0 * ldo + c] = (a0[0] + a0[1]) + (a0[2] + a0[3]);
+        if (n0 + 1 < N) out[(long long)(n0 + 1) * ldo + c] = (a1[0] + a1[1]) + (a1[2] + a1[3]);
     }
 }
 
 // qb[n][h] = sum_c q[n][h*d + c] * bp[h*d + c]
-__global__ void __launch_bounds__(256) head_bias_kernel(const float* __restrict__ q, const float* __restrict__ bp, int N, int C,
+__global__ void __launch_bounds__(256) head_bias_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ bp, int N, int C,
                                                         int H, float* __restrict__ qb) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= N * H) return;
     const int n = t / H, h = t % H, d = C / H;
     float s = 0.f;
-    for (int c = 0; c < d; ++c) s = fmaf(q[(long long)n * C + h * d + c], bp[h * d + c], s);
+    for (int c = 0; c < d; ++c) s = fmaf(q[(long long)n * ldq + h * d + c], bp[h * d + c], s);
     qb[t] = s;
 }
 
@@ -155,31 +196,36 @@ using namespace geob200;
 
 extern "C" {
 
-int geob200_attention(const float* q, const float* k, const float* v, const float* qp, const float* qb, const float* embed,
-                      int64_t n_query, int64_t n_key, int64_t channels, int64_t heads, float* out, void* stream) {
+int geob200_attention(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv, const float* qp,
+                      const float* qb, const float* embed, int64_t n_query, int64_t n_key, int64_t channels, int64_t heads,
+                      float* out, int64_t ldo, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     GEOB_REQUIRE(n_query > 0 && n_key > 0, "attention: empty input");
-    GEOB_REQUIRE(channels % 32 == 0 && channels <= 256 && heads > 0 && 32 % heads == 0 && channels % heads == 0,
+    GEOB_REQUIRE(channels % 4 == 0 && channels <= 256 && heads > 0 && heads <= ATT_MAXH && channels % heads == 0 &&
+                     (channels / heads) % 4 == 0,
                  "attention: unsupported channels=%lld heads=%lld", (long long)channels, (long long)heads);
     GEOB_REQUIRE((embed == nullptr) == (qp == nullptr) && (embed == nullptr) == (qb == nullptr), "attention: qp/qb/embed must come together");
-    constexpr int R = 2;
-    const size_t smem = sizeof(float) * (R * channels + R * heads * channels + R * heads * n_key);
+    GEOB_REQUIRE(ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0, "attention: row strides must be multiples of 4 floats");
+    const size_t smem = sizeof(float) * (ATT_R * channels + ATT_R * heads * channels + ATT_R * heads * n_key);
     GEOB_REQUIRE(smem <= 200 * 1024, "attention: too many keys (%lld)", (long long)n_key);
     static size_t smem_set = 0;
     if (smem > 48 * 1024 && smem > smem_set) {
-        GEOB_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GEOB_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
     const float div = sqrtf((float)(channels / heads));   // d_model_per_head ** 0.5
-    attention_kernel<R><<<(unsigned)((n_query + R - 1) / R), 256, smem, st>>>(q, k, v, qp, qb, embed, (int)n_query, (int)n_key,
-                                                                             (int)channels, (int)heads, div, out);
+    attention_kernel<<<(unsigned)((n_query + ATT_R - 1) / ATT_R), 256, smem, st>>>(q, (int)ldq, k, (int)ldk, v, (int)ldv, qp, qb, embed,
+                                                                                  (int)n_query, (int)n_key, (int)channels, (int)heads,
+                                                                                  div, out, (int)ldo);
     GEOB_CHECK_LAUNCH();
     count_launches(1);
     return 0;
 }
 
-int geob200_head_bias(const float* q, const float* bias_p, int64_t n, int64_t channels, int64_t heads, float* qb, void* stream) {
-    head_bias_kernel<<<(unsigned)((n * heads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(q, bias_p, (int)n, (int)channels, (int)heads, qb);
+int geob200_head_bias(const float* q, int64_t ldq, const float* bias_p, int64_t n, int64_t channels, int64_t heads, float* qb,
+                      void* stream) {
+    head_bias_kernel<<<(unsigned)((n * heads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(q, (int)ldq, bias_p, (int)n, (int)channels,
+                                                                                          (int)heads, qb);
     GEOB_CHECK_LAUNCH();
     count_launches(1);
     return 0;

@@ -18,7 +18,7 @@ namespace geob200 {
 
 static thread_local char g_err[1024] = "";
 static unsigned long long g_launches = 0;
-void count_launches(int n) { g_launches += (unsigned long long)n; }
+void count_launches(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
 void set_error(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);

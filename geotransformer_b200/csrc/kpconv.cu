@@ -18,7 +18,7 @@ namespace geob200 {
 constexpr int KP = 15;        // kernel points of every shipped model (config.py: backbone.kernel_size)
 constexpr int KP_PAD = 16;
 constexpr int TQ = 32;        // queries per CTA
-constexpr int CC = 64;        // input-channel chunk staged in shared memory
+constexpr int CC = 32;        // input-channel chunk staged in shared memory (one float per lane per neighbour row)
 
 __device__ __forceinline__ void influence15(const float* __restrict__ kp_s, float rx, float ry, float rz, float inv_dummy,
                                             float sigma, float* w) {
@@ -82,17 +82,31 @@ __global__ void __launch_bounds__(256) kpconv_c1_kernel(const float* __restrict_
     }
 }
 
+// pos[n] = 1 iff the sum of support row n is > 0: KPConv normalises by the number of such neighbours (kpconv.py:113-116)
+__global__ void __launch_bounds__(256) row_positive_kernel(const float* __restrict__ x, int N, int C, unsigned char* __restrict__ pos) {
+    const int lane = threadIdx.x & 31;
+    const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (n >= N) return;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += x[(long long)n * C + c];
+    s = warp_sum(s);
+    if (lane == 0) pos[n] = (s > 0.f) ? 1 : 0;
+}
+
 // General KPConv, Cin % 32 == 0 and Cout % 32 == 0 (mid channels 32..512 of the bottleneck blocks).
-// RC = Cout / 32 output columns per thread in the contraction phase.
+// RC = output columns per lane handled by this CTA (the CTA owns columns [col0, col0 + 32*RC)).
+// Input channels are processed in chunks of CC = 32 (one float per lane per neighbour row): the tile
+// wf[TQ][15*32] lives in 61 KB of shared memory so that 2-3 CTAs share an SM, and the neighbour rows of a query are
+// fetched eight at a time so that the gather is throughput- rather than latency-bound.
 template <int RC>
-__global__ void __launch_bounds__(256) kpconv_kernel(const float* __restrict__ feats, const float* __restrict__ q_pts,
-                                                     const float* __restrict__ s_pts, const long long* __restrict__ nbr,
-                                                     int H, const float* __restrict__ kp, const float* __restrict__ W,
-                                                     const float* __restrict__ bias, float sigma, int Ns, int M, int Cin,
-                                                     float* __restrict__ out) {
-    constexpr int Cout = RC * 32;
+__global__ void __launch_bounds__(256) kpconv_kernel(const float* __restrict__ feats, const unsigned char* __restrict__ pos,
+                                                     const float* __restrict__ q_pts, const float* __restrict__ s_pts,
+                                                     const long long* __restrict__ nbr, int H, const float* __restrict__ kp,
+                                                     const float* __restrict__ W, const float* __restrict__ bias, float sigma,
+                                                     int Ns, int M, int Cin, int Cout, float* __restrict__ out) {
+    const int col0 = blockIdx.y * (RC * 32);
     extern __shared__ float smem[];
-    float* wf = smem;                                  // [TQ][KP*CC]  (row stride KP*CC)
+    float* wf = smem;                                  // [TQ][KP*CC]
     float* infl = wf + TQ * KP * CC;                   // [8 warps][32][KP_PAD]
     int* sidx = (int*)(infl + 8 * 32 * KP_PAD);        // [8][32]
     float* npos_s = (float*)(sidx + 8 * 32);           // [TQ]
@@ -109,13 +123,12 @@ __global__ void __launch_bounds__(256) kpconv_kernel(const float* __restrict__ f
         for (int j = 0; j < RC; ++j) acc_out[r][j] = 0.f;
 
     for (int c0 = 0; c0 < Cin; c0 += CC) {
-        const int cw = min(CC, Cin - c0);             // 32 or 64 channels in this chunk
-        // ---- phase A: one warp per query; acc[k][j] = sum_h infl[h][k] * f[nbr_h][c0 + lane + 32 j]
+        // ---- phase A: one warp per query; acc[k] = sum_h infl[h][k] * f[nbr_h][c0 + lane]
         for (int q = warp; q < TQ; q += 8) {
             const int m = m0 + q;
-            float acc[KP][2];
+            float acc[KP];
 #pragma unroll
-            for (int k = 0; k < KP; ++k) { acc[k][0] = 0.f; acc[k][1] = 0.f; }
+            for (int k = 0; k < KP; ++k) acc[k] = 0.f;
             int npos = 0;
             if (m < M) {
                 const float qx = q_pts[3ll * m], qy = q_pts[3ll * m + 1], qz = q_pts[3ll * m + 2];
@@ -123,40 +136,39 @@ __global__ void __launch_bounds__(256) kpconv_kernel(const float* __restrict__ f
                     const int h = h0 + lane;
                     long long idx = (h < H) ? nbr[(long long)m * H + h] : (long long)Ns;
                     float w[KP];
+                    int id = 0;                         // shadow neighbours: zero influence, row 0 is read but unused
                     if (idx < Ns) {
+                        id = (int)idx;
                         influence15(kp_s, s_pts[3 * idx] - qx, s_pts[3 * idx + 1] - qy, s_pts[3 * idx + 2] - qz, 0.f, sigma, w);
+                        if (c0 == 0) npos += pos[idx];
                     } else {
-                        idx = Ns;
 #pragma unroll
                         for (int k = 0; k < KP; ++k) w[k] = 0.f;
                     }
                     float* irow = infl + (warp * 32 + lane) * KP_PAD;
 #pragma unroll
                     for (int k = 0; k < KP; ++k) irow[k] = w[k];
-                    sidx[warp * 32 + lane] = (int)idx;
+                    irow[KP] = 0.f;
+                    sidx[warp * 32 + lane] = id;
                     __syncwarp();
                     const int hn = min(32, H - h0);
-                    for (int hh = 0; hh < hn; ++hh) {
-                        const int id = sidx[warp * 32 + hh];
-                        if (id >= Ns) continue;                      // shadow neighbour: zero feature row
-                        const float* frow = feats + (long long)id * Cin;
-                        const float f0 = frow[c0 + lane];
-                        const float f1 = (cw > 32) ? frow[c0 + 32 + lane] : 0.f;
-                        if (c0 == 0) {
-                            // neighbour counts as valid iff the sum of its WHOLE feature row is > 0 (kpconv.py:113-114)
-                            float s = f0 + f1;
-                            for (int c = CC + lane; c < Cin; c += 32) s += frow[c];
-                            s = warp_sum(s);
-                            npos += (s > 0.f);
-                        }
-                        const float4* iv = reinterpret_cast<const float4*>(infl + (warp * 32 + hh) * KP_PAD);
-                        const float4 a0 = iv[0], a1 = iv[1], a2 = iv[2], a3 = iv[3];
-                        const float wv[16] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w,
-                                              a2.x, a2.y, a2.z, a2.w, a3.x, a3.y, a3.z, a3.w};
+                    for (int hb = 0; hb < hn; hb += 8) {
+                        float f[8];
 #pragma unroll
-                        for (int k = 0; k < KP; ++k) {
-                            acc[k][0] = fmaf(wv[k], f0, acc[k][0]);
-                            acc[k][1] = fmaf(wv[k], f1, acc[k][1]);
+                        for (int u = 0; u < 8; ++u) {   // 8 independent row fetches in flight (rows past hn have zero weights)
+                            const int id2 = sidx[warp * 32 + ((hb + u) & 31)];
+                            f[u] = __ldg(feats + (long long)id2 * Cin + c0 + lane);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            if (hb + u < hn) {
+                                const float4* iv = reinterpret_cast<const float4*>(infl + (warp * 32 + hb + u) * KP_PAD);
+                                const float4 a0 = iv[0], a1 = iv[1], a2 = iv[2], a3 = iv[3];
+                                const float wv[16] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w,
+                                                      a2.x, a2.y, a2.z, a2.w, a3.x, a3.y, a3.z, a3.w};
+#pragma unroll
+                                for (int k = 0; k < KP; ++k) acc[k] = fmaf(wv[k], f[u], acc[k]);
+                            }
                         }
                     }
                     __syncwarp();
@@ -164,23 +176,25 @@ __global__ void __launch_bounds__(256) kpconv_kernel(const float* __restrict__ f
             }
             float* wrow = wf + q * (KP * CC);
 #pragma unroll
-            for (int k = 0; k < KP; ++k) {
-                wrow[k * CC + lane] = acc[k][0];
-                wrow[k * CC + 32 + lane] = acc[k][1];
+            for (int k = 0; k < KP; ++k) wrow[k * CC + lane] = acc[k];
+            if (c0 == 0) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) npos += __shfl_xor_sync(0xffffffffu, npos, o);
+                if (lane == 0) npos_s[q] = (float)max(npos, 1);
             }
-            if (c0 == 0 && lane == 0) npos_s[q] = (float)max(npos, 1);
         }
         __syncthreads();
-        // ---- phase B: out[TQ x Cout] += wf[TQ x (KP*cw)] . W[k][c0:c0+cw][:]
-        // warp `warp` owns query rows 4*warp .. 4*warp+3 ; lane owns columns lane + 32 j
+        // ---- phase B: out[TQ x 32*RC] += wf[TQ x (KP*CC)] . W[k][c0:c0+CC][col0 : col0+32*RC]
+        // warp `warp` owns query rows 4*warp .. 4*warp+3 ; lane owns columns col0 + lane + 32 j
         {
             const float* a0p = wf + (4 * warp + 0) * (KP * CC);
             const float* a1p = wf + (4 * warp + 1) * (KP * CC);
             const float* a2p = wf + (4 * warp + 2) * (KP * CC);
             const float* a3p = wf + (4 * warp + 3) * (KP * CC);
             for (int k = 0; k < KP; ++k) {
-                const float* wbase = W + ((long long)k * Cin + c0) * Cout + lane;
-                for (int c = 0; c < cw; c += 4) {
+                const float* wbase = W + ((long long)k * Cin + c0) * Cout + col0 + lane;
+#pragma unroll 2
+                for (int c = 0; c < CC; c += 4) {
                     const float4 x0 = *reinterpret_cast<const float4*>(a0p + k * CC + c);
                     const float4 x1 = *reinterpret_cast<const float4*>(a1p + k * CC + c);
                     const float4 x2 = *reinterpret_cast<const float4*>(a2p + k * CC + c);
@@ -214,7 +228,7 @@ __global__ void __launch_bounds__(256) kpconv_kernel(const float* __restrict__ f
         const float nn = npos_s[q];
 #pragma unroll
         for (int j = 0; j < RC; ++j) {
-            const int c = lane + 32 * j;
+            const int c = col0 + lane + 32 * j;
             float o = acc_out[r][j] / nn;                          // kpconv.py:116
             if (bias != nullptr) o += bias[c];
             out[(long long)m * Cout + c] = o;
@@ -329,7 +343,14 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
         const int c = threadIdx.x % C, rr = threadIdx.x / C;
         if (rr < rpb) {
             double s = 0.0, s2 = 0.0;
-            for (int r = r0 + rr; r < r1; r += rpb) {
+            int r = r0 + rr;
+            for (; r + 3 * rpb < r1; r += 4 * rpb) {        // four independent loads in flight
+                const float v0 = x[(long long)r * C + c], v1 = x[(long long)(r + rpb) * C + c];
+                const float v2 = x[(long long)(r + 2 * rpb) * C + c], v3 = x[(long long)(r + 3 * rpb) * C + c];
+                s += ((double)v0 + (double)v1) + ((double)v2 + (double)v3);
+                s2 += ((double)v0 * v0 + (double)v1 * v1) + ((double)v2 * v2 + (double)v3 * v3);
+            }
+            for (; r < r1; r += rpb) {
                 const double v = (double)x[(long long)r * C + c];
                 s += v; s2 += v * v;
             }
@@ -339,7 +360,14 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
     } else {
         for (int c = threadIdx.x; c < C; c += 256) {
             double s = 0.0, s2 = 0.0;
-            for (int r = r0; r < r1; ++r) {
+            int r = r0;
+            for (; r + 3 < r1; r += 4) {
+                const float v0 = x[(long long)r * C + c], v1 = x[(long long)(r + 1) * C + c];
+                const float v2 = x[(long long)(r + 2) * C + c], v3 = x[(long long)(r + 3) * C + c];
+                s += ((double)v0 + (double)v1) + ((double)v2 + (double)v3);
+                s2 += ((double)v0 * v0 + (double)v1 * v1) + ((double)v2 * v2 + (double)v3 * v3);
+            }
+            for (; r < r1; ++r) {
                 const double v = (double)x[(long long)r * C + c];
                 s += v; s2 += v * v;
             }
@@ -355,18 +383,28 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
     if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
     __syncthreads();
     if (last) {
-        for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        // fold the per-CTA partials in a fixed order: 8 threads per group stride over the CTAs, then a 3-step shuffle
+        for (int g0 = 0; g0 < G; g0 += 32) {
+            const int g = g0 + (threadIdx.x >> 3), u = threadIdx.x & 7;
             double s = 0.0, s2 = 0.0;
-            for (unsigned b = 0; b < gridDim.x; ++b) {
-                s += partial[(long long)b * 2 * G + 2 * g];
-                s2 += partial[(long long)b * 2 * G + 2 * g + 1];
+            if (g < G)
+                for (unsigned b = u; b < gridDim.x; b += 8) {
+                    s += partial[(long long)b * 2 * G + 2 * g];
+                    s2 += partial[(long long)b * 2 * G + 2 * g + 1];
+                }
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) {
+                s += __shfl_xor_sync(0xffffffffu, s, o);
+                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
             }
-            const double cnt = (double)cpg * (double)N;
-            const double mean = s / cnt;
-            double var = s2 / cnt - mean * mean;
-            if (var < 0.0) var = 0.0;
-            mean_rstd[2 * g] = (float)mean;
-            mean_rstd[2 * g + 1] = (float)(1.0 / sqrt(var + eps));
+            if (g < G && u == 0) {
+                const double cnt = (double)cpg * (double)N;
+                const double mean = s / cnt;
+                double var = s2 / cnt - mean * mean;
+                if (var < 0.0) var = 0.0;
+                mean_rstd[2 * g] = (float)mean;
+                mean_rstd[2 * g + 1] = (float)(1.0 / sqrt(var + eps));
+            }
         }
         if (threadIdx.x == 0) *ticket = 0u;   // self-reset for the next launch on this stream
     }
@@ -432,10 +470,12 @@ using namespace geob200;
 
 extern "C" {
 
+size_t geob200_kpconv_workspace_bytes(int64_t n_support) { return (size_t)n_support + 256; }
+
 int geob200_kpconv(const float* s_feats, const float* q_points, const float* s_points, const int64_t* neighbors,
                    int64_t n_query, int64_t n_support, int64_t n_neighbors, const float* kernel_points, int64_t n_kernel,
                    const float* weights, const float* bias, int64_t c_in, int64_t c_out, float sigma, float* out,
-                   void* stream) {
+                   void* workspace, size_t workspace_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     GEOB_REQUIRE(n_kernel == KP, "kpconv: kernel_size %lld unsupported (all shipped models use 15)", (long long)n_kernel);
     GEOB_REQUIRE(n_query > 0 && n_support > 0 && n_neighbors > 0, "kpconv: empty input");
@@ -449,8 +489,17 @@ int geob200_kpconv(const float* s_feats, const float* q_points, const float* s_p
     }
     GEOB_REQUIRE(c_in % 32 == 0 && c_out % 32 == 0 && c_out <= 512,
                  "kpconv: channel counts (%lld -> %lld) must be multiples of 32, c_out <= 512", (long long)c_in, (long long)c_out);
+    GEOB_REQUIRE(workspace != nullptr && workspace_bytes >= geob200_kpconv_workspace_bytes(n_support), "kpconv: workspace too small");
+    unsigned char* pos = (unsigned char*)workspace;
+    row_positive_kernel<<<(unsigned)((n_support + 7) / 8), 256, 0, st>>>(s_feats, (int)n_support, (int)c_in, pos);
     const size_t smem = sizeof(float) * (TQ * KP * CC + 8 * 32 * KP_PAD + TQ + KP * 3 + 3) + sizeof(int) * 8 * 32;
-    const unsigned grid = (unsigned)((n_query + TQ - 1) / TQ);
+    const unsigned qtiles = (unsigned)((n_query + TQ - 1) / TQ);
+    // columns per CTA: full width unless the level has too few query tiles to fill the GPU; then split the columns over at
+    // most 4 CTAs (each of them repeats the gather phase)
+    int rc = (int)(c_out / 32);
+    int split = 1;
+    while (rc > 1 && split < 4 && (long long)qtiles * split < 2ll * num_sms()) { rc >>= 1; split <<= 1; }
+    const dim3 grid(qtiles, (unsigned)split);
 #define LAUNCH_KP(RCV)                                                                                              \
     {                                                                                                               \
         static bool set = false;                                                                                    \
@@ -458,11 +507,11 @@ int geob200_kpconv(const float* s_feats, const float* q_points, const float* s_p
             GEOB_CHECK_CUDA(cudaFuncSetAttribute(kpconv_kernel<RCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             set = true;                                                                                             \
         }                                                                                                           \
-        kpconv_kernel<RCV><<<grid, 256, smem, st>>>(s_feats, q_points, s_points, (const long long*)neighbors,       \
+        kpconv_kernel<RCV><<<grid, 256, smem, st>>>(s_feats, pos, q_points, s_points, (const long long*)neighbors,  \
                                                     (int)n_neighbors, kernel_points, weights, bias, sigma,         \
-                                                    (int)n_support, (int)n_query, (int)c_in, out);                 \
+                                                    (int)n_support, (int)n_query, (int)c_in, (int)c_out, out);     \
     }
-    switch (c_out / 32) {
+    switch (rc) {
         case 1: LAUNCH_KP(1) break;
         case 2: LAUNCH_KP(2) break;
         case 4: LAUNCH_KP(4) break;
@@ -472,7 +521,7 @@ int geob200_kpconv(const float* s_feats, const float* q_points, const float* s_p
     }
 #undef LAUNCH_KP
     GEOB_CHECK_LAUNCH();
-    count_launches(1);
+    count_launches(2);
     return 0;
 }
 
@@ -482,17 +531,18 @@ int geob200_linear_batched(const float* x, int64_t ldx, int64_t stride_x, const 
     cudaStream_t st = (cudaStream_t)stream;
     GEOB_REQUIRE(m > 0 && n > 0 && k > 0 && batch > 0, "linear: empty problem");
     const unsigned z = (unsigned)batch;
-    if (m <= 1024 && n <= 64) {
-        dim3 grid((unsigned)((n + 31) / 32), (unsigned)((m + 31) / 32), z);
-        linear_kernel<32, 32><<<grid, 256, 0, st>>>(x, (int)ldx, weight, (int)ldw, bias, y, (int)ldy, (int)m, (int)n, (int)k, relu,
+    const long long c64 = ((n + 63) / 64) * ((m + 63) / 64) * batch, c6432 = ((n + 31) / 32) * ((m + 63) / 64) * batch;
+    if (c64 >= 148) {
+        dim3 grid((unsigned)((n + 63) / 64), (unsigned)((m + 63) / 64), z);
+        linear_kernel<64, 64><<<grid, 256, 0, st>>>(x, (int)ldx, weight, (int)ldw, bias, y, (int)ldy, (int)m, (int)n, (int)k, relu,
                                                     stride_x, stride_w, stride_b, stride_y);
-    } else if (m * n * batch <= 148ll * 64 * 64 * 2) {
+    } else if (c6432 >= 148) {
         dim3 grid((unsigned)((n + 31) / 32), (unsigned)((m + 63) / 64), z);
         linear_kernel<64, 32><<<grid, 256, 0, st>>>(x, (int)ldx, weight, (int)ldw, bias, y, (int)ldy, (int)m, (int)n, (int)k, relu,
                                                     stride_x, stride_w, stride_b, stride_y);
     } else {
-        dim3 grid((unsigned)((n + 63) / 64), (unsigned)((m + 63) / 64), z);
-        linear_kernel<64, 64><<<grid, 256, 0, st>>>(x, (int)ldx, weight, (int)ldw, bias, y, (int)ldy, (int)m, (int)n, (int)k, relu,
+        dim3 grid((unsigned)((n + 31) / 32), (unsigned)((m + 31) / 32), z);
+        linear_kernel<32, 32><<<grid, 256, 0, st>>>(x, (int)ldx, weight, (int)ldw, bias, y, (int)ldy, (int)m, (int)n, (int)k, relu,
                                                     stride_x, stride_w, stride_b, stride_y);
     }
     GEOB_CHECK_LAUNCH();
@@ -505,7 +555,7 @@ int geob200_linear(const float* x, int64_t ldx, const float* weight, const float
     return geob200_linear_batched(x, ldx, 0, weight, k, 0, bias, 0, y, ldy, 0, m, n, k, 1, relu, stream);
 }
 
-size_t geob200_group_norm_workspace_bytes(int64_t groups) { return (size_t)(296 * 2 * groups * 8 + 2 * groups * 4 + 256 + 1024); }
+size_t geob200_group_norm_workspace_bytes(int64_t groups) { return (size_t)(592 * 2 * groups * 8 + 2 * groups * 4 + 256 + 1024); }
 
 int geob200_group_norm(const float* x, int64_t n_rows, int64_t channels, int64_t groups, const float* gamma,
                        const float* beta, float eps, const float* residual, int leaky, float slope, float* y,
@@ -517,9 +567,9 @@ int geob200_group_norm(const float* x, int64_t n_rows, int64_t channels, int64_t
     Arena ar(workspace, workspace_bytes);
     unsigned* ticket = ar.take<unsigned>(64);           // must be zero on first use: caller provides zeroed ws once
     float* mean_rstd = ar.take<float>(2 * groups);
-    double* partial = ar.take<double>(296 * 2 * groups);
-    int nblk = (int)((n_rows + 127) / 128);
-    if (nblk > 296) nblk = 296;
+    double* partial = ar.take<double>(592 * 2 * groups);
+    int nblk = (int)((n_rows + 63) / 64);
+    if (nblk > 592) nblk = 592;
     if (nblk < 1) nblk = 1;
     gn_stats_kernel<<<nblk, 256, sizeof(double) * 2 * groups, st>>>(x, (int)n_rows, (int)channels, (int)groups, (double)eps,
                                                                     partial, ticket, mean_rstd);

@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(256) patch_scores_kernel(const float* __restri
 // ---- Sinkhorn --------------------------------------------------------------------------------------------
 // One CTA per patch pair.  Z (K+1)x(K+1) padded scores in shared memory, row/col potentials u, v.
 // learnable_sinkhorn.py:13-18:  u = log_mu - LSE_j(Z + v) ; v = log_nu - LSE_i(Z + u)   x num_iterations
-__global__ void __launch_bounds__(256) sinkhorn_kernel(const float* __restrict__ scores, const unsigned char* __restrict__ row_masks,
+__global__ void __launch_bounds__(1024) sinkhorn_kernel(const float* __restrict__ scores, const unsigned char* __restrict__ row_masks,
                                                        const unsigned char* __restrict__ col_masks, const float* __restrict__ alpha_p,
                                                        int K, int iters, float inf, float* __restrict__ out) {
     extern __shared__ float sm[];
@@ -307,8 +307,9 @@ __global__ void __launch_bounds__(256) sinkhorn_kernel(const float* __restrict__
         lmu[i] = mu; lnu[i] = nu; u[i] = 0.f; v[i] = 0.f;
     }
     __syncthreads();
+    const int nwarp = blockDim.x >> 5;
     for (int it = 0; it < iters; ++it) {
-        for (int i = warp; i < K1; i += 8) {
+        for (int i = warp; i < K1; i += nwarp) {
             const float* zr = Z + i * ld;
             float mx = -INFINITY;
             for (int j = lane; j < K1; j += 32) mx = fmaxf(mx, zr[j] + v[j]);
@@ -319,7 +320,7 @@ __global__ void __launch_bounds__(256) sinkhorn_kernel(const float* __restrict__
             if (lane == 0) u[i] = lmu[i] - (logf(s) + mx);
         }
         __syncthreads();
-        for (int j = warp; j < K1; j += 8) {
+        for (int j = warp; j < K1; j += nwarp) {
             float mx = -INFINITY;
             for (int i = lane; i < K1; i += 32) mx = fmaxf(mx, Z[i * ld + j] + u[i]);
             mx = warp_max(mx);
@@ -425,7 +426,7 @@ int geob200_sinkhorn(const float* scores, const uint8_t* row_masks, const uint8_
         GEOB_CHECK_CUDA(cudaFuncSetAttribute(sinkhorn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
-    sinkhorn_kernel<<<(unsigned)n_patches, 256, smem, st>>>(scores, row_masks, col_masks, alpha, (int)k, (int)num_iterations, inf, out);
+    sinkhorn_kernel<<<(unsigned)n_patches, (k >= 48 ? 1024 : 512), smem, st>>>(scores, row_masks, col_masks, alpha, (int)k, (int)num_iterations, inf, out);
     GEOB_CHECK_LAUNCH();
     count_launches(1);
     return 0;

@@ -96,3 +96,14 @@ def radius_neighbors(q_points, s_points, q_lengths, s_lengths, radius, neighbor_
         if mc > 0:
             _radius_call(q_points, s_points, ql_h, sl_h, radius, mc, out, None, max_count)
     return out.cpu() if was_cpu else out
+
+
+def radius_neighbors_deferred(q_points, s_points, q_lengths, s_lengths, radius, neighbor_limit):
+    """Limited-width search with NO host synchronisation: (table (Nq, limit) int64, max_count int32[1] on the device)."""
+    q_points, ql_h, _ = _prep(q_points, q_lengths, 'q_points', 'q_lengths')
+    s_points, sl_h, _ = _prep(s_points, s_lengths, 's_points', 's_lengths')
+    dev = q_points.device
+    max_count = torch.empty((1,), dtype=torch.int32, device=dev)
+    out = torch.empty((q_points.shape[0], neighbor_limit), dtype=torch.int64, device=dev)
+    _radius_call(q_points, s_points, ql_h, sl_h, radius, neighbor_limit, out, None, max_count)
+    return out, max_count

@@ -51,7 +51,7 @@ _GN_WS = {}
 
 
 def _gn_workspace(device, groups):
-    key = (device.index, groups)
+    key = (device.index, L.stream_ptr(), groups)
     ws = _GN_WS.get(key)
     if ws is None:
         ws = torch.zeros(L.lib().geob200_group_norm_workspace_bytes(groups), dtype=_u8, device=device)
@@ -69,10 +69,12 @@ def kpconv(s_feats, q_points, s_points, neighbor_indices, kernel_points, weights
     ns = s_points.shape[0]
     k, cin, cout = weights.shape
     out = torch.empty((m, cout), dtype=_f32, device=s_feats.device)
-    L.check(L.lib().geob200_kpconv(s_feats.data_ptr(), q_points.data_ptr(), s_points.data_ptr(),
-                                   neighbor_indices.data_ptr(), m, ns, h, kernel_points.data_ptr(), k,
-                                   weights.data_ptr(), L.ptr(bias), cin, cout, float(sigma), out.data_ptr(),
-                                   L.stream_ptr()), 'kpconv')
+    lib = L.lib()
+    ws = L.workspace(lib.geob200_kpconv_workspace_bytes(ns), s_feats.device, 'kpconv')
+    L.check(lib.geob200_kpconv(s_feats.data_ptr(), q_points.data_ptr(), s_points.data_ptr(),
+                               neighbor_indices.data_ptr(), m, ns, h, kernel_points.data_ptr(), k,
+                               weights.data_ptr(), L.ptr(bias), cin, cout, float(sigma), out.data_ptr(),
+                               ws.data_ptr(), ws.numel(), L.stream_ptr()), 'kpconv')
     return out
 
 
@@ -196,34 +198,50 @@ def gse_embed(d_indices, a_indices, div_term, wd, wa, bd, ba, wd_t, wa_t, mode=N
     return emb
 
 
-def attention(q, k, v, heads, qp=None, qb=None, embed=None):
+def _rows(t, name):
+    if not t.is_cuda or t.dtype != _f32 or t.ndim != 2 or t.stride(1) != 1:
+        raise RuntimeError(f'{name} must be a 2-D float32 CUDA tensor with unit inner stride')
+    return t
+
+
+def attention(q, k, v, heads, qp=None, qb=None, embed=None, out=None):
+    """q, k, v may be column slices of a fused projection buffer (row stride != channels)."""
+    _rows(q, 'q'); _rows(k, 'k'); _rows(v, 'v')
     n, c = q.shape
     m = k.shape[0]
-    out = torch.empty((n, c), dtype=_f32, device=q.device)
-    L.check(L.lib().geob200_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), L.ptr(qp), L.ptr(qb), L.ptr(embed), n, m,
-                                      c, heads, out.data_ptr(), L.stream_ptr()), 'attention')
+    if out is None:
+        out = torch.empty((n, c), dtype=_f32, device=q.device)
+    L.check(L.lib().geob200_attention(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
+                                      L.ptr(qp), L.ptr(qb), L.ptr(embed), n, m, c, heads, out.data_ptr(), out.stride(0),
+                                      L.stream_ptr()), 'attention')
     return out
 
 
 def head_project(q, wp_t, bp, heads):
     """qp[n,h,:] = Wp[h*d:(h+1)*d, :]^T q[n,h*d:(h+1)*d]  and  qb[n,h] = q_h . bp_h   (proj_p moved onto q)."""
+    _rows(q, 'q')
     n, c = q.shape
     d = c // heads
     qp = torch.empty((n, heads, c), dtype=_f32, device=q.device)
     qb = torch.empty((n, heads), dtype=_f32, device=q.device)
     lib = L.lib()
-    # batched over heads: x = q[:, h*d:(h+1)*d] (ldx=c, stride d), W' = wp_t[:, h*d:(h+1)*d] (ldw=c, stride d),
+    # batched over heads: x = q[:, h*d:(h+1)*d] (ldx=row stride, stride d), W' = wp_t[:, h*d:(h+1)*d] (ldw=c, stride d),
     # y = qp[:, h, :] (ldy=heads*c, stride c)
-    L.check(lib.geob200_linear_batched(q.data_ptr(), c, d, wp_t.data_ptr(), c, d, None, 0, qp.data_ptr(), heads * c, c,
+    L.check(lib.geob200_linear_batched(q.data_ptr(), q.stride(0), d, wp_t.data_ptr(), c, d, None, 0, qp.data_ptr(), heads * c, c,
                                        n, c, d, heads, 0, L.stream_ptr()), 'head_project')
-    L.check(lib.geob200_head_bias(q.data_ptr(), bp.data_ptr(), n, c, heads, qb.data_ptr(), L.stream_ptr()), 'head_bias')
+    L.check(lib.geob200_head_bias(q.data_ptr(), q.stride(0), bp.data_ptr(), n, c, heads, qb.data_ptr(), L.stream_ptr()), 'head_bias')
     return qp, qb
 
 
-def add_layernorm(a, b, weight, bias, eps=1e-5):
+def add_layernorm(a, b, weight, bias, eps=1e-5, out=None):
     weight, bias = _detach(weight), _detach(bias)
+    L.require_cuda(a, 'a', _f32)
+    if b is not None:
+        L.require_cuda(b, 'b', _f32)
     n, c = a.shape
-    y = torch.empty_like(a)
+    y = torch.empty_like(a) if out is None else out
+    if not y.is_contiguous():
+        raise RuntimeError('add_layernorm: out must be contiguous')
     L.check(L.lib().geob200_add_layernorm(a.data_ptr(), L.ptr(b), weight.data_ptr(), bias.data_ptr(), n, c, float(eps),
                                           y.data_ptr(), L.stream_ptr()), 'add_layernorm')
     return y

@@ -62,11 +62,14 @@ class GeometricTransformer(nn.Module):
             ref_points, src_points, ref_feats, src_feats = ref_points[0], src_points[0], ref_feats[0], src_feats[0]
         ref_emb = self.embedding(ref_points)
         src_emb = self.embedding(src_points)
-        rf = GF.linear(ref_feats, self.in_proj.weight, self.in_proj.bias)
-        sf = GF.linear(src_feats, self.in_proj.weight, self.in_proj.bias)
-        rf, sf = self.transformer(rf, sf, ref_emb, src_emb)
-        rf = GF.linear(rf, self.out_proj.weight, self.out_proj.bias)
-        sf = GF.linear(sf, self.out_proj.weight, self.out_proj.bias)
+        n0, n1 = ref_feats.shape[0], src_feats.shape[0]
+        # both clouds share every weight: keep them stacked [ref; src] through the whole transformer
+        x = torch.empty((n0 + n1, self.in_proj.out_features), dtype=torch.float32, device=ref_feats.device)
+        GF.linear(ref_feats, self.in_proj.weight, self.in_proj.bias, out=x[:n0])
+        GF.linear(src_feats, self.in_proj.weight, self.in_proj.bias, out=x[n0:])
+        x = self.transformer.forward_stacked(x, n0, ref_emb, src_emb)
+        y = GF.linear(x, self.out_proj.weight, self.out_proj.bias)
+        rf, sf = y[:n0], y[n0:]
         if batched:
             return rf.unsqueeze(0), sf.unsqueeze(0)
         return rf, sf

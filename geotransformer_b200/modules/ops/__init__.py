@@ -17,6 +17,12 @@ def radius_search(q_points, s_points, q_lengths, s_lengths, radius, neighbor_lim
     return _ext.radius_neighbors(q_points, s_points, q_lengths, s_lengths, radius, neighbor_limit=max(int(neighbor_limit), 0))
 
 
+def radius_search_deferred(q_points, s_points, q_lengths, s_lengths, radius, neighbor_limit):
+    """radius_search without the host read-back: returns (table (N, limit), max_count device int32[1]); the caller cuts
+    the table to min(limit, max_count) columns once it has read the counts (one sync for many searches)."""
+    return _ext.radius_neighbors_deferred(q_points, s_points, q_lengths, s_lengths, radius, int(neighbor_limit))
+
+
 def point_to_node_partition(points, nodes, point_limit, return_count=False):
     """reference ``modules/ops/pointcloud_partition.py:60-107``."""
     return GF.point_to_node_partition(points, nodes, point_limit, return_count)

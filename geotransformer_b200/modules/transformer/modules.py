@@ -186,6 +186,25 @@ class TransformerLayer(nn.Module):
         return self.output(hidden), scores
 
 
+def _tail(layer, hidden, inp, out=None):
+    """attention.linear + residual LayerNorm, then the FFN block with its residual LayerNorm (5 launches)."""
+    att, ffn = layer.attention, layer.output
+    h = GF.linear(hidden, att.linear.weight, att.linear.bias)
+    x = GF.add_layernorm(h, inp, att.norm.weight, att.norm.bias, att.norm.eps)
+    y = GF.linear(x, ffn.expand.weight, ffn.expand.bias, relu=True)
+    y = GF.linear(y, ffn.squeeze.weight, ffn.squeeze.bias)
+    return GF.add_layernorm(x, y, ffn.norm.weight, ffn.norm.bias, ffn.norm.eps, out=out)
+
+
+def _fused(cache, mha, names):
+    """concatenated projection weights/biases (one GEMM instead of len(names)); cached per parameter version"""
+    key = '+'.join(names)
+    first = getattr(mha, names[0]).weight
+    w = cache.get('w_' + key, first, lambda _: torch.cat([getattr(mha, n).weight.detach() for n in names], dim=0).contiguous())
+    b = cache.get('b_' + key, first, lambda _: torch.cat([getattr(mha, n).bias.detach() for n in names], dim=0).contiguous())
+    return w, b
+
+
 class RPEConditionalTransformer(nn.Module):
     """reference ``conditional_transformer.py:73-117`` (sequential cross updates unless ``parallel``)."""
 
@@ -206,15 +225,48 @@ class RPEConditionalTransformer(nn.Module):
         self.parallel = parallel
 
     def forward(self, feats0, feats1, embeddings0, embeddings1, masks0=None, masks1=None):
+        _no_masks(masks0=masks0, masks1=masks1)
+        n0 = feats0.shape[0]
+        x = torch.empty((n0 + feats1.shape[0], feats0.shape[1]), dtype=feats0.dtype, device=feats0.device)
+        x[:n0].copy_(feats0)
+        x[n0:].copy_(feats1)
+        x = self.forward_stacked(x, n0, embeddings0, embeddings1)
+        return x[:n0], x[n0:]
+
+    def forward_stacked(self, x, n0, embeddings0, embeddings1):
+        """Same computation on the stacked features [feats0; feats1] (they share every layer's weights): the q|k|v
+        projections of both clouds are ONE GEMM, the attention kernel reads them as column slices, and the
+        Linear/LayerNorm/FFN tail runs once per layer on all rows."""
+        if not hasattr(self, '_cache'):
+            self._cache = _WeightCache()
+        c = x.shape[1]
         for i, block in enumerate(self.blocks):
+            layer = self.layers[i]
+            mha = layer.attention.attention
+            h = mha.num_heads
             if block == 'self':
-                feats0, _ = self.layers[i](feats0, feats0, embeddings0, memory_masks=masks0)
-                feats1, _ = self.layers[i](feats1, feats1, embeddings1, memory_masks=masks1)
-            elif self.parallel:
-                new0, _ = self.layers[i](feats0, feats1, memory_masks=masks1)
-                new1, _ = self.layers[i](feats1, feats0, memory_masks=masks0)
-                feats0, feats1 = new0, new1
+                w, b = _fused(self._cache, mha, ('proj_q', 'proj_k', 'proj_v'))
+                qkv = GF.linear(x, w, b)                                          # (N0+N1, 3C)
+                q, k, v = qkv[:, :c], qkv[:, c:2 * c], qkv[:, 2 * c:]
+                wp_t = self._cache.get(f'wp_t{i}', mha.proj_p.weight, lambda p: p.t().contiguous())
+                qp, qb = GF.head_project(q, wp_t, mha.proj_p.bias.detach(), h)
+                hidden = torch.empty_like(x)
+                GF.attention(q[:n0], k[:n0], v[:n0], h, qp=qp[:n0], qb=qb[:n0], embed=embeddings0, out=hidden[:n0])
+                GF.attention(q[n0:], k[n0:], v[n0:], h, qp=qp[n0:], qb=qb[n0:], embed=embeddings1, out=hidden[n0:])
+                x = _tail(layer, hidden, x)
             else:
-                feats0, _ = self.layers[i](feats0, feats1, memory_masks=masks1)
-                feats1, _ = self.layers[i](feats1, feats0, memory_masks=masks0)
-        return feats0, feats1
+                wkv, bkv = _fused(self._cache, mha, ('proj_k', 'proj_v'))
+                y = torch.empty_like(x)
+                # feats0 <- layer(feats0, feats1)
+                q0 = GF.linear(x[:n0], mha.proj_q.weight, mha.proj_q.bias)
+                kv1 = GF.linear(x[n0:], wkv, bkv)
+                hid0 = GF.attention(q0, kv1[:, :c], kv1[:, c:], h)
+                _tail(layer, hid0, x[:n0], out=y[:n0])
+                # feats1 <- layer(feats1, feats0): sees the UPDATED feats0 unless `parallel`
+                mem = x[:n0] if self.parallel else y[:n0]
+                q1 = GF.linear(x[n0:], mha.proj_q.weight, mha.proj_q.bias)
+                kv0 = GF.linear(mem, wkv, bkv)
+                hid1 = GF.attention(q1, kv0[:, :c], kv0[:, c:], h)
+                _tail(layer, hid1, x[n0:], out=y[n0:])
+                x = y
+        return x

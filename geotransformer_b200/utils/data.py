@@ -7,7 +7,7 @@ forked workers, so here the raw pair is moved to the device and collated in the 
 import numpy as np
 import torch
 
-from ..modules.ops import grid_subsample, radius_search
+from ..modules.ops import grid_subsample, radius_search, radius_search_deferred
 
 
 def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, neighbor_limits):
@@ -24,16 +24,27 @@ def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, 
         lengths_list.append(lengths_h.to(points.device))
         voxel_size *= 2
 
-    neighbors_list, subsampling_list, upsampling_list = [], [], []
+    # all 3S-2 searches are launched back to back at their full `limit` width; the reference's row width is
+    # min(limit, max neighbour count) (radius_search.py:25-26), so the max counts are read back ONCE at the end and only
+    # the tables that are narrower than their limit are cut (rare: the coarsest level)
+    pending = []
     for i in range(num_stages):
         cur_points, cur_lengths = points_list[i], lengths_host[i]
-        neighbors_list.append(radius_search(cur_points, cur_points, cur_lengths, cur_lengths, radius, neighbor_limits[i]))
+        pending.append(('n', radius_search_deferred(cur_points, cur_points, cur_lengths, cur_lengths, radius, neighbor_limits[i])))
         if i < num_stages - 1:
             sub_points, sub_lengths = points_list[i + 1], lengths_host[i + 1]
-            subsampling_list.append(radius_search(sub_points, cur_points, sub_lengths, cur_lengths, radius, neighbor_limits[i]))
-            upsampling_list.append(radius_search(cur_points, sub_points, cur_lengths, sub_lengths, radius * 2,
-                                                 neighbor_limits[i + 1]))
+            pending.append(('s', radius_search_deferred(sub_points, cur_points, sub_lengths, cur_lengths, radius, neighbor_limits[i])))
+            pending.append(('u', radius_search_deferred(cur_points, sub_points, cur_lengths, sub_lengths, radius * 2,
+                                                        neighbor_limits[i + 1])))
         radius *= 2
+    counts = torch.stack([p[1][1] for p in pending]).cpu().flatten().tolist()      # the single D2H of the searches
+    neighbors_list, subsampling_list, upsampling_list = [], [], []
+    for (kind, (table, _)), mc in zip(pending, counts):
+        if mc < 0:
+            raise RuntimeError('radius_search: more than 16384 neighbours for one query')
+        if mc < table.shape[1]:
+            table = table[:, :mc].contiguous()
+        {'n': neighbors_list, 's': subsampling_list, 'u': upsampling_list}[kind].append(table)
     return {'points': points_list, 'lengths': lengths_list, 'lengths_host': [l.tolist() for l in lengths_host],
             'neighbors': neighbors_list, 'subsampling': subsampling_list, 'upsampling': upsampling_list}
 

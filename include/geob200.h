@@ -52,10 +52,11 @@ int geob200_radius_search(const float* q_points, int64_t n_query, const float* s
  * influence -> contraction -> neighbour-count normalisation -> bias.  neighbors (n_query, n_neighbors) int64 with
  * sentinel n_support; kernel_points (15,3); weights (15, c_in, c_out); bias may be NULL.
  * c_in == 1, or c_in, c_out multiples of 32 with c_out <= 512. */
+size_t geob200_kpconv_workspace_bytes(int64_t n_support);
 int geob200_kpconv(const float* s_feats, const float* q_points, const float* s_points, const int64_t* neighbors,
                    int64_t n_query, int64_t n_support, int64_t n_neighbors, const float* kernel_points, int64_t n_kernel,
                    const float* weights, const float* bias, int64_t c_in, int64_t c_out, float sigma, float* out,
-                   void* stream);
+                   void* workspace, size_t workspace_bytes, void* stream);
 
 /* nn.Linear: y[m,n] = x[m,k] . weight[n,k]^T + bias (UnaryBlock.mlp, modules.py:78; every transformer Linear).
  * ldx / ldy are row strides in floats (inputs may be column slices). */
@@ -112,9 +113,11 @@ int geob200_gse_embed(const float* d_indices, const float* a_indices, int64_t n,
 /* Fused multi-head attention: softmax((q.k + qp.E + qb)/sqrt(d)) v  (rpe_transformer.py:51-70 with proj_p moved onto
  * q; vanilla_transformer.py:50-68 when qp = qb = embed = NULL).  q (n_query,C), k,v (n_key,C), qp (n_query,H,C),
  * qb (n_query,H), embed (n_query,n_key,C). */
-int geob200_attention(const float* q, const float* k, const float* v, const float* qp, const float* qb, const float* embed,
-                      int64_t n_query, int64_t n_key, int64_t channels, int64_t heads, float* out, void* stream);
-int geob200_head_bias(const float* q, const float* bias_p, int64_t n, int64_t channels, int64_t heads, float* qb, void* stream);
+int geob200_attention(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv, const float* qp,
+                      const float* qb, const float* embed, int64_t n_query, int64_t n_key, int64_t channels, int64_t heads,
+                      float* out, int64_t ldo, void* stream);
+int geob200_head_bias(const float* q, int64_t ldq, const float* bias_p, int64_t n, int64_t channels, int64_t heads, float* qb,
+                      void* stream);
 /* y = LayerNorm(a + b) (b may be NULL) */
 int geob200_add_layernorm(const float* a, const float* b, const float* gamma, const float* beta, int64_t n, int64_t channels,
                           float eps, float* y, void* stream);
