@@ -74,6 +74,13 @@ __device__ __forceinline__ double warp_sum_d(double v) {
     return v;
 }
 
+// fp32 -> tf32 (10-bit mantissa) with round-to-nearest, returned as an fp32 bit pattern (low 13 bits zero)
+__device__ __forceinline__ float tf32_rn(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
 static inline int num_sms() {
     static int n = 0;
     if (n == 0) {

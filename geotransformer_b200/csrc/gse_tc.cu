@@ -118,7 +118,7 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 }
 
 // Packs B = [Wa | Wd] (row n = output channel, 512 K values) into per-chunk shared-memory images:
-// image[kc][n/8][n%8][(e/4) ^ (n%8)][e%4], hi part (tf32-truncated) and lo part (remainder).
+// image[kc][n/8][n%8][(e/4) ^ (n%8)][e%4], hi part (tf32, round-to-nearest) and lo part (remainder).
 __global__ void __launch_bounds__(256) gse_pack_b_kernel(const float* __restrict__ Wd, const float* __restrict__ Wa,
                                                          const float* __restrict__ bd, const float* __restrict__ ba,
                                                          float* __restrict__ img_hi, float* __restrict__ img_lo,
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(256) gse_pack_b_kernel(const float* __restrict
     if (t >= C * KTOT) return;
     const int n = t / KTOT, k = t % KTOT;
     const float w = (k < 256) ? Wa[n * 256 + k] : Wd[n * 256 + (k - 256)];
-    const float hi = __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
+    const float hi = tf32_rn(w);
     const int kc = k / KC, e = k % KC;
     const int dst = kc * (C * KC) + (n >> 3) * 256 + (n & 7) * 32 + (((e >> 2) ^ (n & 7)) << 2) + (e & 3);
     img_hi[dst] = hi;
@@ -211,10 +211,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gse_embed_tc_kernel(const float* 
                     sincos_cw(__fmul_rn(x, __ldg(div_term + f0 + 2 * c + 1)), s1, c1);
                     float4 hi = make_float4(s0, c0, s1, c1), lo = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (NPASS == 3) {
-                        hi.x = __uint_as_float(__float_as_uint(s0) & 0xFFFFE000u); lo.x = s0 - hi.x;
-                        hi.y = __uint_as_float(__float_as_uint(c0) & 0xFFFFE000u); lo.y = c0 - hi.y;
-                        hi.z = __uint_as_float(__float_as_uint(s1) & 0xFFFFE000u); lo.z = s1 - hi.z;
-                        hi.w = __uint_as_float(__float_as_uint(c1) & 0xFFFFE000u); lo.w = c1 - hi.w;
+                        hi.x = tf32_rn(s0); lo.x = s0 - hi.x;
+                        hi.y = tf32_rn(c0); lo.y = c0 - hi.y;
+                        hi.z = tf32_rn(s1); lo.z = s1 - hi.z;
+                        hi.w = tf32_rn(c1); lo.w = c1 - hi.w;
                     }
                     const int nrep = angle ? 1 : 3;
                     for (int rep = 0; rep < nrep; ++rep) {

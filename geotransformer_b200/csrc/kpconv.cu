@@ -468,7 +468,15 @@ __global__ void __launch_bounds__(256) upsample_concat_kernel(const float* __res
 
 using namespace geob200;
 
+namespace geob200 {
+int linear_tc(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, float* y, int64_t ldy, int64_t m, int64_t n,
+              int64_t k, int relu, cudaStream_t st);   // linear_tc.cu
+static int g_linear_mode = 1;   // 1 = tcgen05 3xTF32 where the shape allows, 0 = fp32 CUDA cores only
+}
+
 extern "C" {
+
+void geob200_set_linear_mode(int mode) { g_linear_mode = mode; }
 
 size_t geob200_kpconv_workspace_bytes(int64_t n_support) { return (size_t)n_support + 256; }
 
@@ -530,6 +538,10 @@ int geob200_linear_batched(const float* x, int64_t ldx, int64_t stride_x, const 
                            int64_t k, int64_t batch, int relu, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     GEOB_REQUIRE(m > 0 && n > 0 && k > 0 && batch > 0, "linear: empty problem");
+    if (batch == 1 && g_linear_mode == 1) {
+        const int rc = linear_tc(x, ldx, weight, ldw, bias, y, ldy, m, n, k, relu, st);
+        if (rc <= 0) return rc;       // done (0) or hard error (<0); 1 = shape not handled -> fp32 kernel below
+    }
     const unsigned z = (unsigned)batch;
     const long long c64 = ((n + 63) / 64) * ((m + 63) / 64) * batch, c6432 = ((n + 31) / 32) * ((m + 63) / 64) * batch;
     if (c64 >= 148) {

@@ -1,0 +1,293 @@
+// nn.Linear on the 5th-gen tensor cores: Y[M,N] = X[M,K] . W[N,K]^T + b (optional ReLU), fp32 in / fp32 out.
+//
+// The reference's Linears are true fp32 (torch default allow_tf32=False), so the product is computed with the
+// error-compensated 3xTF32 scheme: x = x_hi + x_lo, w = w_hi + w_lo (hi = top 19 bits), D += x_hi w_hi + x_hi w_lo +
+// x_lo w_hi with fp32 accumulation in TMEM (~1e-6 relative, same as an fp32 FMA chain).
+//
+// One CTA per 128 x BN output tile (BN = min(N,128)), K in chunks of 32 floats (one 128-byte swizzle row):
+//   warp 0      TMA producer : cp.async.bulk.tensor.2d (UTMALDG) of the raw X tile (128 x 32) and W tile (BN x 32) through
+//                              SWIZZLE_128B tensor maps; out-of-bounds rows/columns are zero-filled by the TMA unit
+//   warps 1-4   splitters    : in-place hi = tf32_rn(x), lo = x - hi into a second buffer (generic proxy ->
+//                              fence.proxy.async), so the MMA sees exact tf32 operands
+//   warp 5      MMA issuer   : tcgen05.mma.cta_group::1.kind::tf32 M128 N{BN} K8, 3 per K-step; tcgen05.commit frees the stage
+//   warps 6-9   epilogue     : tcgen05.ld 32x32b, + bias, ReLU, direct row-segment stores (each thread owns one output row)
+#include <cuda.h>
+
+#include "common.cuh"
+#include "geob200.h"
+
+namespace geob200 {
+namespace ltc {
+
+constexpr int BM = 128;
+constexpr int KC = 32;
+constexpr int TILE_A = BM * 128;       // 16 KB
+constexpr int TILE_B = 128 * 128;      // 16 KB (BN <= 128 rows)
+constexpr int STAGE = 2 * TILE_A + 2 * TILE_B;   // raw/hi + lo for both operands = 64 KB
+constexpr int NSTAGE = 3;
+constexpr int NTHREADS = 320;
+constexpr int SMEM = NSTAGE * STAGE + 1024 + 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(addr), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {   // K-major SWIZZLE_128B, SBO = 1024 B (see gse_tc.cu)
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const __grid_constant__ CUtensorMap map_x,
+                                                                const __grid_constant__ CUtensorMap map_w,
+                                                                const float* __restrict__ bias, float* __restrict__ Y, int ldy, int M,
+                                                                int N, int K, int BN, int relu) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = (uint64_t*)(smem + NSTAGE * STAGE);
+    uint64_t* raw_full = bars;                  // TMA landed
+    uint64_t* split_full = bars + NSTAGE;       // hi/lo ready
+    uint64_t* empty = bars + 2 * NSTAGE;        // MMAs done with the stage
+    uint64_t* acc_full = bars + 3 * NSTAGE;
+    uint32_t* tmem_slot = (uint32_t*)(acc_full + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int nk = (K + KC - 1) / KC;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&split_full[s], 4); mbar_init(&empty[s], 1); }
+        mbar_init(acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    }
+    if (warp == 5) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int kc = 0; kc < nk; ++kc) {
+                mbar_wait(&empty[s], ph ^ 1u);
+                unsigned char* st = smem + s * STAGE;
+                mbar_arrive_expect_tx(&raw_full[s], (uint32_t)(TILE_A + BN * 128));
+                tma_load_2d(st, &map_x, kc * KC, m0, &raw_full[s]);
+                tma_load_2d(st + 2 * TILE_A, &map_w, kc * KC, n0, &raw_full[s]);
+                if (++s == NSTAGE) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp <= 4) {
+        const int t = threadIdx.x - 32;              // 0..127
+        int s = 0;
+        uint32_t ph = 0;
+        for (int kc = 0; kc < nk; ++kc) {
+            mbar_wait(&raw_full[s], ph);
+            unsigned char* st = smem + s * STAGE;
+            // element-wise, so the swizzled positions are irrelevant: same offset in the hi and lo buffers
+            const int nvec_a = TILE_A / 16, nvec_b = BN * 128 / 16;
+            for (int v = t; v < nvec_a + nvec_b; v += 128) {
+                unsigned char* p = (v < nvec_a) ? (st + v * 16) : (st + 2 * TILE_A + (v - nvec_a) * 16);
+                unsigned char* pl = p + ((v < nvec_a) ? TILE_A : TILE_B);
+                float4 x = *reinterpret_cast<float4*>(p);
+                float4 hi, lo;
+                hi.x = tf32_rn(x.x); lo.x = x.x - hi.x;     // round-to-nearest split: |lo| <= 2^-12 |x|, unbiased
+                hi.y = tf32_rn(x.y); lo.y = x.y - hi.y;
+                hi.z = tf32_rn(x.z); lo.z = x.z - hi.z;
+                hi.w = tf32_rn(x.w); lo.w = x.w - hi.w;
+                *reinterpret_cast<float4*>(p) = hi;
+                *reinterpret_cast<float4*>(pl) = lo;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&split_full[s]);
+            if (++s == NSTAGE) { s = 0; ph ^= 1u; }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            int s = 0;
+            uint32_t ph = 0;
+            for (int kc = 0; kc < nk; ++kc) {
+                mbar_wait(&split_full[s], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t st = smem_u32(smem + s * STAGE);
+                const uint64_t a_hi = make_desc(st), a_lo = make_desc(st + TILE_A);
+                const uint64_t b_hi = make_desc(st + 2 * TILE_A), b_lo = make_desc(st + 2 * TILE_A + TILE_B);
+#pragma unroll
+                for (int kk = 0; kk < KC / 8; ++kk) {
+                    const uint64_t adv = (uint64_t)(kk * 2);
+                    // main products and the (2^-11 smaller) correction products go to separate accumulators (columns
+                    // [0,128) and [128,256)): the fp32 accumulation in the tensor core truncates, so keeping the number of
+                    // additions into the main accumulator at K/8 instead of 3K/8 cuts the systematic error by 3x
+                    const uint32_t first = (kc == 0 && kk == 0) ? 0u : 1u;
+                    umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, first);
+                    umma_tf32(tmem_base + 128, a_hi + adv, b_lo + adv, idesc, first);
+                    umma_tf32(tmem_base + 128, a_lo + adv, b_hi + adv, idesc, 1u);
+                }
+                umma_commit(&empty[s]);
+                if (++s == NSTAGE) { s = 0; ph ^= 1u; }
+            }
+            umma_commit(acc_full);
+        }
+    } else {
+        const int q = warp & 3;
+        mbar_wait(acc_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int m = m0 + q * 32 + lane;
+        for (int cc = 0; cc < BN; cc += 32) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                  "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+                  "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+                  "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr));
+            uint32_t w2[32];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(w2[0]), "=r"(w2[1]), "=r"(w2[2]), "=r"(w2[3]), "=r"(w2[4]), "=r"(w2[5]), "=r"(w2[6]), "=r"(w2[7]), "=r"(w2[8]),
+                  "=r"(w2[9]), "=r"(w2[10]), "=r"(w2[11]), "=r"(w2[12]), "=r"(w2[13]), "=r"(w2[14]), "=r"(w2[15]), "=r"(w2[16]),
+                  "=r"(w2[17]), "=r"(w2[18]), "=r"(w2[19]), "=r"(w2[20]), "=r"(w2[21]), "=r"(w2[22]), "=r"(w2[23]), "=r"(w2[24]),
+                  "=r"(w2[25]), "=r"(w2[26]), "=r"(w2[27]), "=r"(w2[28]), "=r"(w2[29]), "=r"(w2[30]), "=r"(w2[31])
+                : "r"(taddr + 128));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int c = 0; c < 32; ++c) v[c] = __float_as_uint(__uint_as_float(v[c]) + __uint_as_float(w2[c]));
+            if (m < M) {
+                float* yr = Y + (long long)m * ldy + n0 + cc;
+                const int nvalid = min(32, N - (n0 + cc));
+                if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(yr) & 15) == 0)) {
+#pragma unroll
+                    for (int c = 0; c < 32; c += 4) {
+                        float4 o;
+                        o.x = __uint_as_float(v[c]) + (bias ? __ldg(bias + n0 + cc + c) : 0.f);
+                        o.y = __uint_as_float(v[c + 1]) + (bias ? __ldg(bias + n0 + cc + c + 1) : 0.f);
+                        o.z = __uint_as_float(v[c + 2]) + (bias ? __ldg(bias + n0 + cc + c + 2) : 0.f);
+                        o.w = __uint_as_float(v[c + 3]) + (bias ? __ldg(bias + n0 + cc + c + 3) : 0.f);
+                        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                        *reinterpret_cast<float4*>(yr + c) = o;
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c)
+                        if (c < nvalid) {
+                            float o = __uint_as_float(v[c]) + (bias ? __ldg(bias + n0 + cc + c) : 0.f);
+                            if (relu) o = fmaxf(o, 0.f);
+                            yr[c] = o;
+                        }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 5) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+// cuTensorMapEncodeTiled is fetched through the runtime (cudaGetDriverEntryPoint) so that libgeob200.so does not link
+// libcuda directly and still loads on a machine without a driver (the no-GPU ABI tests).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+static int encode_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (fn == nullptr) { set_error("cuTensorMapEncodeTiled entry point not available"); return -1; }
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return -1; }
+    return 0;
+}
+
+}  // namespace ltc
+
+// returns 1 when the shape/alignment is not handled by the tensor-core path (caller falls back to the fp32 kernel)
+int linear_tc(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, float* y, int64_t ldy, int64_t m, int64_t n,
+              int64_t k, int relu, cudaStream_t st) {
+    if (m < 64 || n < 32 || (n % 16) != 0 || (k % 4) != 0 || (ldx % 4) != 0 || (ldw % 4) != 0) return 1;
+    if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15)) return 1;
+    if (n > 128 && (n % 128) != 0) return 1;
+    const int BN = (int)(n >= 128 ? 128 : n);
+    CUtensorMap mx, mw;
+    if (ltc::encode_map(&mx, x, m, k, ldx, ltc::BM)) return -1;
+    if (ltc::encode_map(&mw, w, n, k, ldw, BN)) return -1;
+    static bool set = false;
+    if (!set) {
+        GEOB_CHECK_CUDA(cudaFuncSetAttribute(ltc::linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ltc::SMEM));
+        set = true;
+    }
+    dim3 grid((unsigned)(n / BN), (unsigned)((m + ltc::BM - 1) / ltc::BM));
+    ltc::linear_tc_kernel<<<grid, ltc::NTHREADS, ltc::SMEM, st>>>(mx, mw, bias, y, (int)ldy, (int)m, (int)n, (int)k, BN, relu);
+    GEOB_CHECK_LAUNCH();
+    count_launches(1);
+    return 0;
+}
+
+}  // namespace geob200

@@ -60,6 +60,8 @@ int geob200_kpconv(const float* s_feats, const float* q_points, const float* s_p
 
 /* nn.Linear: y[m,n] = x[m,k] . weight[n,k]^T + bias (UnaryBlock.mlp, modules.py:78; every transformer Linear).
  * ldx / ldy are row strides in floats (inputs may be column slices). */
+/* 1 (default): Linears run on tcgen05 with 3xTF32 when the shape allows; 0: fp32 CUDA cores only */
+void geob200_set_linear_mode(int mode);
 int geob200_linear(const float* x, int64_t ldx, const float* weight, const float* bias, float* y, int64_t ldy, int64_t m,
                    int64_t n, int64_t k, int relu, void* stream);
 int geob200_linear_batched(const float* x, int64_t ldx, int64_t stride_x, const float* weight, int64_t ldw, int64_t stride_w,

@@ -114,8 +114,6 @@ def test_forward_matches_reference(workload, cfg_name, golden, models):
     if not only:
         assert np.array_equal(out['ref_corr_points'].cpu().numpy(), gold['ref_corr_points'])      # same order too
     T = out['estimated_transform'].cpu().numpy()
-    if not only:
-        assert np.abs(T - gold['estimated_transform']).max() < 1e-4, f'transform\n{T}\nvs\n{gold["estimated_transform"]}'
     # LGR given OUR assignment matrix must agree with the oracle run on the very same matrix (hypothesis selection by
     # inlier count is discontinuous: one borderline correspondence can legitimately change the winning hypothesis on a
     # near-symmetric shape such as the ModelNet-shape sphere, so the fixture comparison above is only made when the
@@ -147,6 +145,8 @@ def test_forward_matches_reference(workload, cfg_name, golden, models):
     o_best = int(valid[int(otaps['best_index'])])
     if best == o_best:
         assert (o_T - T2.cpu()).abs().max() < 1e-4, f'{o_T} vs {T2}'
+        if not only:    # same correspondences and same winning hypothesis as the reference run: same transform
+            assert np.abs(T - gold['estimated_transform']).max() < 1e-4, f'transform\n{T}\nvs\n{gold["estimated_transform"]}'
     else:
         # either two hypotheses within the count noise, or the oracle's winner is one of the ill-conditioned patches
         # (its fp32 LAPACK Kabsch solution differs from our double-precision one by more than 1e-3)
