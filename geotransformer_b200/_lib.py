@@ -33,6 +33,8 @@ _sig('geob200_radius_search', c_int, P, I64, P, I64, P, P, I64, F, I64, P, P, P,
 
 _sig('geob200_kpconv_workspace_bytes', SZ, I64)
 _sig('geob200_kpconv', c_int, P, P, P, P, I64, I64, I64, P, I64, P, P, I64, I64, F, P, P, SZ, P)
+_sig('geob200_kpconv_tc_workspace_bytes', SZ, I64, I64, I64)
+_sig('geob200_kpconv_tc', c_int, P, P, P, P, I64, I64, I64, P, I64, P, P, I64, I64, F, P, P, SZ, P)
 _sig('geob200_set_linear_mode', None, c_int)
 _sig('geob200_linear', c_int, P, I64, P, P, P, I64, I64, I64, I64, c_int, P)
 _sig('geob200_linear_batched', c_int, P, I64, I64, P, I64, I64, P, I64, P, I64, I64, I64, I64, I64, I64, c_int, P)

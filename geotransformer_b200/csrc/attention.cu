@@ -23,10 +23,11 @@ constexpr int ATT_R = 2;
 constexpr int ATT_KPT = 2;
 constexpr int ATT_MAXH = 8;
 
+template <int H>
 __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk,
                                                         const float* __restrict__ v, int ldv, const float* __restrict__ qp,
                                                         const float* __restrict__ qb, const float* __restrict__ E, int N, int M,
-                                                        int C, int H, float div, float* __restrict__ out, int ldo) {
+                                                        int C, float div, float* __restrict__ out, int ldo) {
     extern __shared__ float sm[];
     float* q_s = sm;                            // [R][C]
     float* qp_s = q_s + ATT_R * C;              // [R][H][C]
@@ -51,13 +52,13 @@ __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict_
         bool ok[ATT_KPT];
 #pragma unroll
         for (int u = 0; u < ATT_KPT; ++u) { mk[u] = mb + u * 32 + lane; ok[u] = mk[u] < M; if (!ok[u]) mk[u] = M - 1; }
+        float tot[ATT_KPT][ATT_R][H];
+        // q . k : every channel belongs to exactly one head
+#pragma unroll
         for (int h = 0; h < H; ++h) {
-            float aq[ATT_KPT][ATT_R], ae[ATT_KPT][ATT_R];
+            float aq[ATT_KPT][ATT_R];
 #pragma unroll
-            for (int u = 0; u < ATT_KPT; ++u)
-#pragma unroll
-                for (int r = 0; r < ATT_R; ++r) { aq[u][r] = 0.f; ae[u][r] = 0.f; }
-            // q . k over this head's channels
+            for (int u = 0; u < ATT_KPT; ++u) { aq[u][0] = 0.f; aq[u][1] = 0.f; }
             for (int c = h * d; c < (h + 1) * d; c += 4) {
                 const float4 q0 = *reinterpret_cast<const float4*>(q_s + c);
                 const float4 q1 = *reinterpret_cast<const float4*>(q_s + C + c);
@@ -68,40 +69,54 @@ __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict_
                     aq[u][1] = fmaf(kv.x, q1.x, fmaf(kv.y, q1.y, fmaf(kv.z, q1.z, fmaf(kv.w, q1.w, aq[u][1]))));
                 }
             }
-            // (Wp_h^T q_h) . E[n, m, :] over ALL channels
-            if (has_e) {
-                const float* w0 = qp_s + (0 * H + h) * C;
-                const float* w1 = qp_s + (1 * H + h) * C;
-                const float* e00 = E + ((long long)n0 * M + mk[0]) * C;
-                const float* e01 = E + ((long long)n0 * M + mk[1]) * C;
-                const float* e10 = E + ((long long)(n0 + r1ok) * M + mk[0]) * C;
-                const float* e11 = E + ((long long)(n0 + r1ok) * M + mk[1]) * C;
-#pragma unroll 4
-                for (int c = 0; c < C; c += 4) {
-                    const float4 a0 = *reinterpret_cast<const float4*>(w0 + c);
-                    const float4 a1 = *reinterpret_cast<const float4*>(w1 + c);
-                    const float4 x00 = __ldg(reinterpret_cast<const float4*>(e00 + c));
-                    const float4 x01 = __ldg(reinterpret_cast<const float4*>(e01 + c));
-                    const float4 x10 = __ldg(reinterpret_cast<const float4*>(e10 + c));
-                    const float4 x11 = __ldg(reinterpret_cast<const float4*>(e11 + c));
-                    ae[0][0] = fmaf(x00.x, a0.x, fmaf(x00.y, a0.y, fmaf(x00.z, a0.z, fmaf(x00.w, a0.w, ae[0][0]))));
-                    ae[1][0] = fmaf(x01.x, a0.x, fmaf(x01.y, a0.y, fmaf(x01.z, a0.z, fmaf(x01.w, a0.w, ae[1][0]))));
-                    ae[0][1] = fmaf(x10.x, a1.x, fmaf(x10.y, a1.y, fmaf(x10.z, a1.z, fmaf(x10.w, a1.w, ae[0][1]))));
-                    ae[1][1] = fmaf(x11.x, a1.x, fmaf(x11.y, a1.y, fmaf(x11.z, a1.z, fmaf(x11.w, a1.w, ae[1][1]))));
+#pragma unroll
+            for (int u = 0; u < ATT_KPT; ++u) { tot[u][0][h] = aq[u][0]; tot[u][1][h] = aq[u][1]; }
+        }
+        // (Wp_h^T q_h) . E[n, m, :] : E is read ONCE and contracted with the H projected queries
+        if (has_e) {
+            float ae[ATT_KPT][ATT_R][H];
+#pragma unroll
+            for (int u = 0; u < ATT_KPT; ++u)
+#pragma unroll
+                for (int r = 0; r < ATT_R; ++r)
+#pragma unroll
+                    for (int h = 0; h < H; ++h) ae[u][r][h] = 0.f;
+            const float* e00 = E + ((long long)n0 * M + mk[0]) * C;
+            const float* e01 = E + ((long long)n0 * M + mk[1]) * C;
+            const float* e10 = E + ((long long)(n0 + r1ok) * M + mk[0]) * C;
+            const float* e11 = E + ((long long)(n0 + r1ok) * M + mk[1]) * C;
+#pragma unroll 2
+            for (int c = 0; c < C; c += 4) {
+                const float4 x00 = __ldg(reinterpret_cast<const float4*>(e00 + c));
+                const float4 x01 = __ldg(reinterpret_cast<const float4*>(e01 + c));
+                const float4 x10 = __ldg(reinterpret_cast<const float4*>(e10 + c));
+                const float4 x11 = __ldg(reinterpret_cast<const float4*>(e11 + c));
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+                    const float4 a0 = *reinterpret_cast<const float4*>(qp_s + (0 * H + h) * C + c);
+                    const float4 a1 = *reinterpret_cast<const float4*>(qp_s + (1 * H + h) * C + c);
+                    ae[0][0][h] = fmaf(x00.x, a0.x, fmaf(x00.y, a0.y, fmaf(x00.z, a0.z, fmaf(x00.w, a0.w, ae[0][0][h]))));
+                    ae[1][0][h] = fmaf(x01.x, a0.x, fmaf(x01.y, a0.y, fmaf(x01.z, a0.z, fmaf(x01.w, a0.w, ae[1][0][h]))));
+                    ae[0][1][h] = fmaf(x10.x, a1.x, fmaf(x10.y, a1.y, fmaf(x10.z, a1.z, fmaf(x10.w, a1.w, ae[0][1][h]))));
+                    ae[1][1][h] = fmaf(x11.x, a1.x, fmaf(x11.y, a1.y, fmaf(x11.z, a1.z, fmaf(x11.w, a1.w, ae[1][1][h]))));
                 }
             }
 #pragma unroll
             for (int u = 0; u < ATT_KPT; ++u)
-                if (ok[u]) {
 #pragma unroll
-                    for (int r = 0; r < ATT_R; ++r) {
-                        const int n = n0 + r;
-                        float tot = aq[u][r];
-                        if (has_e && n < N) tot += ae[u][r] + qb[(long long)n * H + h];
-                        sc[(r * H + h) * M + mk[u]] = tot / div;
-                    }
-                }
+                for (int r = 0; r < ATT_R; ++r)
+#pragma unroll
+                    for (int h = 0; h < H; ++h)
+                        if (n0 + r < N) tot[u][r][h] += ae[u][r][h] + qb[(long long)(n0 + r) * H + h];
         }
+#pragma unroll
+        for (int u = 0; u < ATT_KPT; ++u)
+            if (ok[u]) {
+#pragma unroll
+                for (int r = 0; r < ATT_R; ++r)
+#pragma unroll
+                    for (int h = 0; h < H; ++h) sc[(r * H + h) * M + mk[u]] = tot[u][r][h] / div;
+            }
     }
     __syncthreads();
     // softmax over m, one warp per (row, head)
@@ -210,13 +225,25 @@ int geob200_attention(const float* q, int64_t ldq, const float* k, int64_t ldk, 
     GEOB_REQUIRE(smem <= 200 * 1024, "attention: too many keys (%lld)", (long long)n_key);
     static size_t smem_set = 0;
     if (smem > 48 * 1024 && smem > smem_set) {
-        GEOB_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GEOB_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GEOB_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GEOB_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GEOB_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
     const float div = sqrtf((float)(channels / heads));   // d_model_per_head ** 0.5
-    attention_kernel<<<(unsigned)((n_query + ATT_R - 1) / ATT_R), 256, smem, st>>>(q, (int)ldq, k, (int)ldk, v, (int)ldv, qp, qb, embed,
-                                                                                  (int)n_query, (int)n_key, (int)channels, (int)heads,
-                                                                                  div, out, (int)ldo);
+    const unsigned grid = (unsigned)((n_query + ATT_R - 1) / ATT_R);
+#define LAUNCH_ATT(HV)                                                                                                              \
+    attention_kernel<HV><<<grid, 256, smem, st>>>(q, (int)ldq, k, (int)ldk, v, (int)ldv, qp, qb, embed, (int)n_query, (int)n_key,  \
+                                                  (int)channels, div, out, (int)ldo)
+    switch (heads) {
+        case 1: LAUNCH_ATT(1); break;
+        case 2: LAUNCH_ATT(2); break;
+        case 4: LAUNCH_ATT(4); break;
+        case 8: LAUNCH_ATT(8); break;
+        default: GEOB_REQUIRE(false, "attention: heads must be 1, 2, 4 or 8");
+    }
+#undef LAUNCH_ATT
     GEOB_CHECK_LAUNCH();
     count_launches(1);
     return 0;

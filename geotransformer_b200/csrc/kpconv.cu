@@ -93,6 +93,75 @@ __global__ void __launch_bounds__(256) row_positive_kernel(const float* __restri
     if (lane == 0) pos[n] = (s > 0.f) ? 1 : 0;
 }
 
+// KPConv, stage 1 of 2 (tensor-core path): wf[m][k*Cin + c] = sum_h influence[m][h][k] * f[nbr[m][h]][c]   (kpconv.py:91-105)
+// One warp per query point, small shared-memory footprint (many resident warps hide the gather latency); the neighbour
+// rows are fetched eight at a time.  Also emits inv_count[m] = 1 / max(#neighbours with a positive feature sum, 1)
+// (kpconv.py:113-116).  Stage 2 is the 3xTF32 tcgen05 GEMM wf (M x 15 Cin) . W (15 Cin x Cout) with the per-row scale and the
+// bias applied in its epilogue (linear_tc.cu).
+__global__ void __launch_bounds__(256) kpconv_gather_kernel(const float* __restrict__ feats, const unsigned char* __restrict__ pos,
+                                                            const float* __restrict__ q_pts, const float* __restrict__ s_pts,
+                                                            const long long* __restrict__ nbr, int H, const float* __restrict__ kp,
+                                                            float sigma, int Ns, int M, int Cin, float* __restrict__ wf,
+                                                            float* __restrict__ inv_count) {
+    __shared__ float infl[8][32][KP_PAD];
+    __shared__ int sidx[8][32];
+    __shared__ float kp_s[KP * 3];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < KP * 3) kp_s[threadIdx.x] = kp[threadIdx.x];
+    __syncthreads();
+    const int m = blockIdx.x * 8 + warp;
+    if (m >= M) return;
+    const float qx = q_pts[3ll * m], qy = q_pts[3ll * m + 1], qz = q_pts[3ll * m + 2];
+    int npos = 0;
+    for (int c0 = 0; c0 < Cin; c0 += 32) {
+        float acc[KP];
+#pragma unroll
+        for (int k = 0; k < KP; ++k) acc[k] = 0.f;
+        for (int h0 = 0; h0 < H; h0 += 32) {
+            const int h = h0 + lane;
+            const long long idx = (h < H) ? nbr[(long long)m * H + h] : (long long)Ns;
+            float w[KP];
+            int id = 0;
+            if (idx < Ns) {
+                id = (int)idx;
+                influence15(kp_s, s_pts[3 * idx] - qx, s_pts[3 * idx + 1] - qy, s_pts[3 * idx + 2] - qz, 0.f, sigma, w);
+                if (c0 == 0) npos += pos[idx];
+            } else {
+#pragma unroll
+                for (int k = 0; k < KP; ++k) w[k] = 0.f;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < KP; ++k) infl[warp][lane][k] = w[k];
+            infl[warp][lane][KP] = 0.f;
+            sidx[warp][lane] = id;
+            __syncwarp();
+            const int hn = min(32, H - h0);
+            for (int hb = 0; hb < hn; hb += 8) {
+                float f[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) f[u] = __ldg(feats + (long long)sidx[warp][(hb + u) & 31] * Cin + c0 + lane);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (hb + u < hn) {
+                        const float4* iv = reinterpret_cast<const float4*>(&infl[warp][hb + u][0]);
+                        const float4 a0 = iv[0], a1 = iv[1], a2 = iv[2], a3 = iv[3];
+                        const float wv[16] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w, a3.x, a3.y, a3.z, a3.w};
+#pragma unroll
+                        for (int k = 0; k < KP; ++k) acc[k] = fmaf(wv[k], f[u], acc[k]);
+                    }
+                }
+            }
+        }
+        float* wrow = wf + (long long)m * (KP * Cin) + c0 + lane;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) wrow[(long long)k * Cin] = acc[k];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) npos += __shfl_xor_sync(0xffffffffu, npos, o);
+    if (lane == 0) inv_count[m] = 1.0f / (float)max(npos, 1);
+}
+
 // General KPConv, Cin % 32 == 0 and Cout % 32 == 0 (mid channels 32..512 of the bottleneck blocks).
 // RC = output columns per lane handled by this CTA (the CTA owns columns [col0, col0 + 32*RC)).
 // Input channels are processed in chunks of CC = 32 (one float per lane per neighbour row): the tile
@@ -337,6 +406,37 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
     const int cpg = C / G;
     const int rows_per_blk = (N + gridDim.x - 1) / gridDim.x;
     const int r0 = blockIdx.x * rows_per_blk, r1 = min(N, r0 + rows_per_blk);
+    const int C4 = C >> 2;
+    if (C4 <= 256 && (256 % C4) == 0) {
+        // vectorised: thread t owns the 4 channels 4*(t % C4).. and walks rows r0 + t / C4, stride 256 / C4, four rows in flight
+        const int cg = threadIdx.x % C4, rstep = 256 / C4;
+        double s[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
+        const float4* xv = reinterpret_cast<const float4*>(x);
+        int r = r0 + threadIdx.x / C4;
+        for (; r + 3 * rstep < r1; r += 4 * rstep) {
+            const float4 a = xv[(long long)r * C4 + cg], b = xv[(long long)(r + rstep) * C4 + cg];
+            const float4 c = xv[(long long)(r + 2 * rstep) * C4 + cg], d = xv[(long long)(r + 3 * rstep) * C4 + cg];
+            s[0] += ((double)a.x + (double)b.x) + ((double)c.x + (double)d.x);
+            s[1] += ((double)a.y + (double)b.y) + ((double)c.y + (double)d.y);
+            s[2] += ((double)a.z + (double)b.z) + ((double)c.z + (double)d.z);
+            s[3] += ((double)a.w + (double)b.w) + ((double)c.w + (double)d.w);
+            s2[0] += ((double)a.x * a.x + (double)b.x * b.x) + ((double)c.x * c.x + (double)d.x * d.x);
+            s2[1] += ((double)a.y * a.y + (double)b.y * b.y) + ((double)c.y * c.y + (double)d.y * d.y);
+            s2[2] += ((double)a.z * a.z + (double)b.z * b.z) + ((double)c.z * c.z + (double)d.z * d.z);
+            s2[3] += ((double)a.w * a.w + (double)b.w * b.w) + ((double)c.w * c.w + (double)d.w * d.w);
+        }
+        for (; r < r1; r += rstep) {
+            const float4 a = xv[(long long)r * C4 + cg];
+            s[0] += a.x; s[1] += a.y; s[2] += a.z; s[3] += a.w;
+            s2[0] += (double)a.x * a.x; s2[1] += (double)a.y * a.y; s2[2] += (double)a.z * a.z; s2[3] += (double)a.w * a.w;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int g = (4 * cg + u) / cpg;
+            atomicAdd(&sh[2 * g], s[u]);
+            atomicAdd(&sh[2 * g + 1], s2[u]);
+        }
+    } else
     // thread t walks channel c = t % C (C <= 256 -> several rows in flight per CTA; C > 256 -> loop)
     if (C <= 256) {
         const int rpb = 256 / C;               // rows processed concurrently
@@ -469,8 +569,8 @@ __global__ void __launch_bounds__(256) upsample_concat_kernel(const float* __res
 using namespace geob200;
 
 namespace geob200 {
-int linear_tc(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, float* y, int64_t ldy, int64_t m, int64_t n,
-              int64_t k, int relu, cudaStream_t st);   // linear_tc.cu
+int linear_tc(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, const float* row_scale, float* y, int64_t ldy,
+              int64_t m, int64_t n, int64_t k, int relu, cudaStream_t st);   // linear_tc.cu
 static int g_linear_mode = 1;   // 1 = tcgen05 3xTF32 where the shape allows, 0 = fp32 CUDA cores only
 }
 
@@ -479,6 +579,37 @@ extern "C" {
 void geob200_set_linear_mode(int mode) { g_linear_mode = mode; }
 
 size_t geob200_kpconv_workspace_bytes(int64_t n_support) { return (size_t)n_support + 256; }
+
+// Tensor-core KPConv: gather stage + 3xTF32 GEMM.  weights_t = weights viewed as (15*c_in, c_out), transposed to (c_out, 15*c_in).
+// workspace: n_support bytes (positivity flags) + n_query floats (row scales) + n_query*15*c_in floats (gathered features).
+size_t geob200_kpconv_tc_workspace_bytes(int64_t n_query, int64_t n_support, int64_t c_in) {
+    return align_up((size_t)n_support, 256) + align_up((size_t)n_query * 4, 256) + (size_t)n_query * KP * (size_t)c_in * 4 + 1024;
+}
+
+int geob200_kpconv_tc(const float* s_feats, const float* q_points, const float* s_points, const int64_t* neighbors, int64_t n_query,
+                      int64_t n_support, int64_t n_neighbors, const float* kernel_points, int64_t n_kernel, const float* weights_t,
+                      const float* bias, int64_t c_in, int64_t c_out, float sigma, float* out, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    GEOB_REQUIRE(n_kernel == KP, "kpconv_tc: kernel_size %lld unsupported", (long long)n_kernel);
+    GEOB_REQUIRE(n_query > 0 && n_support > 0 && n_neighbors > 0, "kpconv_tc: empty input");
+    GEOB_REQUIRE(c_in % 32 == 0 && c_out % 16 == 0 && c_out >= 32 && (c_out <= 128 || c_out % 128 == 0) && n_query >= 64,
+                 "kpconv_tc: unsupported shape (%lld -> %lld, %lld queries)", (long long)c_in, (long long)c_out, (long long)n_query);
+    GEOB_REQUIRE(workspace_bytes >= geob200_kpconv_tc_workspace_bytes(n_query, n_support, c_in), "kpconv_tc: workspace too small");
+    Arena ar(workspace, workspace_bytes);
+    unsigned char* pos = ar.take<unsigned char>(n_support);
+    float* inv_count = ar.take<float>(n_query);
+    float* wf = ar.take<float>((size_t)n_query * KP * c_in);
+    row_positive_kernel<<<(unsigned)((n_support + 7) / 8), 256, 0, st>>>(s_feats, (int)n_support, (int)c_in, pos);
+    kpconv_gather_kernel<<<(unsigned)((n_query + 7) / 8), 256, 0, st>>>(s_feats, pos, q_points, s_points, (const long long*)neighbors,
+                                                                       (int)n_neighbors, kernel_points, sigma, (int)n_support,
+                                                                       (int)n_query, (int)c_in, wf, inv_count);
+    GEOB_CHECK_LAUNCH();
+    count_launches(2);
+    const int rc = linear_tc(wf, KP * c_in, weights_t, KP * c_in, bias, inv_count, out, c_out, n_query, c_out, KP * c_in, 0, st);
+    GEOB_REQUIRE(rc == 0, "kpconv_tc: tensor-core GEMM rejected the shape");
+    return 0;
+}
 
 int geob200_kpconv(const float* s_feats, const float* q_points, const float* s_points, const int64_t* neighbors,
                    int64_t n_query, int64_t n_support, int64_t n_neighbors, const float* kernel_points, int64_t n_kernel,
@@ -539,7 +670,7 @@ int geob200_linear_batched(const float* x, int64_t ldx, int64_t stride_x, const 
     cudaStream_t st = (cudaStream_t)stream;
     GEOB_REQUIRE(m > 0 && n > 0 && k > 0 && batch > 0, "linear: empty problem");
     if (batch == 1 && g_linear_mode == 1) {
-        const int rc = linear_tc(x, ldx, weight, ldw, bias, y, ldy, m, n, k, relu, st);
+        const int rc = linear_tc(x, ldx, weight, ldw, bias, nullptr, y, ldy, m, n, k, relu, st);
         if (rc <= 0) return rc;       // done (0) or hard error (<0); 1 = shape not handled -> fp32 kernel below
     }
     const unsigned z = (unsigned)batch;
@@ -580,8 +711,8 @@ int geob200_group_norm(const float* x, int64_t n_rows, int64_t channels, int64_t
     unsigned* ticket = ar.take<unsigned>(64);           // must be zero on first use: caller provides zeroed ws once
     float* mean_rstd = ar.take<float>(2 * groups);
     double* partial = ar.take<double>(592 * 2 * groups);
-    int nblk = (int)((n_rows + 63) / 64);
-    if (nblk > 592) nblk = 592;
+    int nblk = (int)((n_rows + 127) / 128);
+    if (nblk > 296) nblk = 296;
     if (nblk < 1) nblk = 1;
     gn_stats_kernel<<<nblk, 256, sizeof(double) * 2 * groups, st>>>(x, (int)n_rows, (int)channels, (int)groups, (double)eps,
                                                                     partial, ticket, mean_rstd);

@@ -77,8 +77,8 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 
 __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const __grid_constant__ CUtensorMap map_x,
                                                                 const __grid_constant__ CUtensorMap map_w,
-                                                                const float* __restrict__ bias, float* __restrict__ Y, int ldy, int M,
-                                                                int N, int K, int BN, int relu) {
+                                                                const float* __restrict__ bias, const float* __restrict__ row_scale,
+                                                                float* __restrict__ Y, int ldy, int M, int N, int K, int BN, int relu) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = (uint64_t*)(smem + NSTAGE * STAGE);
@@ -201,8 +201,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const __grid_con
                   "=r"(w2[25]), "=r"(w2[26]), "=r"(w2[27]), "=r"(w2[28]), "=r"(w2[29]), "=r"(w2[30]), "=r"(w2[31])
                 : "r"(taddr + 128));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const float rs = (row_scale != nullptr && m < M) ? row_scale[m] : 1.0f;   // KPConv: 1 / neighbour count
 #pragma unroll
-            for (int c = 0; c < 32; ++c) v[c] = __float_as_uint(__uint_as_float(v[c]) + __uint_as_float(w2[c]));
+            for (int c = 0; c < 32; ++c) v[c] = __float_as_uint((__uint_as_float(v[c]) + __uint_as_float(w2[c])) * rs);
             if (m < M) {
                 float* yr = Y + (long long)m * ldy + n0 + cc;
                 const int nvalid = min(32, N - (n0 + cc));
@@ -269,8 +270,8 @@ static int encode_map(CUtensorMap* map, const float* base, int64_t rows, int64_t
 }  // namespace ltc
 
 // returns 1 when the shape/alignment is not handled by the tensor-core path (caller falls back to the fp32 kernel)
-int linear_tc(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, float* y, int64_t ldy, int64_t m, int64_t n,
-              int64_t k, int relu, cudaStream_t st) {
+int linear_tc(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, const float* row_scale, float* y, int64_t ldy,
+              int64_t m, int64_t n, int64_t k, int relu, cudaStream_t st) {
     if (m < 64 || n < 32 || (n % 16) != 0 || (k % 4) != 0 || (ldx % 4) != 0 || (ldw % 4) != 0) return 1;
     if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15)) return 1;
     if (n > 128 && (n % 128) != 0) return 1;
@@ -284,7 +285,7 @@ int linear_tc(const float* x, int64_t ldx, const float* w, int64_t ldw, const fl
         set = true;
     }
     dim3 grid((unsigned)(n / BN), (unsigned)((m + ltc::BM - 1) / ltc::BM));
-    ltc::linear_tc_kernel<<<grid, ltc::NTHREADS, ltc::SMEM, st>>>(mx, mw, bias, y, (int)ldy, (int)m, (int)n, (int)k, BN, relu);
+    ltc::linear_tc_kernel<<<grid, ltc::NTHREADS, ltc::SMEM, st>>>(mx, mw, bias, row_scale, y, (int)ldy, (int)m, (int)n, (int)k, BN, relu);
     GEOB_CHECK_LAUNCH();
     count_launches(1);
     return 0;

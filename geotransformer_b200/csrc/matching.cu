@@ -307,27 +307,38 @@ __global__ void __launch_bounds__(1024) sinkhorn_kernel(const float* __restrict_
         lmu[i] = mu; lnu[i] = nu; u[i] = 0.f; v[i] = 0.f;
     }
     __syncthreads();
-    const int nwarp = blockDim.x >> 5;
+    // 8 lanes per row/column (4 rows per warp at once): 3-step shuffle reductions and ~K/8 independent exp per lane keep the
+    // dependent chain of one half-iteration short (the kernel is latency-, not throughput-bound)
+    const int nslot = (blockDim.x >> 5) * 4;
+    const int grp = lane >> 3, sub = lane & 7;
     for (int it = 0; it < iters; ++it) {
-        for (int i = warp; i < K1; i += nwarp) {
+        for (int base = warp * 4; base < K1; base += nslot) {     // warp-uniform trip count: every lane joins the shuffles
+            const bool act = base + grp < K1;
+            const int i = act ? base + grp : K1 - 1;
             const float* zr = Z + i * ld;
             float mx = -INFINITY;
-            for (int j = lane; j < K1; j += 32) mx = fmaxf(mx, zr[j] + v[j]);
-            mx = warp_max(mx);
+            for (int j = sub; j < K1; j += 8) mx = fmaxf(mx, zr[j] + v[j]);
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
             float s = 0.f;
-            for (int j = lane; j < K1; j += 32) s += expf(zr[j] + v[j] - mx);
-            s = warp_sum(s);
-            if (lane == 0) u[i] = lmu[i] - (logf(s) + mx);
+            for (int j = sub; j < K1; j += 8) s += expf(zr[j] + v[j] - mx);
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (act && sub == 0) u[i] = lmu[i] - (logf(s) + mx);
         }
         __syncthreads();
-        for (int j = warp; j < K1; j += nwarp) {
+        for (int base = warp * 4; base < K1; base += nslot) {
+            const bool act = base + grp < K1;
+            const int j = act ? base + grp : K1 - 1;
             float mx = -INFINITY;
-            for (int i = lane; i < K1; i += 32) mx = fmaxf(mx, Z[i * ld + j] + u[i]);
-            mx = warp_max(mx);
+            for (int i = sub; i < K1; i += 8) mx = fmaxf(mx, Z[i * ld + j] + u[i]);
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
             float s = 0.f;
-            for (int i = lane; i < K1; i += 32) s += expf(Z[i * ld + j] + u[i] - mx);
-            s = warp_sum(s);
-            if (lane == 0) v[j] = lnu[j] - (logf(s) + mx);
+            for (int i = sub; i < K1; i += 8) s += expf(Z[i * ld + j] + u[i] - mx);
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (act && sub == 0) v[j] = lnu[j] - (logf(s) + mx);
         }
         __syncthreads();
     }

@@ -61,7 +61,12 @@ def _gn_workspace(device, groups):
 
 # ------------------------------------------------------------------------------------------------ backbone
 
-def kpconv(s_feats, q_points, s_points, neighbor_indices, kernel_points, weights, bias, sigma):
+# KPConv formulation: 'tc' = gather kernel + tcgen05 3xTF32 GEMM (default where the shape allows), 'fused' = single fp32 kernel
+KPCONV_MODE = 'tc'
+
+
+def kpconv(s_feats, q_points, s_points, neighbor_indices, kernel_points, weights, bias, sigma, weights_t=None):
+    """weights_t: optional cached (c_out, 15*c_in) transpose of the weights for the tensor-core path"""
     s_feats, weights, bias = _detach(s_feats), _detach(weights), _detach(bias)
     _f(s_feats, 's_feats'); _f(q_points, 'q_points'); _f(s_points, 's_points')
     L.require_cuda(neighbor_indices, 'neighbor_indices', _i64)
@@ -70,6 +75,14 @@ def kpconv(s_feats, q_points, s_points, neighbor_indices, kernel_points, weights
     k, cin, cout = weights.shape
     out = torch.empty((m, cout), dtype=_f32, device=s_feats.device)
     lib = L.lib()
+    if (KPCONV_MODE == 'tc' and cin % 32 == 0 and cout % 16 == 0 and cout >= 32 and (cout <= 128 or cout % 128 == 0) and m >= 64):
+        if weights_t is None:
+            weights_t = weights.reshape(k * cin, cout).t().contiguous()
+        ws = L.workspace(lib.geob200_kpconv_tc_workspace_bytes(m, ns, cin), s_feats.device, 'kpconv_tc')
+        L.check(lib.geob200_kpconv_tc(s_feats.data_ptr(), q_points.data_ptr(), s_points.data_ptr(), neighbor_indices.data_ptr(), m, ns,
+                                      h, kernel_points.data_ptr(), k, weights_t.data_ptr(), L.ptr(bias), cin, cout, float(sigma),
+                                      out.data_ptr(), ws.data_ptr(), ws.numel(), L.stream_ptr()), 'kpconv_tc')
+        return out
     ws = L.workspace(lib.geob200_kpconv_workspace_bytes(ns), s_feats.device, 'kpconv')
     L.check(lib.geob200_kpconv(s_feats.data_ptr(), q_points.data_ptr(), s_points.data_ptr(),
                                neighbor_indices.data_ptr(), m, ns, h, kernel_points.data_ptr(), k,

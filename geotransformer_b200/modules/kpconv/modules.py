@@ -29,8 +29,13 @@ class KPConv(nn.Module):
         self.register_buffer('kernel_points', default_kernel_points(kernel_size, radius))
 
     def forward(self, s_feats, q_points, s_points, neighbor_indices):
+        w = self.weights
+        key = (w.data_ptr(), w._version)
+        if getattr(self, '_wt_key', None) != key:     # (c_out, 15*c_in) copy for the tensor-core GEMM, rebuilt if weights change
+            self._wt = w.detach().reshape(-1, w.shape[2]).t().contiguous()
+            self._wt_key = key
         return GF.kpconv(s_feats, q_points, s_points, neighbor_indices, self.kernel_points, self.weights, self.bias,
-                         self.sigma)
+                         self.sigma, weights_t=self._wt)
 
     def __repr__(self):
         return (f'KPConv(kernel_size: {self.kernel_size}, in_channels: {self.in_channels}, out_channels: '

@@ -60,6 +60,15 @@ int geob200_kpconv(const float* s_feats, const float* q_points, const float* s_p
 
 /* nn.Linear: y[m,n] = x[m,k] . weight[n,k]^T + bias (UnaryBlock.mlp, modules.py:78; every transformer Linear).
  * ldx / ldy are row strides in floats (inputs may be column slices). */
+/* Same op, two-stage tensor-core formulation: gather kernel (wf = influence-weighted neighbour features, M x 15 c_in) followed by
+ * the 3xTF32 tcgen05 GEMM with the neighbour-count scale and bias in its epilogue.  weights_t is the (15*c_in, c_out) weight
+ * matrix transposed to (c_out, 15*c_in). */
+size_t geob200_kpconv_tc_workspace_bytes(int64_t n_query, int64_t n_support, int64_t c_in);
+int geob200_kpconv_tc(const float* s_feats, const float* q_points, const float* s_points, const int64_t* neighbors, int64_t n_query,
+                      int64_t n_support, int64_t n_neighbors, const float* kernel_points, int64_t n_kernel, const float* weights_t,
+                      const float* bias, int64_t c_in, int64_t c_out, float sigma, float* out, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
 /* 1 (default): Linears run on tcgen05 with 3xTF32 when the shape allows; 0: fp32 CUDA cores only */
 void geob200_set_linear_mode(int mode);
 int geob200_linear(const float* x, int64_t ldx, const float* weight, const float* bias, float* y, int64_t ldy, int64_t m,
