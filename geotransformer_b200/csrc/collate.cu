@@ -408,7 +408,9 @@ struct RsCloud {
 
 // support bounding box -> uniform grid with cell >= 1.001 r, shrunk to the per-cloud cell budget
 __global__ void __launch_bounds__(1024) rs_bounds_kernel(const float* __restrict__ pts, const CloudSeg* __restrict__ segs,
-                                                         float radius, RsCloud* __restrict__ out) {
+                                                         float radius, RsCloud* __restrict__ out, CloudSeg* __restrict__ cell_segs,
+                                                         int* __restrict__ max_count) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *max_count = 0;
     const CloudSeg sg = segs[blockIdx.x];
     float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (int i = threadIdx.x; i < sg.len; i += blockDim.x) {
@@ -447,6 +449,8 @@ __global__ void __launch_bounds__(1024) rs_bounds_kernel(const float* __restrict
         c.cell = cell; c.cx = (int)cx; c.cy = (int)cy; c.cz = (int)cz;
         c.cell_base = 2 * sg.start + 1025 * blockIdx.x;   // budget+1 cells (one extra for the end offset)
         out[blockIdx.x] = c;
+        cell_segs[blockIdx.x].start = c.cell_base;
+        cell_segs[blockIdx.x].len = c.cx * c.cy * c.cz + 1;   // +1: the trailing entry receives the cloud total
     }
 }
 
@@ -663,9 +667,9 @@ int geob200_grid_subsample(const float* points, int64_t n_points, const int64_t*
     int* pt_slot = ar.take<int>(n);
     int* flag = ar.take<int>(n);
     int* rank = ar.take<int>(n);
-    int* vox_count = ar.take<int>(n);
+    int* vox_count = ar.take<int>(2 * n);      // [vox_count | vox_cursor], zeroed together
+    int* vox_cursor = vox_count + n;
     int* vox_off = ar.take<int>(n);
-    int* vox_cursor = ar.take<int>(n);
     int* vox_pts = ar.take<int>(n);
     int* cur = ar.take<int>(n);
     int* nxt = ar.take<int>(n);
@@ -685,8 +689,7 @@ int geob200_grid_subsample(const float* points, int64_t n_points, const int64_t*
 
     GEOB_CHECK_CUDA(cudaMemsetAsync(tab_key, 0xFF, 8 * 2 * n, st));
     GEOB_CHECK_CUDA(cudaMemsetAsync(tab_first, 0x7F, 4 * 2 * n, st));
-    GEOB_CHECK_CUDA(cudaMemsetAsync(vox_count, 0, 4 * n, st));
-    GEOB_CHECK_CUDA(cudaMemsetAsync(vox_cursor, 0, 4 * n, st));
+    GEOB_CHECK_CUDA(cudaMemsetAsync(vox_count, 0, 4 * 2 * n, st));
 
     const dim3 pgrid((max_len + 255) / 256, (unsigned)batch);
     gs_bounds_kernel<<<(unsigned)batch, 1024, 0, st>>>(points, segs, voxel, clouds);
@@ -711,7 +714,7 @@ size_t geob200_radius_search_workspace_bytes(int64_t n_query, int64_t n_support,
     size_t cells = 2 * ns + 1025 * b + 64;
     size_t bytes = 0;
     bytes += align_up(sizeof(CloudSeg) * b, 256) * 3 + align_up(sizeof(RsCloud) * b, 256);
-    bytes += align_up(4 * cells, 256) * 3;     // cnt, start, cursor
+    bytes += align_up(4 * cells, 256) * 3 + 1024;     // cnt, start, cursor (+ counters)
     bytes += align_up(4 * ns, 256);            // pt_cell
     bytes += align_up(16 * ns, 256);           // sorted float4
     bytes += align_up(4 * nq, 256);            // overflow list
@@ -738,13 +741,15 @@ int geob200_radius_search(const float* q_points, int64_t n_query, const float* s
     CloudSeg* s_segs = ar.take<CloudSeg>(batch);
     CloudSeg* cell_segs = ar.take<CloudSeg>(batch);
     RsCloud* clouds = ar.take<RsCloud>(batch);
-    int* cell_cnt = ar.take<int>(cells);
+    // one zero-filled block: [cell_cnt | cell_cursor | overflow counters]
+    int* zero_block = ar.take<int>(2 * cells + 64);
+    int* cell_cnt = zero_block;
+    int* cell_cursor = zero_block + cells;
+    int* overflow_n = zero_block + 2 * cells;
     int* cell_start = ar.take<int>(cells);
-    int* cell_cursor = ar.take<int>(cells);
     int* pt_cell = ar.take<int>(ns);
     float4* sorted = ar.take<float4>(ns);
     int* overflow_list = ar.take<int>((size_t)n_query);
-    int* overflow_n = ar.take<int>(64);
     GEOB_REQUIRE(ar.ok(), "radius_search: workspace accounting error");
 
     int64_t tq = 0, ts = 0;
@@ -753,14 +758,10 @@ int geob200_radius_search(const float* q_points, int64_t n_query, const float* s
     if (upload_segs(s_lengths_h, batch, s_segs, &ts, &max_s, st)) return -1;
     GEOB_REQUIRE(tq == n_query && ts == n_support, "radius_search: lengths do not sum to the row counts");
 
-    GEOB_CHECK_CUDA(cudaMemsetAsync(cell_cnt, 0, 4 * cells, st));
-    GEOB_CHECK_CUDA(cudaMemsetAsync(cell_cursor, 0, 4 * cells, st));
-    GEOB_CHECK_CUDA(cudaMemsetAsync(overflow_n, 0, 4 * 2, st));
-    GEOB_CHECK_CUDA(cudaMemsetAsync(max_count, 0, 4, st));
+    GEOB_CHECK_CUDA(cudaMemsetAsync(zero_block, 0, 4 * (2 * cells + 64), st));
 
     const dim3 sgrid((max_s + 255) / 256, (unsigned)batch);
-    rs_bounds_kernel<<<(unsigned)batch, 1024, 0, st>>>(s_points, s_segs, radius, clouds);
-    rs_cellsegs_kernel<<<((unsigned)batch + 127) / 128, 128, 0, st>>>(clouds, (int)batch, cell_segs);
+    rs_bounds_kernel<<<(unsigned)batch, 1024, 0, st>>>(s_points, s_segs, radius, clouds, cell_segs, max_count);
     rs_count_kernel<<<sgrid, 256, 0, st>>>(s_points, s_segs, clouds, cell_cnt, pt_cell);
     seg_exclusive_scan_kernel<<<(unsigned)batch, 1024, 0, st>>>(cell_cnt, cell_start, cell_segs, nullptr);
     rs_scatter_kernel<<<sgrid, 256, 0, st>>>(s_points, s_segs, clouds, cell_start, cell_cursor, pt_cell, sorted);
@@ -784,7 +785,7 @@ int geob200_radius_search(const float* q_points, int64_t n_query, const float* s
         count_launches(2);
     }
     GEOB_CHECK_LAUNCH();
-    count_launches(5);
+    count_launches(4);
     return 0;
 }
 

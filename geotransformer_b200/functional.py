@@ -194,7 +194,25 @@ def gse_indices(points, sigma_d, sigma_a, angle_k):
     return d, a
 
 
-def gse_embed(d_indices, a_indices, div_term, wd, wa, bd, ba, wd_t, wa_t, mode=None):
+def scratch(shape, device, tag):
+    """View of a grow-only per-(device, stream, tag) float buffer: for big intermediates whose size changes from pair to
+    pair (the N x N x C structure embedding), so that the caching allocator never has to cudaMalloc inside the timed loop.
+    The result aliases the buffer: it is only valid until the next call with the same tag on the same stream."""
+    numel = 1
+    for s in shape:
+        numel *= int(s)
+    key = (device.index if device.index is not None else torch.cuda.current_device(), L.stream_ptr(), tag)
+    buf = _SCRATCH.get(key)
+    if buf is None or buf.numel() < numel:
+        buf = torch.empty(int(numel * 1.3) + 1024, dtype=_f32, device=device)
+        _SCRATCH[key] = buf
+    return buf[:numel].view(*shape)
+
+
+_SCRATCH = {}
+
+
+def gse_embed(d_indices, a_indices, div_term, wd, wa, bd, ba, wd_t, wa_t, mode=None, out=None):
     n = d_indices.shape[0]
     c = wd.shape[0]
     mode = GSE_MODE if mode is None else mode
@@ -202,7 +220,7 @@ def gse_embed(d_indices, a_indices, div_term, wd, wa, bd, ba, wd_t, wa_t, mode=N
         mode = 0                     # the tcgen05 contraction is specialised for hidden_dim 256 (3DMatch / ModelNet)
     lib = L.lib()
     ws = L.workspace(lib.geob200_gse_embed_workspace_bytes(n, c), d_indices.device, 'gse')
-    emb = torch.empty((n, n, c), dtype=_f32, device=d_indices.device)
+    emb = torch.empty((n, n, c), dtype=_f32, device=d_indices.device) if out is None else out
     with _timed('gse_embed'):
         L.check(lib.geob200_gse_embed(d_indices.data_ptr(), a_indices.data_ptr(), n, c, div_term.data_ptr(),
                                       wd_t.data_ptr(), wa_t.data_ptr(), wd.data_ptr(), wa.data_ptr(), bd.data_ptr(),

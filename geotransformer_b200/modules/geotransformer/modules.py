@@ -29,7 +29,9 @@ class GeometricStructureEmbedding(nn.Module):
         d, a = GF.gse_indices(pts.contiguous(), self.sigma_d, self.sigma_a, self.angle_k)
         return (d.unsqueeze(0), a.unsqueeze(0)) if squeeze else (d, a)
 
-    def forward(self, points):
+    def forward(self, points, scratch_tag=None):
+        """``scratch_tag``: write E into the grow-only scratch buffer of that name (valid until the next call with the same
+        tag on this stream) instead of a fresh allocation; used by GeometricTransformer for its two embeddings."""
         squeeze = points.ndim == 3
         if squeeze and points.shape[0] != 1:
             raise NotImplementedError('one cloud per call (the reference model always passes B=1)')
@@ -37,8 +39,10 @@ class GeometricStructureEmbedding(nn.Module):
         d, a = GF.gse_indices(pts, self.sigma_d, self.sigma_a, self.angle_k)
         wd_t = self._cache.get('wd_t', self.proj_d.weight, lambda w: w.t().contiguous())
         wa_t = self._cache.get('wa_t', self.proj_a.weight, lambda w: w.t().contiguous())
+        n, c = pts.shape[0], self.proj_d.out_features
+        out = GF.scratch((n, n, c), pts.device, scratch_tag) if scratch_tag is not None else None
         emb = GF.gse_embed(d, a, self.embedding.div_term, self.proj_d.weight.detach(), self.proj_a.weight.detach(),
-                           self.proj_d.bias.detach(), self.proj_a.bias.detach(), wd_t, wa_t)
+                           self.proj_d.bias.detach(), self.proj_a.bias.detach(), wd_t, wa_t, out=out)
         return emb.unsqueeze(0) if squeeze else emb
 
 
@@ -60,8 +64,8 @@ class GeometricTransformer(nn.Module):
         batched = ref_points.ndim == 3
         if batched:
             ref_points, src_points, ref_feats, src_feats = ref_points[0], src_points[0], ref_feats[0], src_feats[0]
-        ref_emb = self.embedding(ref_points)
-        src_emb = self.embedding(src_points)
+        ref_emb = self.embedding(ref_points, scratch_tag='gse_ref')     # consumed inside this forward only
+        src_emb = self.embedding(src_points, scratch_tag='gse_src')
         n0, n1 = ref_feats.shape[0], src_feats.shape[0]
         # both clouds share every weight: keep them stacked [ref; src] through the whole transformer
         x = torch.empty((n0 + n1, self.in_proj.out_features), dtype=torch.float32, device=ref_feats.device)
