@@ -213,6 +213,7 @@ def main():
 
     timed(resident, 0, W)
     timed(pinned, 0, W)
+    seg0 = torch.cuda.memory_stats(dev).get('segment.all.allocated', 0)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -225,8 +226,19 @@ def main():
     GF.EVENTS = None
     results = []
     ms_e2e = timed(pinned, W, K, sink=results)
+    # roofline pass: the dominant kernel timed ALONE (one pair in flight, so no other stream shares the SMs), same workload
+    solo = RegistrationEngine(model, cfg, limits, num_streams=1, device=dev)
+    GF.EVENTS = {}
+    barrier()
+    n_solo = min(K * S, 8)
+    solo.register(resident[W * S:W * S + n_solo])
+    barrier()
+    events_solo = GF.EVENTS
+    GF.EVENTS = None
+    solo.close()
     sampler.stop_flag = True
     engine.close()
+    seg1 = torch.cuda.memory_stats(dev).get('segment.all.allocated', 0)
 
     # metric rows (RRE, RTE, nCorr, pair id) gathered with ONE collective
     rows = []
@@ -247,16 +259,20 @@ def main():
     C = cfg.geotransformer.hidden_dim
     gse = events.get('gse_embed', [])
     gse_ms = [s.elapsed_time(e) for s, e in gse]
+    gse_solo_ms = [s.elapsed_time(e) for s, e in events_solo.get('gse_embed', [])]
     n_c = [r['num_superpoints'][0] for r in results] + [r['num_superpoints'][1] for r in results]
     mean_n2 = float(np.mean([n * n for n in n_c])) if n_c else 0.0
     flops = 2.0 * mean_n2 * 4 * C * C
     peak_tf, peak_hbm, peak_src = load_peaks()
-    avg_ms = float(np.mean(gse_ms)) if gse_ms else None
+    avg_ms = float(np.mean(gse_solo_ms)) if gse_solo_ms else None
     achieved = flops / (avg_ms * 1e-3) / 1e12 if avg_ms else None
-    mode_name = {0: 'fp32 CUDA cores', 1: 'tcgen05 3xTF32', 2: 'tcgen05 1xTF32'}[GF.GSE_MODE]
+    avg_ms_concurrent = float(np.mean(gse_ms)) if gse_ms else None
+    mode_name = {0: 'fp32 CUDA cores', 1: 'tcgen05 3xTF32', 2: 'tcgen05 1xTF32', 3: 'tcgen05 3xFP16 (fp32-accurate split)'}[GF.GSE_MODE]
     roofline = {'kernel': 'gse_embed (structure-embedding contraction)', 'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf,
                 'unit': 'TFLOP/s', 'frac': (achieved / peak_tf) if achieved else None, 'traffic': None,
-                'avg_ms_per_launch': avg_ms, 'launches_timed': len(gse_ms), 'flops_per_launch': flops,
+                'avg_ms_per_launch': avg_ms, 'launches_timed': len(gse_solo_ms), 'flops_per_launch': flops,
+                'avg_ms_per_launch_with_other_streams_active': avg_ms_concurrent,
+                'timing': 'CUDA events around the launch, one pair in flight (kernel alone on the GPU), same workload, after the timed regions',
                 'share_of_gpu_time': (sum(gse_ms) / (ms_res * S)) if gse_ms else None, 'mode': mode_name,
                 'peak_source': f'{peak_src} bf16 dense (MEASURED_PEAKS.json); TF32 dense peak is half of it'}
 
@@ -282,7 +298,7 @@ def main():
                    'weights': 'random init (synthetic_state_dict seed 7351)'},
         'e2e': {'value': total_pairs / (ms_e2e * 1e-3), 'unit': 'pairs/s', 'ms_per_step': ms_e2e / K,
                 'h2d_bytes_per_step': int(h2d_bytes), 'd2h_bytes_per_step': 64 * S},
-        'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu, 'clocks': sampler.summary(),
+        'gpu_launches': int(launches), 'cuda_mallocs_in_timed_regions': int(seg1 - seg0), 'roofline': roofline, 'cpu_baseline': cpu, 'clocks': sampler.summary(),
         'quality': {'median_rre_deg': float(rows_t[:, 0].median()), 'median_rte': float(rows_t[:, 1].median()),
                     'mean_correspondences': float(rows_t[:, 2].mean()), 'pairs': int(rows_t.shape[0])},
     }

@@ -5,6 +5,7 @@ The product path has NO fallback: if the library is missing or a call fails, a R
 """
 import ctypes
 import os
+import threading
 
 import torch
 
@@ -85,8 +86,32 @@ def check(rc, what):
         raise RuntimeError(f'{what} failed ({rc}): {msg}')
 
 
+_tls = threading.local()
+
+
 def stream_ptr():
+    """cudaStream_t of the current torch stream.  Inside a ``stream_scope`` the pointer is served from a thread-local
+    (querying torch costs ~2 us, and every op of the forward asks for it)."""
+    p = getattr(_tls, 'stream', None)
+    if p is not None:
+        return p
     return torch.cuda.current_stream().cuda_stream
+
+
+class stream_scope:
+    """``with torch.cuda.stream(s), stream_scope(s.cuda_stream): ...`` -- pins the stream pointer for this thread."""
+
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+    def __enter__(self):
+        self.prev = getattr(_tls, 'stream', None)
+        _tls.stream = self.ptr
+        return self
+
+    def __exit__(self, *a):
+        _tls.stream = self.prev
+        return False
 
 
 def require_cuda(t, name, dtype=None):

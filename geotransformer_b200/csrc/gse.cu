@@ -265,7 +265,8 @@ size_t geob200_gse_embed_workspace_bytes(int64_t n, int64_t channels) {
     return (size_t)(4 * channels * channels * 4 * 3 + 4096);   // room for split/packed weight copies of the tensor-core path
 }
 
-// mode: 0 = fp32 CUDA cores (exact-fp32 accumulation), 1 = tcgen05 3xTF32 (fp32-accurate), 2 = tcgen05 1xTF32
+// mode: 0 = fp32 CUDA cores (exact-fp32 accumulation), 1 = tcgen05 3xTF32 (fp32-accurate), 2 = tcgen05 1xTF32,
+//       3 = tcgen05 3xFP16 (fp32-accurate, half the tensor-pipe time of 3xTF32; default)
 int geob200_gse_embed(const float* d_indices, const float* a_indices, int64_t n, int64_t channels, const float* div_term,
                       const float* wd_t, const float* wa_t, const float* wd, const float* wa, const float* bd, const float* ba,
                       float* embeddings, int mode, void* workspace, size_t workspace_bytes, void* stream) {

@@ -11,6 +11,7 @@ from concurrent.futures import ThreadPoolExecutor
 import numpy as np
 import torch
 
+from . import _lib
 from .utils.data import registration_collate_fn_stack_mode
 
 
@@ -26,7 +27,7 @@ class RegistrationEngine:
     def _one(self, slot, pair, start_event, keep):
         torch.cuda.set_device(self.device)
         stream = self.streams[slot]
-        with torch.cuda.stream(stream):
+        with torch.cuda.stream(stream), _lib.stream_scope(stream.cuda_stream):
             if start_event is not None:
                 stream.wait_event(start_event)
             b = self.cfg.backbone

@@ -115,7 +115,7 @@ int geob200_gse_indices(const float* points, int64_t n, float sigma_d, float fac
 
 /* GeometricStructureEmbedding.forward (geotransformer.py:57-72) given the indices: sinusoid -> proj_d / proj_a ->
  * max over k -> sum, fused.  wd/wa are the nn.Linear weights (out,in); wd_t/wa_t their transposes (in,out).
- * mode 0: fp32 CUDA cores; 1: tcgen05 3xTF32; 2: tcgen05 1xTF32. */
+ * mode 0: fp32 CUDA cores; 1: tcgen05 3xTF32; 2: tcgen05 1xTF32; 3: tcgen05 3xFP16 split (fp32-accurate, fastest). */
 size_t geob200_gse_embed_workspace_bytes(int64_t n, int64_t channels);
 int geob200_gse_embed(const float* d_indices, const float* a_indices, int64_t n, int64_t channels, const float* div_term,
                       const float* wd_t, const float* wa_t, const float* wd, const float* wa, const float* bd, const float* ba,

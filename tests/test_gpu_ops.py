@@ -212,9 +212,28 @@ def test_gse_embedding_tensor_core_modes(n):
     cu = {k: v.cuda() for k, v in sd.items()}
     args = (d, a, cu['e.embedding.div_term'], cu['e.proj_d.weight'], cu['e.proj_a.weight'], cu['e.proj_d.bias'], cu['e.proj_a.bias'],
             cu['e.proj_d.weight'].t().contiguous(), cu['e.proj_a.weight'].t().contiguous())
+    close(GF.gse_embed(*args, mode=3), want, 2e-5, 'structure embedding 3xFP16')
     close(GF.gse_embed(*args, mode=1), want, 2e-5, 'structure embedding 3xTF32')
     close(GF.gse_embed(*args, mode=2), want, 2e-3, 'structure embedding 1xTF32')
     close(GF.gse_embed(*args, mode=0), want, 2e-5, 'structure embedding fp32')
+
+
+def test_gse_embedding_fp16_split_is_scale_invariant():
+    """the 3xFP16 path pre-scales the weights by a power of two: tiny and huge weights keep fp32-level accuracy"""
+    g = torch.Generator().manual_seed(5)
+    c, n = 256, 60
+    pts = torch.rand(n, 3, generator=g)
+    for wscale in (1e-4, 1.0, 300.0):
+        sd = {'e.embedding.div_term': torch.exp(torch.arange(0, c, 2).float() * (-np.log(10000.0) / c)),
+              'e.proj_d.weight': torch.randn(c, c, generator=g) * wscale, 'e.proj_d.bias': torch.randn(c, generator=g) * wscale,
+              'e.proj_a.weight': torch.randn(c, c, generator=g) * wscale, 'e.proj_a.bias': torch.randn(c, generator=g) * wscale}
+        want = G.structure_embedding(sd, 'e.', pts, 0.2, 15, 3)
+        d, a = GF.gse_indices(pts.cuda(), 0.2, 15, 3)
+        cu = {k: v.cuda() for k, v in sd.items()}
+        got = GF.gse_embed(d, a, cu['e.embedding.div_term'], cu['e.proj_d.weight'], cu['e.proj_a.weight'], cu['e.proj_d.bias'],
+                           cu['e.proj_a.bias'], cu['e.proj_d.weight'].t().contiguous(), cu['e.proj_a.weight'].t().contiguous(), mode=3)
+        err = (got.cpu() - want).abs().max().item() / want.abs().max().item()
+        assert err < 2e-5, f'weight scale {wscale}: relative error {err:.2e}'
 
 
 def test_gse_embedding_generic_channels():
