@@ -178,6 +178,8 @@ def main():
     model = create_model(cfg)
     model.load_state_dict(synthetic_state_dict(model, 7351), strict=True)
     model = model.to(dev).eval()
+    from geotransformer_b200.model import enable_native
+    enable_native(model)
 
     from geotransformer_b200.engine import RegistrationEngine
     W, K, S = args.warmup, args.steps, max(1, args.streams)
@@ -267,7 +269,7 @@ def main():
     avg_ms = float(np.mean(gse_solo_ms)) if gse_solo_ms else None
     achieved = flops / (avg_ms * 1e-3) / 1e12 if avg_ms else None
     avg_ms_concurrent = float(np.mean(gse_ms)) if gse_ms else None
-    mode_name = {0: 'fp32 CUDA cores', 1: 'tcgen05 3xTF32', 2: 'tcgen05 1xTF32', 3: 'tcgen05 3xFP16 (fp32-accurate split)'}[GF.GSE_MODE]
+    mode_name = {0: 'fp32 CUDA cores', 1: 'tcgen05 3xTF32', 2: 'tcgen05 1xTF32', 3: 'tcgen05 3xFP16 (fp32-accurate split)', 4: 'tcgen05 3xFP16 split, CTA-pair TMA multicast of B'}[GF.GSE_MODE]
     roofline = {'kernel': 'gse_embed (structure-embedding contraction)', 'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf,
                 'unit': 'TFLOP/s', 'frac': (achieved / peak_tf) if achieved else None, 'traffic': None,
                 'avg_ms_per_launch': avg_ms, 'launches_timed': len(gse_solo_ms), 'flops_per_launch': flops,

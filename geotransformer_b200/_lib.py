@@ -62,6 +62,11 @@ _sig('geob200_local_global_registration', c_int, P, P, P, P, P, I64, I64, I64, I
      P, P, P, P, P, SZ, P)
 _sig('geob200_weighted_procrustes', c_int, P, P, P, I64, I64, F, F, P, P)
 
+_sig('geob200_backbone_workspace_bytes', SZ, P, P)
+_sig('geob200_backbone_forward', c_int, P, P, P, P, P, P, P, P, P, P, P, P, SZ, P, SZ, P)
+_sig('geob200_transformer_workspace_bytes', SZ, I64, I64, I64, I64, I64)
+_sig('geob200_transformer_forward', c_int, P, I64, I64, I64, P, I64, I64, P, P, P, P, SZ, P)
+
 
 def lib():
     """Load (once) and return the C-ABI library; raises RuntimeError if it has not been built."""

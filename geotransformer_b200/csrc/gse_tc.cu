@@ -81,6 +81,16 @@ __device__ __forceinline__ void sincos_cw(float x, float& s, float& c) {
     c = ((q + 1) & 2) ? -cc : cc;
 }
 
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {   // waits for remote (cluster-scope) arrivals
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(addr), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -578,6 +588,214 @@ __global__ void __launch_bounds__(NTHREADS, 1) gse_embed_f16_kernel(const float*
     }
 }
 
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) gse_embed_f16_cluster_kernel(const float* __restrict__ d_idx, const float* __restrict__ a_idx,
+                                                                    long long n_pairs, const float* __restrict__ div_term,
+                                                                    const __half* __restrict__ img_hi, const __half* __restrict__ img_lo,
+                                                                    const float* __restrict__ bias_sum, const float* __restrict__ scale,
+                                                                    float* __restrict__ E) {
+    constexpr int NSTAGE = F16_NSTAGE;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    float* xstage = (float*)(smem + NSTAGE * F16_STAGE_BYTES);
+    uint64_t* bars = (uint64_t*)(xstage + ROWS * STAGE_LD);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + NSTAGE;
+    uint64_t* tfull = bars + 2 * NSTAGE;
+    uint64_t* tempty = tfull + 2;
+    uint64_t* peer_empty = tempty + 2;     // [NSTAGE]: the peer CTA's stage is free (remote arrive)
+    uint32_t* tmem_slot = (uint32_t*)(peer_empty + NSTAGE);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long n_tiles = (n_pairs + PAIRS - 1) / PAIRS;
+    // the two CTAs of a cluster advance in lockstep (they share every B chunk): same number of tile slots for everybody
+    const long long n_iters = (n_tiles + gridDim.x - 1) / gridDim.x;
+    uint32_t cta_rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], NGEN_WARPS + 1); mbar_init(&empty[s], 1); mbar_init(&peer_empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == NGEN_WARPS + 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");   // peer barriers are initialised
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < NGEN_WARPS) {
+        {   // zero the two padding rows (126, 127) of every A buffer once
+            for (int e = threadIdx.x; e < NSTAGE * 2 * 64; e += NGEN_WARPS * 32) {
+                const int sidx = e / 128, rem = e % 128, part = rem / 64, w = rem % 64;
+                float* base = (float*)(smem + sidx * F16_STAGE_BYTES + part * A_BYTES + 15 * 1024 + 6 * 128);
+                base[w] = 0.f;
+            }
+            asm volatile("bar.sync 2, %0;" ::"n"(NGEN_WARPS * 32) : "memory");
+        }
+        int s = 0;
+        uint32_t ph = 0;
+        for (long long itile = 0; itile < n_iters; ++itile) {
+            const long long tile = itile * gridDim.x + blockIdx.x;   // tile >= n_tiles: idle slot, pipeline still runs
+            const long long p0 = tile * PAIRS;
+            for (int kc = 0; kc < NCHUNK16; ++kc) {
+                mbar_wait(&empty[s], ph ^ 1u);
+                unsigned char* st = smem + s * F16_STAGE_BYTES;
+                const int f0 = (kc & 3) * 32;               // 32 frequencies (64 halves) per chunk
+                const bool angle = kc < 4;
+                const int n_items = (angle ? 3 * PAIRS : PAIRS) * 8;
+                for (int it = threadIdx.x; it < n_items; it += NGEN_WARPS * 32) {
+                    const int c = it & 7, rr = it >> 3;     // 16-byte chunk c = frequencies f0+4c .. f0+4c+3
+                    const int j = angle ? (rr % PAIRS) : rr;
+                    const long long p = p0 + j;
+                    float x = 0.f;
+                    if (p < n_pairs) x = angle ? __ldg(a_idx + p * 3 + rr / PAIRS) : __ldg(d_idx + p);
+                    float v[8];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) sincos_cw(__fmul_rn(x, __ldg(div_term + f0 + 4 * c + u)), v[2 * u], v[2 * u + 1]);
+                    __half2 hi[4], lo[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const __half h0 = __float2half_rn(v[2 * u]), h1 = __float2half_rn(v[2 * u + 1]);
+                        hi[u] = __halves2half2(h0, h1);
+                        lo[u] = __halves2half2(__float2half_rn(v[2 * u] - __half2float(h0)), __float2half_rn(v[2 * u + 1] - __half2float(h1)));
+                    }
+                    const uint4 hv = make_uint4(*reinterpret_cast<uint32_t*>(&hi[0]), *reinterpret_cast<uint32_t*>(&hi[1]),
+                                                *reinterpret_cast<uint32_t*>(&hi[2]), *reinterpret_cast<uint32_t*>(&hi[3]));
+                    const uint4 lv = make_uint4(*reinterpret_cast<uint32_t*>(&lo[0]), *reinterpret_cast<uint32_t*>(&lo[1]),
+                                                *reinterpret_cast<uint32_t*>(&lo[2]), *reinterpret_cast<uint32_t*>(&lo[3]));
+                    const int nrep = angle ? 1 : 3;
+                    for (int rep = 0; rep < nrep; ++rep) {
+                        const int r = angle ? rr : (rep * PAIRS + j);
+                        const uint32_t off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+                        *reinterpret_cast<uint4*>(st + off) = hv;
+                        *reinterpret_cast<uint4*>(st + A_BYTES + off) = lv;
+                    }
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[s]);
+                if (++s == NSTAGE) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp == NGEN_WARPS) {
+        if (lane == 0) {
+            // B copier: rank 0 streams the hi image, rank 1 the lo image, each MULTICAST into both CTAs of the cluster
+            // (cp.async.bulk ... .multicast::cluster): every B byte leaves L2 once per CTA pair instead of once per CTA.
+            const uint32_t peer = cta_rank ^ 1u;
+            int s = 0;
+            uint32_t ph = 0;
+            for (long long itile = 0; itile < n_iters; ++itile) {
+                for (int kc = 0; kc < NCHUNK16; ++kc) {
+                    mbar_wait(&empty[s], ph ^ 1u);                         // my MMAs are done with stage s
+                    {   // tell the peer, then wait until the peer's stage s is free too
+                        uint32_t raddr;
+                        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(&peer_empty[s])), "r"(peer));
+                        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+                    }
+                    mbar_wait_cluster(&peer_empty[s], ph);
+                    unsigned char* st = smem + s * F16_STAGE_BYTES;
+                    mbar_arrive_expect_tx(&full[s], 2 * B_BYTES);          // both halves land here (mine + the peer's multicast)
+                    const __half* src = (cta_rank == 0 ? img_hi : img_lo) + (size_t)kc * (C * KC16);
+                    unsigned char* dst = st + 2 * A_BYTES + (cta_rank == 0 ? 0 : B_BYTES);
+                    asm volatile(
+                        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+                            smem_u32(dst)),
+                        "l"(src), "r"((uint32_t)B_BYTES), "r"(smem_u32(&full[s])), "h"((unsigned short)3)
+                        : "memory");
+                    if (++s == NSTAGE) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == NGEN_WARPS + 1) {
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            int acc = 0;
+            uint32_t acc_ph[2] = {0, 0};
+            for (long long itile = 0; itile < n_iters; ++itile) {
+            const long long tile = itile * gridDim.x + blockIdx.x;   // tile >= n_tiles: idle slot, pipeline still runs
+                mbar_wait(&tempty[acc], acc_ph[acc] ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * C);
+                for (int kc = 0; kc < NCHUNK16; ++kc) {
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t st = smem_u32(smem + s * F16_STAGE_BYTES);
+                    const uint64_t da_hi = make_desc(st), da_lo = make_desc(st + A_BYTES);
+                    const uint64_t db_hi = make_desc(st + 2 * A_BYTES), db_lo = make_desc(st + 2 * A_BYTES + B_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < KC16 / 16; ++kk) {        // 4 MMAs of K = 16 (32 bytes) per operand pair
+                        const uint64_t adv = (uint64_t)(kk * 2);
+                        umma_f16(d_tmem, da_hi + adv, db_hi + adv, (kc == 0 && kk == 0) ? 0u : 1u);
+                        umma_f16(d_tmem, da_hi + adv, db_lo + adv, 1u);
+                        umma_f16(d_tmem, da_lo + adv, db_hi + adv, 1u);
+                    }
+                    umma_commit(&empty[s]);
+                    if (++s == NSTAGE) { s = 0; ph ^= 1u; }
+                }
+                umma_commit(&tfull[acc]);
+                acc_ph[acc] ^= 1u;
+                acc ^= 1;
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int et = (warp - (NGEN_WARPS + 2)) * 32 + lane;
+        const float inv_scale = scale[1];
+        int acc = 0;
+        uint32_t acc_ph[2] = {0, 0};
+        for (long long itile = 0; itile < n_iters; ++itile) {
+            const long long tile = itile * gridDim.x + blockIdx.x;   // tile >= n_tiles: idle slot, pipeline still runs
+            mbar_wait(&tfull[acc], acc_ph[acc]);
+            tc_fence_after();
+            const long long p0 = tile * PAIRS;
+            for (int cc = 0; cc < C / 32; ++cc) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C + cc * 32);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                      "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+                      "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                      "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                float* xr = xstage + (q * 32 + lane) * STAGE_LD;
+#pragma unroll
+                for (int c = 0; c < 32; ++c) xr[c] = __uint_as_float(v[c]);
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int idx = et; idx < PAIRS * 32; idx += 128) {
+                    const int jj = idx >> 5, c = idx & 31;
+                    const long long p = p0 + jj;
+                    if (p < n_pairs) {
+                        const float m = fmaxf(fmaxf(xstage[jj * STAGE_LD + c], xstage[(PAIRS + jj) * STAGE_LD + c]),
+                                              xstage[(2 * PAIRS + jj) * STAGE_LD + c]);
+                        E[p * C + cc * 32 + c] = fmaf(m, inv_scale, __ldg(bias_sum + cc * 32 + c));
+                    }
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            acc_ph[acc] ^= 1u;
+            acc ^= 1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");   // no CTA leaves while its peer may still write to it
+    if (warp == NGEN_WARPS + 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
 }  // namespace tc
 }  // namespace geob200
 
@@ -587,7 +805,7 @@ int geob200_gse_embed_tc(const float* d_idx, const float* a_idx, long long n_pai
                          const float* Wd, const float* Wa, const float* bd, const float* ba, float* E, int mode,
                          void* workspace, size_t workspace_bytes, cudaStream_t st) {
     if (C != tc::C) return 1;
-    if (mode != 1 && mode != 2 && mode != 3) return 1;
+    if (mode != 1 && mode != 2 && mode != 3 && mode != 4) return 1;
     const size_t img_floats = (size_t)tc::C * tc::KTOT;
     const size_t need = sizeof(float) * (2 * img_floats + tc::C) + 1024;
     GEOB_REQUIRE(workspace_bytes >= need, "gse_embed_tc: workspace too small (%zu < %zu)", workspace_bytes, need);
@@ -596,7 +814,7 @@ int geob200_gse_embed_tc(const float* d_idx, const float* a_idx, long long n_pai
     float* bias_sum = img_lo + img_floats;
     const long long n_tiles = (n_pairs + tc::PAIRS - 1) / tc::PAIRS;
     const int grid = (int)(n_tiles < (long long)num_sms() ? n_tiles : (long long)num_sms());
-    if (mode == 3) {
+    if (mode == 3 || mode == 4) {
         __half* h_hi = (__half*)img_hi;
         __half* h_lo = h_hi + img_floats;
         float* bsum = (float*)(h_lo + img_floats);
@@ -606,9 +824,15 @@ int geob200_gse_embed_tc(const float* d_idx, const float* a_idx, long long n_pai
         static bool set16 = false;
         if (!set16) {
             GEOB_CHECK_CUDA(cudaFuncSetAttribute(tc::gse_embed_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::F16_SMEM));
+            GEOB_CHECK_CUDA(cudaFuncSetAttribute(tc::gse_embed_f16_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::F16_SMEM));
             set16 = true;
         }
-        tc::gse_embed_f16_kernel<<<grid, tc::NTHREADS, tc::F16_SMEM, st>>>(d_idx, a_idx, n_pairs, div_term, h_hi, h_lo, bsum, scale, E);
+        if (mode == 4) {
+            // CTA pairs (cluster of 2) share every B chunk through TMA multicast; grid = even number of CTAs, one per SM
+            int g2 = (int)((n_tiles + 1) / 2 < (long long)(num_sms() / 2) ? (n_tiles + 1) / 2 : (long long)(num_sms() / 2)) * 2;
+            tc::gse_embed_f16_cluster_kernel<<<g2, tc::NTHREADS, tc::F16_SMEM, st>>>(d_idx, a_idx, n_pairs, div_term, h_hi, h_lo, bsum, scale, E);
+        } else
+            tc::gse_embed_f16_kernel<<<grid, tc::NTHREADS, tc::F16_SMEM, st>>>(d_idx, a_idx, n_pairs, div_term, h_hi, h_lo, bsum, scale, E);
         GEOB_CHECK_LAUNCH();
         count_launches(3);
         return 0;

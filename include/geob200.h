@@ -177,6 +177,56 @@ int geob200_local_global_registration(const float* ref_knn_points, const float* 
 int geob200_weighted_procrustes(const float* src_points, const float* ref_points, const float* weights, int64_t batch,
                                 int64_t n, float weight_thresh, float eps, float* transforms, void* stream);
 
+/* ---- native stage drivers (native.cu) ------------------------------------------------------------------------
+ * The whole KPConv-FPN backbone / geometric transformer as ONE call: same kernels in the same order as the per-op entry
+ * points above (bitwise-identical results), driven from C++ so that the host cost per pair is a few hundred microseconds
+ * instead of milliseconds.  All pointers are device pointers; the structs are plain C (built from a state_dict by
+ * geotransformer_b200/native.py). */
+#define GEOB200_MAX_STAGES 6
+typedef struct { const float* weight; const float* bias; int64_t c_in, c_out; } geob200_linear_t;
+typedef struct { const float* gamma; const float* beta; } geob200_norm_t;
+typedef struct { const float* weights; const float* weights_t; const float* bias; const float* kernel_points;
+                 int64_t c_in, c_out; float sigma; } geob200_kpconv_t;
+/* ResidualBlock (reference geotransformer/modules/kpconv/modules.py:151-225) */
+typedef struct {
+    int32_t has_unary1, has_shortcut, strided, reserved;
+    int64_t c_in;
+    geob200_linear_t unary1; geob200_norm_t norm1;
+    geob200_kpconv_t conv;   geob200_norm_t norm_conv;
+    geob200_linear_t unary2; geob200_norm_t norm2;
+    geob200_linear_t shortcut; geob200_norm_t norm_sc;
+} geob200_resblock_t;
+/* KPConvFPN (reference experiments/.../backbone.py): encoder1_1 = conv1+norm1, blocks[0] = encoder1_2, then three blocks per
+ * further level; decoders[0] is the coarsest decoder, the last one (level finest_decoder) has no norm/activation. */
+typedef struct {
+    int32_t num_stages, finest_decoder, groups, init_dim;
+    geob200_kpconv_t conv1; geob200_norm_t norm1;
+    geob200_resblock_t blocks[1 + 3 * (GEOB200_MAX_STAGES - 1)];
+    geob200_linear_t decoders[GEOB200_MAX_STAGES];
+    geob200_norm_t decoder_norms[GEOB200_MAX_STAGES];
+} geob200_backbone_t;
+size_t geob200_backbone_workspace_bytes(const geob200_backbone_t* net, const int64_t* level_rows);
+/* out_feats[0] = coarsest encoder output (rows level_rows[S-1]); out_feats[i>0] = decoder outputs, coarse to fine. */
+int geob200_backbone_forward(const geob200_backbone_t* net, const float* feats, const float* const* points, const int64_t* level_rows,
+                             const int64_t* const* neighbors, const int64_t* neighbor_width, const int64_t* const* subsampling,
+                             const int64_t* subsampling_width, const int64_t* const* upsampling, const int64_t* upsampling_width,
+                             float* const* out_feats, void* gn_workspace, size_t gn_workspace_bytes, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
+/* one transformer layer ('self' with the structure embedding, or 'cross'); w_qkv = [Wq;Wk;Wv] (3C,C), w_kv = [Wk;Wv], wp_t = Wp^T */
+typedef struct {
+    int32_t is_self, reserved;
+    const float* w_qkv; const float* b_qkv; const float* w_q; const float* b_q; const float* w_kv; const float* b_kv;
+    const float* wp_t; const float* bp;
+    geob200_linear_t att_linear; geob200_norm_t att_norm;
+    geob200_linear_t expand; geob200_linear_t squeeze; geob200_norm_t out_norm;
+} geob200_tlayer_t;
+size_t geob200_transformer_workspace_bytes(int64_t n0, int64_t n1, int64_t channels, int64_t heads, int64_t num_layers);
+/* RPEConditionalTransformer.forward on stacked features x = [feats0; feats1] (after in_proj), sequential cross updates */
+int geob200_transformer_forward(const geob200_tlayer_t* layers, int64_t num_layers, int64_t channels, int64_t heads, const float* x,
+                                int64_t n0, int64_t n1, const float* emb0, const float* emb1, float* out, void* workspace,
+                                size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

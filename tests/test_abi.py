@@ -12,6 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _header_decls():
     hdr = open(os.path.join(ROOT, 'include', 'geob200.h')).read()
     hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    hdr = re.sub(r'typedef struct \{.*?\} \w+;', '', hdr, flags=re.S)
     return re.findall(r'\b(?:int|void|size_t|uint64_t|const char\*)\s+(geob200_\w+)\s*\(([^;]*?)\)\s*;', hdr, flags=re.S)
 
 

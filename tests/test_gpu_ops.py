@@ -213,6 +213,7 @@ def test_gse_embedding_tensor_core_modes(n):
     args = (d, a, cu['e.embedding.div_term'], cu['e.proj_d.weight'], cu['e.proj_a.weight'], cu['e.proj_d.bias'], cu['e.proj_a.bias'],
             cu['e.proj_d.weight'].t().contiguous(), cu['e.proj_a.weight'].t().contiguous())
     close(GF.gse_embed(*args, mode=3), want, 2e-5, 'structure embedding 3xFP16')
+    close(GF.gse_embed(*args, mode=4), want, 2e-5, 'structure embedding 3xFP16, CTA-pair multicast')
     close(GF.gse_embed(*args, mode=1), want, 2e-5, 'structure embedding 3xTF32')
     close(GF.gse_embed(*args, mode=2), want, 2e-3, 'structure embedding 1xTF32')
     close(GF.gse_embed(*args, mode=0), want, 2e-5, 'structure embedding fp32')
