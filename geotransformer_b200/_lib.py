@@ -62,6 +62,10 @@ _sig('geob200_local_global_registration', c_int, P, P, P, P, P, I64, I64, I64, I
      P, P, P, P, P, SZ, P)
 _sig('geob200_weighted_procrustes', c_int, P, P, P, I64, I64, F, F, P, P)
 
+_sig('geob200_node_correspondences_workspace_bytes', SZ, I64, I64, I64)
+_sig('geob200_node_correspondences', c_int, P, P, P, P, P, P, P, P, I64, I64, I64, P, F, P, P, P, P, SZ, P)
+_sig('geob200_evaluate', c_int, P, P, I64, F, P, P, I64, P, P, I64, F, P, P, P, I64, c_int, F, F, F, P, P)
+
 _sig('geob200_backbone_workspace_bytes', SZ, P, P)
 _sig('geob200_backbone_forward', c_int, P, P, P, P, P, P, P, P, P, P, P, P, SZ, P, SZ, P)
 _sig('geob200_transformer_workspace_bytes', SZ, I64, I64, I64, I64, I64)

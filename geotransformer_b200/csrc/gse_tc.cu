@@ -81,6 +81,22 @@ __device__ __forceinline__ void sincos_cw(float x, float& s, float& c) {
     c = ((q + 1) & 2) ? -cc : cc;
 }
 
+// Cheaper variant for the fp16 kernels: same Cody-Waite reduction to [-pi/4, pi/4], then the SFU (sin.approx / cos.approx, abs
+// error ~4e-7 on that interval -- below the 2^-12 half-ulp of the fp16 hi/lo split that consumes the values).
+__device__ __forceinline__ void sincos_sfu(float x, float& s, float& c) {
+    if (fabsf(x) > 48000.f) { sincosf(x, &s, &c); return; }
+    const float k = rintf(x * 0.636619772367581343f);
+    float r = fmaf(k, -1.57079601287841796875f, x);
+    r = fmaf(k, -3.1391647326017846353352069854736328125e-7f, r);
+    r = fmaf(k, -5.390302529957764765e-15f, r);
+    const float sp = __sinf(r), cp = __cosf(r);
+    const int q = (int)k;
+    const float ss = (q & 1) ? cp : sp;
+    const float cc = (q & 1) ? sp : cp;
+    s = (q & 2) ? -ss : ss;
+    c = ((q + 1) & 2) ? -cc : cc;
+}
+
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {   // waits for remote (cluster-scope) arrivals
     const uint32_t addr = smem_u32(bar);
     uint32_t done;
@@ -463,7 +479,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gse_embed_f16_kernel(const float*
                     if (p < n_pairs) x = angle ? __ldg(a_idx + p * 3 + rr / PAIRS) : __ldg(d_idx + p);
                     float v[8];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) sincos_cw(__fmul_rn(x, __ldg(div_term + f0 + 4 * c + u)), v[2 * u], v[2 * u + 1]);
+                    for (int u = 0; u < 4; ++u) sincos_sfu(__fmul_rn(x, __ldg(div_term + f0 + 4 * c + u)), v[2 * u], v[2 * u + 1]);
                     __half2 hi[4], lo[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
@@ -654,7 +670,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) gse_emb
                     if (p < n_pairs) x = angle ? __ldg(a_idx + p * 3 + rr / PAIRS) : __ldg(d_idx + p);
                     float v[8];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) sincos_cw(__fmul_rn(x, __ldg(div_term + f0 + 4 * c + u)), v[2 * u], v[2 * u + 1]);
+                    for (int u = 0; u < 4; ++u) sincos_sfu(__fmul_rn(x, __ldg(div_term + f0 + 4 * c + u)), v[2 * u], v[2 * u + 1]);
                     __half2 hi[4], lo[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {

@@ -2,10 +2,12 @@
 
 Pairs are independent.  Most kernels of one pair leave SMs idle (a few hundred CTAs, deep levels
 with ~600 points), so the engine runs ``num_streams`` pairs concurrently, each on its own CUDA stream driven by its own
-host thread (ctypes and torch release the GIL while launching / synchronising).  Per pair it performs: H2D of the raw
+host thread (ctypes and torch release the GIL while launching / synchronising) that pulls the next pair from a shared
+cursor.  Per pair it performs: H2D of the raw
 clouds (pinned staging) -> GPU collate -> model forward -> D2H of the estimated transform.  This is the caller-facing API
 bench.py measures as `e2e` (the SingleTester-compatible loop, is built on it).
 """
+import threading
 from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
@@ -16,45 +18,72 @@ from .utils.data import registration_collate_fn_stack_mode
 
 
 class RegistrationEngine:
-    def __init__(self, model, cfg, neighbor_limits, num_streams=4, device=None):
+    def __init__(self, model, cfg, neighbor_limits, num_streams=4, device=None, native=True, evaluator=None):
+        """evaluator: optional geotransformer_b200.loss.Evaluator; its metrics (PIR, IR, RRE, RTE, RMSE, RR) are then computed
+        on the device for every pair and travel back with the transform in the same D2H copy."""
         self.model, self.cfg, self.limits = model, cfg, neighbor_limits
+        if native and not hasattr(model, '_native'):
+            from .model import enable_native
+            enable_native(model)          # C++ stage drivers: same results, ~10x less host time per pair
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         self.num_streams = num_streams
+        self.evaluator = evaluator
         self.streams = [torch.cuda.Stream(self.device) for _ in range(num_streams)]
         self.pool = ThreadPoolExecutor(max_workers=num_streams)
-        self.t_host = [torch.empty((4, 4), dtype=torch.float32).pin_memory() for _ in range(num_streams)]
+        # per slot: [estimated_transform (16) | metrics (8)] on the device and pinned on the host
+        self.r_dev = [torch.zeros((24,), dtype=torch.float32, device=self.device) for _ in range(num_streams)]
+        self.r_host = [torch.zeros((24,), dtype=torch.float32).pin_memory() for _ in range(num_streams)]
 
-    def _one(self, slot, pair, start_event, keep):
+    def _one(self, slot, pair, keep):
+        stream = self.streams[slot]
+        b = self.cfg.backbone
+        data = registration_collate_fn_stack_mode([pair], b.num_stages, b.init_voxel_size, b.init_radius, self.limits,
+                                                  device=self.device)
+        out = self.model(data)
+        r_dev, r_host = self.r_dev[slot], self.r_host[slot]
+        r_dev[:16].copy_(out['estimated_transform'].reshape(16))
+        if self.evaluator is not None:
+            self.evaluator.metrics_tensor(out, data, out=r_dev[16:])
+        r_host.copy_(r_dev, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(stream)
+        done.synchronize()                      # this thread only; the other streams keep running
+        res = {'estimated_transform': r_host[:16].reshape(4, 4).clone(), 'num_corr': int(out['ref_corr_points'].shape[0]),
+               'num_superpoints': (int(out['ref_points_c'].shape[0]), int(out['src_points_c'].shape[0]))}
+        if self.evaluator is not None:
+            m = r_host[16:].tolist()
+            res['metrics'] = dict(zip(('PIR', 'IR', 'RRE', 'RTE', 'RMSE', 'RR'), m[:6]))
+        if keep:
+            res['output_dict'] = out
+        return res, done
+
+    def _worker(self, slot, pairs, results, cursor, lock, start_event, keep):
+        """one host thread per stream: pulls the next unregistered pair until none is left (no per-chunk barrier)"""
         torch.cuda.set_device(self.device)
         stream = self.streams[slot]
+        last = None
         with torch.cuda.stream(stream), _lib.stream_scope(stream.cuda_stream):
             if start_event is not None:
                 stream.wait_event(start_event)
-            b = self.cfg.backbone
-            data = registration_collate_fn_stack_mode([pair], b.num_stages, b.init_voxel_size, b.init_radius, self.limits,
-                                                      device=self.device)
-            out = self.model(data)
-            self.t_host[slot].copy_(out['estimated_transform'], non_blocking=True)
-            done = torch.cuda.Event()
-            done.record(stream)
-            done.synchronize()                      # this thread only; the other streams keep running
-            res = {'estimated_transform': self.t_host[slot].clone(), 'num_corr': int(out['ref_corr_points'].shape[0]),
-                   'num_superpoints': (int(out['ref_points_c'].shape[0]), int(out['src_points_c'].shape[0]))}
-            if keep:
-                res['output_dict'] = out
-        return res, done
+            while True:
+                with lock:
+                    i = cursor[0]
+                    cursor[0] += 1
+                if i >= len(pairs):
+                    return last
+                results[i], last = self._one(slot, pairs[i], keep)
 
     def register(self, pairs, start_event=None, keep_outputs=False):
         """pairs: list of dicts with ref_points/src_points/ref_feats/src_feats/transform (numpy, CPU or CUDA tensors).
-        Returns one result dict per pair, in order."""
+        Returns one result dict per pair, in order.  The current stream waits for all of them."""
         results = [None] * len(pairs)
-        for base in range(0, len(pairs), self.num_streams):
-            chunk = pairs[base:base + self.num_streams]
-            futs = [self.pool.submit(self._one, s, p, start_event, keep_outputs) for s, p in enumerate(chunk)]
-            for i, f in enumerate(futs):
-                res, done = f.result()
+        cursor, lock = [0], threading.Lock()
+        futs = [self.pool.submit(self._worker, s, pairs, results, cursor, lock, start_event, keep_outputs)
+                for s in range(min(self.num_streams, max(1, len(pairs))))]
+        for f in futs:
+            done = f.result()
+            if done is not None:
                 torch.cuda.current_stream().wait_event(done)
-                results[base + i] = res
         return results
 
     def close(self):

@@ -211,6 +211,18 @@ def scratch(shape, device, tag):
 
 
 _SCRATCH = {}
+_ARANGE = {}
+
+
+def scratch_arange(n, device, tag='arange'):
+    """arange(n) int64 from a cached, read-only per-device table (no launch, no allocation in steady state)."""
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    buf = _ARANGE.get(key)
+    if buf is None or buf.numel() < n:
+        buf = torch.arange(max(int(n) * 2, 4096), dtype=_i64, device=device)
+        torch.cuda.current_stream(device).synchronize()      # other streams may read it right away
+        _ARANGE[key] = buf
+    return buf[:n]
 
 
 def gse_embed(d_indices, a_indices, div_term, wd, wa, bd, ba, wd_t, wa_t, mode=None, out=None):
@@ -389,3 +401,66 @@ def weighted_procrustes(src_points, ref_points, weights=None, weight_thresh=0.0,
                                                 float(weight_thresh), float(eps), T.data_ptr(), L.stream_ptr()),
             'weighted_procrustes')
     return T
+
+
+def node_correspondences(ref_nodes, src_nodes, ref_knn_points, src_knn_points, transform, pos_radius, ref_masks=None,
+                         src_masks=None, ref_knn_masks=None, src_knn_masks=None):
+    """Ground-truth superpoint pairs (reference matching.py:231-315).  Asynchronous: returns full-capacity
+    ``(indices (M*N,2), overlaps (M*N,), count (1,) int32)``; rows ``[:count]`` are valid (see ``finish_node_correspondences``)."""
+    for t, name in ((ref_nodes, 'ref_nodes'), (src_nodes, 'src_nodes'), (ref_knn_points, 'ref_knn_points'),
+                    (src_knn_points, 'src_knn_points'), (transform, 'transform')):
+        _f(t, name)
+    m, n, k = ref_nodes.shape[0], src_nodes.shape[0], ref_knn_points.shape[1]
+    if src_knn_points.shape[1] != k or tuple(transform.shape) != (4, 4):
+        raise ValueError('node_correspondences: patches must share K and transform must be (4, 4)')
+    for t, shape, name in ((ref_masks, (m,), 'ref_masks'), (src_masks, (n,), 'src_masks'),
+                           (ref_knn_masks, (m, k), 'ref_knn_masks'), (src_knn_masks, (n, k), 'src_knn_masks')):
+        if t is not None:
+            L.require_cuda(t, name, torch.bool)
+            if tuple(t.shape) != shape:
+                raise ValueError('node_correspondences: %s must have shape %s' % (name, shape))
+    dev = ref_nodes.device
+    lib = L.lib()
+    ws = L.workspace(lib.geob200_node_correspondences_workspace_bytes(m, n, k), dev, tag='node_corr')
+    idx = torch.empty((m * n, 2), dtype=_i64, device=dev)
+    ov = torch.empty((m * n,), dtype=_f32, device=dev)
+    cnt = torch.empty((1,), dtype=_i32, device=dev)
+    L.check(lib.geob200_node_correspondences(ref_nodes.data_ptr(), src_nodes.data_ptr(), ref_knn_points.data_ptr(),
+                                             src_knn_points.data_ptr(), L.ptr(ref_masks), L.ptr(src_masks),
+                                             L.ptr(ref_knn_masks), L.ptr(src_knn_masks), m, n, k, transform.data_ptr(),
+                                             float(pos_radius), idx.data_ptr(), ov.data_ptr(), cnt.data_ptr(), ws.data_ptr(),
+                                             ws.numel(), L.stream_ptr()), 'node_correspondences')
+    return idx, ov, cnt
+
+
+def finish_node_correspondences(idx, ov, cnt):
+    c = int(cnt.item())
+    return idx[:c], ov[:c]
+
+
+EVAL_MODES = {'3dmatch': 0, 'kitti': 1, 'modelnet': 2}
+
+
+def evaluate(gt_node_corr_indices, gt_node_corr_overlaps, ref_node_corr_indices, src_node_corr_indices, ref_corr_points,
+             src_corr_points, gt_transform, est_transform, src_points, mode, acceptance_overlap, acceptance_radius,
+             rmse_threshold=0.0, rre_threshold=0.0, rte_threshold=0.0, out=None):
+    """Evaluator.forward (reference experiments/<exp>/loss.py:95-159) as one launch; returns a device tensor
+    ``[PIR, IR, RRE, RTE, RMSE, RR, #corr, #gt_node_corr]``."""
+    dev = est_transform.device
+    if out is None:
+        out = torch.empty((8,), dtype=_f32, device=dev)
+    for t, name in ((ref_corr_points, 'ref_corr_points'), (src_corr_points, 'src_corr_points'), (gt_transform, 'transform'),
+                    (est_transform, 'estimated_transform'), (src_points, 'src_points'), (gt_node_corr_overlaps, 'overlaps')):
+        _f(t, name)
+    for t, name in ((gt_node_corr_indices, 'gt_node_corr_indices'), (ref_node_corr_indices, 'ref_node_corr_indices'),
+                    (src_node_corr_indices, 'src_node_corr_indices')):
+        L.require_cuda(t, name, _i64)
+    L.check(L.lib().geob200_evaluate(gt_node_corr_indices.data_ptr(), gt_node_corr_overlaps.data_ptr(),
+                                     gt_node_corr_indices.shape[0], float(acceptance_overlap),
+                                     ref_node_corr_indices.data_ptr(), src_node_corr_indices.data_ptr(),
+                                     ref_node_corr_indices.shape[0], ref_corr_points.data_ptr(), src_corr_points.data_ptr(),
+                                     ref_corr_points.shape[0], float(acceptance_radius), gt_transform.data_ptr(),
+                                     est_transform.data_ptr(), src_points.data_ptr(), src_points.shape[0], int(mode),
+                                     float(rmse_threshold), float(rre_threshold), float(rte_threshold), out.data_ptr(),
+                                     L.stream_ptr()), 'evaluate')
+    return out

@@ -2,8 +2,8 @@
 
 Reference: ``experiments/*/model.py:18-217``.  Same attribute names (``backbone``, ``transformer``,
 ``coarse_matching``, ``fine_matching``, ``optimal_transport``) and hence the same ``state_dict`` keys; same
-``forward(data_dict) -> output_dict`` contract.  ``gt_node_corr_*`` (needs the ground-truth transform, feeds only
-the training target and the PIR metric) is SURVEY.md section 8f "next" #1 and is not produced.
+``forward(data_dict) -> output_dict`` contract, including ``gt_node_corr_indices/overlaps`` (model.py:112-126, computed
+whenever ``data_dict`` carries the ground-truth ``transform``; the reference requires it).
 """
 import torch
 import torch.nn as nn
@@ -63,6 +63,18 @@ class GeoTransformer(nn.Module):
             taps.update(ref_node_masks=ref_node_masks, src_node_masks=src_node_masks, ref_node_knn_indices=ref_knn_idx,
                         src_node_knn_indices=src_knn_idx, ref_node_knn_masks=ref_knn_masks, src_node_knn_masks=src_knn_masks)
 
+        # ground-truth superpoint correspondences (reference model.py:106-126).  Launched here, read back after the last
+        # host sync of the forward so that it costs no extra synchronisation.
+        gt_pending = None
+        transform = data_dict.get('transform')
+        if transform is not None:
+            ar_r = GF.scratch_arange(ref_c.shape[0], ref_c.device, 'ar_ref')
+            ar_s = GF.scratch_arange(src_c.shape[0], src_c.device, 'ar_src')
+            _, _, ref_all_pts = GF.gather_patches(ar_r, ref_knn_idx, ref_knn_masks, ref_f)
+            _, _, src_all_pts = GF.gather_patches(ar_s, src_knn_idx, src_knn_masks, src_f)
+            gt_pending = GF.node_correspondences(ref_c, src_c, ref_all_pts, src_all_pts, transform, self.matching_radius,
+                                                 ref_node_masks, src_node_masks, ref_knn_masks, src_knn_masks)
+
         native = getattr(self, '_native', None)          # NativeModel: backbone / transformer as one C call each
         feats_list = native.backbone_forward(feats, data_dict) if native is not None else self.backbone(feats, data_dict)
         feats_c, feats_f = feats_list[-1], feats_list[0]
@@ -93,6 +105,8 @@ class GeoTransformer(nn.Module):
 
         rc, sc, cs, T = self.fine_matching(rk_pts, sk_pts, rk_masks, sk_masks, scores, node_scores)
         out.update(ref_corr_points=rc, src_corr_points=sc, corr_scores=cs, estimated_transform=T)
+        if gt_pending is not None:
+            out['gt_node_corr_indices'], out['gt_node_corr_overlaps'] = GF.finish_node_correspondences(*gt_pending)
         return out
 
 

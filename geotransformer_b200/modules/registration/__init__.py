@@ -27,3 +27,13 @@ class WeightedProcrustes(nn.Module):
     def forward(self, src_points, tgt_points, weights=None):
         return weighted_procrustes(src_points, tgt_points, weights=weights, weight_thresh=self.weight_thresh, eps=self.eps,
                                    return_transform=self.return_transform)
+
+
+@torch.no_grad()
+def get_node_correspondences(ref_nodes, src_nodes, ref_knn_points, src_knn_points, transform, pos_radius, ref_masks=None,
+                             src_masks=None, ref_knn_masks=None, src_knn_masks=None):
+    """reference ``geotransformer/modules/registration/matching.py:231-315``: ``(corr_indices (C,2), corr_overlaps (C,))``."""
+    res = GF.node_correspondences(ref_nodes.contiguous(), src_nodes.contiguous(), ref_knn_points.contiguous(),
+                                  src_knn_points.contiguous(), transform.contiguous(), pos_radius, ref_masks, src_masks,
+                                  ref_knn_masks, src_knn_masks)
+    return GF.finish_node_correspondences(*res)

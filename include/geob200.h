@@ -177,6 +177,28 @@ int geob200_local_global_registration(const float* ref_knn_points, const float* 
 int geob200_weighted_procrustes(const float* src_points, const float* ref_points, const float* weights, int64_t batch,
                                 int64_t n, float weight_thresh, float eps, float* transforms, void* stream);
 
+/* get_node_correspondences (modules/registration/matching.py:231-315): ground-truth superpoint pairs and their overlap
+ * ratios under `transform` (4x4, device).  Masks are uint8 (torch.bool) or NULL (= all valid).  corr_indices (capacity
+ * n_ref*n_src rows of 2 int64) and corr_overlaps (capacity n_ref*n_src) receive the pairs with overlap > 0 in row-major
+ * (ref, src) order, `count` (device int32) their number. */
+size_t geob200_node_correspondences_workspace_bytes(int64_t n_ref, int64_t n_src, int64_t k);
+int geob200_node_correspondences(const float* ref_nodes, const float* src_nodes, const float* ref_knn_points,
+                                 const float* src_knn_points, const uint8_t* ref_masks, const uint8_t* src_masks,
+                                 const uint8_t* ref_knn_masks, const uint8_t* src_knn_masks, int64_t n_ref, int64_t n_src,
+                                 int64_t k, const float* transform, float pos_radius, int64_t* corr_indices,
+                                 float* corr_overlaps, int32_t* count, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Evaluator.forward (experiments/<exp>/loss.py:95-159; metrics.py:47-112): metrics[8] (device) =
+ * {PIR, IR, RRE [deg], RTE, RMSE, RR, #correspondences, #gt superpoint pairs}.  mode 0 = 3DMatch (RMSE of the realigned
+ * source cloud, RR = RMSE < rmse_threshold), 1 = KITTI (no RMSE: NaN; RR = RRE < rre_threshold and RTE < rte_threshold),
+ * 2 = ModelNet (RMSE of T_est x - T_gt x; RR as KITTI).  Means over empty sets are NaN, as torch reports them. */
+int geob200_evaluate(const int64_t* gt_node_corr_indices, const float* gt_node_corr_overlaps, int64_t n_gt,
+                     float acceptance_overlap, const int64_t* ref_node_corr_indices, const int64_t* src_node_corr_indices,
+                     int64_t n_node_corr, const float* ref_corr_points, const float* src_corr_points, int64_t n_corr,
+                     float acceptance_radius, const float* gt_transform, const float* est_transform, const float* src_points,
+                     int64_t n_src_points, int mode, float rmse_threshold, float rre_threshold, float rte_threshold,
+                     float* metrics, void* stream);
+
 /* ---- native stage drivers (native.cu) ------------------------------------------------------------------------
  * The whole KPConv-FPN backbone / geometric transformer as ONE call: same kernels in the same order as the per-op entry
  * points above (bitwise-identical results), driven from C++ so that the host cost per pair is a few hundred microseconds

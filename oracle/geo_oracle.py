@@ -479,8 +479,7 @@ def local_global_registration(cfg, ref_knn_pts, src_knn_pts, ref_masks, src_mask
 # ------------------------------------------------------------------------------------------------ assembly
 
 def forward(sd, cfg, data, taps=None):
-    """experiments/*/model.py:69-212 at inference (GT node correspondences are not produced here: they need the
-    GT transform and feed only the training target / PIR metric -- SURVEY.md section 8f 'next' #1)."""
+    """experiments/*/model.py:69-212 at inference; gt_node_corr_* (model.py:112-126) when data carries 'transform'."""
     out = {}
     fl = cfg.model.fine_level
     lens, pts = data['lengths'], data['points']
@@ -498,6 +497,11 @@ def forward(sd, cfg, data, taps=None):
     if taps is not None:
         taps.update(ref_node_masks=r_nm, src_node_masks=s_nm, ref_node_knn_indices=r_knn, src_node_knn_indices=s_knn,
                     ref_node_knn_masks=r_km, src_node_knn_masks=s_km)
+
+    if data.get('transform') is not None:
+        gi, go = get_node_correspondences(ref_c, src_c, r_knn_pts, s_knn_pts, torch.as_tensor(data['transform']),
+                                          cfg.model.ground_truth_matching_radius, r_nm, s_nm, r_km, s_km)
+        out.update(gt_node_corr_indices=gi, gt_node_corr_overlaps=go)
 
     feats_list = backbone(sd, cfg, data['features'], data, taps=taps)
     feats_c, feats_f = feats_list[-1], feats_list[0]
@@ -526,6 +530,60 @@ def forward(sd, cfg, data, taps=None):
     rc, sc_, cs, T = local_global_registration(cfg, rk_p, sk_p, rk_m, sk_m, sm, taps=taps)
     out.update(ref_corr_points=rc, src_corr_points=sc_, corr_scores=cs, estimated_transform=T)
     return out
+
+
+def get_node_correspondences(ref_nodes, src_nodes, ref_knn_points, src_knn_points, transform, pos_radius, ref_masks,
+                             src_masks, ref_knn_masks, src_knn_masks):
+    """modules/registration/matching.py:231-315: GT superpoint pairs = patches sharing at least one point pair closer
+    than pos_radius after the GT transform; overlap = mean of the two covered fractions."""
+    src_nodes = apply_transform(src_nodes, transform)
+    src_knn_points = apply_transform(src_knn_points, transform)
+    node_ok = ref_masks[:, None] & src_masks[None, :]
+    r_d = torch.linalg.norm(ref_knn_points - ref_nodes[:, None], dim=-1).masked_fill(~ref_knn_masks, 0.0).max(1)[0]
+    s_d = torch.linalg.norm(src_knn_points - src_nodes[:, None], dim=-1).masked_fill(~src_knn_masks, 0.0).max(1)[0]
+    centre = torch.sqrt(pairwise_distance(ref_nodes, src_nodes))
+    cand = ((r_d[:, None] + s_d[None, :] + pos_radius - centre) > 0) & node_ok
+    ri, si = torch.nonzero(cand, as_tuple=True)
+    overlaps = torch.zeros(ri.shape[0])
+    for lo in range(0, ri.shape[0], 4096):                       # bounded (B,K,K) chunks
+        r, s_ = ri[lo:lo + 4096], si[lo:lo + 4096]
+        rm, sm_ = ref_knn_masks[r], src_knn_masks[s_]
+        d = pairwise_distance(ref_knn_points[r], src_knn_points[s_])
+        d = d.masked_fill(~(rm[:, :, None] & sm_[:, None, :]), 1e12)
+        hit = d < pos_radius ** 2
+        rc = torch.count_nonzero(hit.sum(-1), dim=-1).float() / rm.sum(-1).float()
+        sc = torch.count_nonzero(hit.sum(-2), dim=-1).float() / sm_.sum(-1).float()
+        overlaps[lo:lo + 4096] = (rc + sc) / 2
+    keep = overlaps > 0
+    return torch.stack([ri[keep], si[keep]], dim=1), overlaps[keep]
+
+
+def evaluate(cfg, out, transform):
+    """experiments/<exp>/loss.py:95-159 Evaluator.forward (3DMatch / KITTI / ModelNet variants by cfg.name)."""
+    e = cfg.eval
+    T_gt = torch.as_tensor(transform)
+    gi, go = out['gt_node_corr_indices'], out['gt_node_corr_overlaps']
+    gi = gi[go > e.acceptance_overlap]
+    gmap = torch.zeros(out['ref_points_c'].shape[0], out['src_points_c'].shape[0])
+    gmap[gi[:, 0], gi[:, 1]] = 1.0
+    res = {'PIR': gmap[out['ref_node_corr_indices'], out['src_node_corr_indices']].mean()}
+    d = torch.linalg.norm(out['ref_corr_points'] - apply_transform(out['src_corr_points'], T_gt), dim=1)
+    res['IR'] = (d < e.acceptance_radius).float().mean()
+    T = out['estimated_transform']
+    x = 0.5 * (torch.trace(T[:3, :3].T @ T_gt[:3, :3]) - 1.0)
+    rre = 180.0 * torch.arccos(x.clamp(min=-1.0, max=1.0)) / np.pi
+    rte = torch.linalg.norm(T_gt[:3, 3] - T[:3, 3])
+    res['RRE'], res['RTE'] = rre, rte
+    src = out['src_points']
+    if cfg.name == '3dmatch':
+        re = apply_transform(src, torch.inverse(T_gt) @ T)
+        res['RMSE'] = torch.linalg.norm(re - src, dim=1).mean()
+        res['RR'] = (res['RMSE'] < e.rmse_threshold).float()
+    else:
+        if cfg.name == 'modelnet':
+            res['RMSE'] = torch.linalg.norm(apply_transform(src, T) - apply_transform(src, T_gt), dim=1).mean()
+        res['RR'] = ((rre < e.rre_threshold) & (rte < e.rte_threshold)).float()
+    return res
 
 
 def registration_error(gt, est):

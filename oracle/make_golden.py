@@ -88,8 +88,33 @@ def run(workload):
         report[k] = (tuple(a.shape) == tuple(b.shape)) and float((a - b).abs().max()) if a.shape == b.shape else 'SHAPE'
     for k in ('ref_node_corr_indices', 'src_node_corr_indices'):
         report[k] = bool(torch.equal(o[k], ref_out[k]))
+    # ground-truth superpoint correspondences and the Evaluator (loss.py:95-159)
+    report['gt_node_corr_indices'] = bool(torch.equal(o['gt_node_corr_indices'], ref_out['gt_node_corr_indices']))
+    report['gt_node_corr_overlaps'] = float((o['gt_node_corr_overlaps'] - ref_out['gt_node_corr_overlaps']).abs().max())
+    evaluator = ref_harness.load_evaluator(pair['config'], rcfg)
+    with torch.no_grad():
+        ref_metrics = {k: float(v) for k, v in evaluator(ref_out, data).items()}
+    o_metrics = {k: float(v) for k, v in geo_oracle.evaluate(cfg, o, data['transform']).items()}
+    assert set(ref_metrics) == set(o_metrics), (ref_metrics, o_metrics)
+    for k in ref_metrics:
+        report['metric_' + k] = abs(ref_metrics[k] - o_metrics[k])
+    # the other two Evaluator variants (KITTI: no RMSE, RR from RRE/RTE; ModelNet: RMSE of T_est x - T_gt x) on the same outputs
+    other_metrics = {}
+    for other in ('3dmatch', 'kitti', 'modelnet'):
+        if other == pair['config']:
+            continue
+        ocfg_ref, _ = ref_harness.load_experiment(other)
+        with torch.no_grad():
+            rm = {k: float(v) for k, v in ref_harness.load_evaluator(other, ocfg_ref)(ref_out, data).items()}
+        om = {k: float(v) for k, v in geo_oracle.evaluate(make_cfg(other), o, data['transform']).items()}
+        assert set(rm) == set(om), (rm, om)
+        for k in rm:
+            report[f'metric_{other}_{k}'] = abs(rm[k] - om[k])
+        other_metrics[other] = rm
+    print(f'[{workload}] reference metrics:', ref_metrics)
     print(f'[{workload}] oracle-vs-reference max abs diff:', report)
-    bad = [k for k, v in report.items() if v == 'SHAPE' or v is False or (isinstance(v, float) and v > 1e-5)]
+    bad = [k for k, v in report.items() if v == 'SHAPE' or v is False or
+           (isinstance(v, float) and v > (1e-3 if k.endswith('RRE') else 1e-5))]   # RRE: acos of an fp32 3x3 product
     assert not bad, f'oracle restatement deviates from the reference: {bad}'
 
     # ---- fixtures
@@ -109,6 +134,13 @@ def run(workload):
     for k in ('ref_feats_c', 'src_feats_c', 'estimated_transform', 'corr_scores', 'ref_corr_points', 'src_corr_points',
               'ref_node_corr_indices', 'src_node_corr_indices'):
         g[k] = ref_out[k].detach().numpy()
+    g['gt_node_corr_indices'] = ref_out['gt_node_corr_indices'].numpy()
+    g['gt_node_corr_overlaps'] = ref_out['gt_node_corr_overlaps'].numpy()
+    g['metric_names'] = np.array(sorted(ref_metrics))
+    g['metric_values'] = np.array([ref_metrics[k] for k in sorted(ref_metrics)], dtype=np.float64)
+    for other, rm in other_metrics.items():
+        g['metric_names_' + other] = np.array(sorted(rm))
+        g['metric_values_' + other] = np.array([rm[k] for k in sorted(rm)], dtype=np.float64)
     g['node_corr_scores'] = o['node_corr_scores'].numpy()
     idx, rows = sample_rows(ref_out['matching_scores'].reshape(ref_out['matching_scores'].shape[0], -1), 16)
     g['matching_scores_rows'], g['matching_scores_sample'] = idx, rows

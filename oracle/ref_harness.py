@@ -118,6 +118,19 @@ def load_experiment(which):
     return config.make_cfg(), model.create_model
 
 
+def load_evaluator(which, cfg):
+    """The reference Evaluator (experiments/<exp>/loss.py) of the experiment; call after load_experiment(which).
+    Its .cuda() allocations resolve to CPU clones through install()."""
+    exp_dir = os.path.join(REF_ROOT, 'experiments', EXP[which])
+    sys.modules.pop('loss', None)
+    sys.path.insert(0, exp_dir)
+    try:
+        loss = importlib.import_module('loss')
+    finally:
+        sys.path.remove(exp_dir)
+    return loss.Evaluator(cfg)
+
+
 def kernel_disposition():
     """The 15x3 float64 kernel-point disposition shipped with the reference (a data fixture)."""
     return _read_ply_points(os.path.join(REF_ROOT, 'geotransformer/modules/kpconv/dispositions/k_015_center_3D.ply'))

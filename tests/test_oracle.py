@@ -73,6 +73,13 @@ def test_forward_restatement_matches_reference_fixture(golden, models):
     assert np.array_equal(out['ref_node_corr_indices'].numpy(), gold['ref_node_corr_indices'])
     assert np.array_equal(out['ref_corr_points'].numpy(), gold['ref_corr_points'])
     assert np.abs(out['estimated_transform'].numpy() - gold['estimated_transform']).max() < 1e-5
+    # ground-truth superpoint correspondences (matching.py:231-315) and the Evaluator (loss.py:95-159)
+    assert np.array_equal(out['gt_node_corr_indices'].numpy(), gold['gt_node_corr_indices'])
+    assert np.abs(out['gt_node_corr_overlaps'].numpy() - gold['gt_node_corr_overlaps']).max() < 1e-6
+    metrics = G.evaluate(cfg, out, data['transform'])
+    assert sorted(metrics) == gold['metric_names'].tolist()
+    for name, v in zip(gold['metric_names'].tolist(), gold['metric_values']):
+        assert abs(float(metrics[name]) - v) < (1e-3 if name == 'RRE' else 1e-5), name
 
 
 def test_sinkhorn_marginals_property():
