@@ -422,8 +422,9 @@ def node_correspondences(ref_nodes, src_nodes, ref_knn_points, src_knn_points, t
     dev = ref_nodes.device
     lib = L.lib()
     ws = L.workspace(lib.geob200_node_correspondences_workspace_bytes(m, n, k), dev, tag='node_corr')
-    idx = torch.empty((m * n, 2), dtype=_i64, device=dev)
-    ov = torch.empty((m * n,), dtype=_f32, device=dev)
+    cap = (m * n + 65535) // 65536 * 65536          # rounded: same block sizes from pair to pair (no allocator churn)
+    idx = torch.empty((cap, 2), dtype=_i64, device=dev)
+    ov = torch.empty((cap,), dtype=_f32, device=dev)
     cnt = torch.empty((1,), dtype=_i32, device=dev)
     L.check(lib.geob200_node_correspondences(ref_nodes.data_ptr(), src_nodes.data_ptr(), ref_knn_points.data_ptr(),
                                              src_knn_points.data_ptr(), L.ptr(ref_masks), L.ptr(src_masks),

@@ -1,6 +1,6 @@
 """Per-stage GPU time of one pair (CUDA events, warm), single stream.  Dev tool."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, numpy as np
 from geotransformer_b200 import functional as GF
 from geotransformer_b200.config import make_cfg
