@@ -48,7 +48,8 @@ _sig('geob200_gather_rows', c_int, P, I64, I64, P, I64, P, P)
 _sig('geob200_gse_indices', c_int, P, I64, F, F, I64, P, P, P)
 _sig('geob200_gse_embed_workspace_bytes', SZ, I64, I64)
 _sig('geob200_gse_embed', c_int, P, P, I64, I64, P, P, P, P, P, P, P, P, c_int, P, SZ, P)
-_sig('geob200_attention', c_int, P, I64, P, I64, P, I64, P, P, P, I64, I64, I64, I64, P, I64, P)
+_sig('geob200_attention_workspace_bytes', SZ, I64, I64, I64)
+_sig('geob200_attention', c_int, P, I64, P, I64, P, I64, P, P, P, I64, I64, I64, I64, P, I64, P, SZ, P)
 _sig('geob200_head_bias', c_int, P, I64, P, I64, I64, I64, P, P)
 _sig('geob200_add_layernorm', c_int, P, P, P, P, I64, I64, F, P, P)
 _sig('geob200_l2_normalize', c_int, P, I64, I64, P, P)

@@ -160,6 +160,177 @@ __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict_
     }
 }
 
+// ---- streaming path (C = 128 or 256) ---------------------------------------------------------------------------
+// The self-attention layers are bound by the single pass over E (N*M*C*4 bytes, 105 MB at N = 320, C = 256).  With
+// lanes <-> keys (kernel above) every lane walks its own 1 KB row: 32 rows in flight per request, and a grid of N/2
+// CTAs leaves the last wave almost empty.  Here lanes <-> CHANNELS: a warp reads one E row as 1 KB of perfectly
+// coalesced float4 loads, keeps its slice of q / qp in registers, and the per-head sums of 4 keys (4*H values) are
+// reduced across the warp with a transposing butterfly (4*H-1 shuffles instead of 5 per value).  The grid is
+// (query, key chunk): ~600 small CTAs stream E at HBM speed; raw scores go to a (N,H,M) scratch (1.6 MB) and a second
+// small kernel does softmax and P.V.
+constexpr int ATS_G = 4;          // keys per butterfly group
+
+__device__ __forceinline__ float dot4(const float4 a, const float4 b, float acc) {
+    return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc))));
+}
+
+template <int H, int J>
+__global__ void __launch_bounds__(128) att_scores_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk,
+                                                         const float* __restrict__ qp, const float* __restrict__ qb,
+                                                         const float* __restrict__ E, int N, int M, int keys_per_cta, float div,
+                                                         float* __restrict__ S) {
+    constexpr int C = 128 * J;
+    constexpr int D = C / H;
+    constexpr int NV = ATS_G * H;                 // values reduced together: (key u, head h) -> v[u * H + h]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = blockIdx.x;
+    const int m_begin = blockIdx.y * keys_per_cta;
+    const int m_end = min(M, m_begin + keys_per_cta);
+    const bool has_e = (E != nullptr);
+    float4 qv[J];
+    float4 qpv[H][J];
+    int hq[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        const int c = j * 128 + 4 * lane;
+        qv[j] = *reinterpret_cast<const float4*>(q + (long long)n * ldq + c);
+        hq[j] = c / D;
+#pragma unroll
+        for (int h = 0; h < H; ++h)
+            qpv[h][j] = has_e ? *reinterpret_cast<const float4*>(qp + ((long long)n * H + h) * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float* e_row = has_e ? E + (long long)n * M * C : nullptr;
+    for (int m0 = m_begin + warp * ATS_G; m0 < m_end; m0 += 4 * ATS_G) {
+        float4 kk[ATS_G][J], ee[ATS_G][J];
+#pragma unroll
+        for (int u = 0; u < ATS_G; ++u) {
+            const int m = min(m0 + u, M - 1);
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                kk[u][j] = __ldg(reinterpret_cast<const float4*>(k + (long long)m * ldk + j * 128 + 4 * lane));
+                if (has_e) ee[u][j] = __ldcs(reinterpret_cast<const float4*>(e_row + (long long)m * C + j * 128 + 4 * lane));
+            }
+        }
+        float v[NV];
+#pragma unroll
+        for (int u = 0; u < ATS_G; ++u) {
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                float a = 0.f;
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    const float p = dot4(kk[u][j], qv[j], 0.f);
+                    a += (hq[j] == h) ? p : 0.f;
+                    if (has_e) a = dot4(ee[u][j], qpv[h][j], a);
+                }
+                v[u * H + h] = a;
+            }
+        }
+        // transposing butterfly: after the step with `mask`, a lane keeps the half of the values selected by that lane bit
+        int cnt = NV;
+#pragma unroll
+        for (int mask = 16; mask >= 1; mask >>= 1) {
+            if (cnt > 1) {
+                const int half = cnt / 2;
+                const bool upper = (lane & mask) != 0;
+#pragma unroll
+                for (int i = 0; i < half; ++i) {
+                    const float send = upper ? v[i] : v[i + half];
+                    const float keep = upper ? v[i + half] : v[i];
+                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+                }
+                cnt = half;
+            } else {
+                v[0] += __shfl_xor_sync(0xffffffffu, v[0], mask);
+            }
+        }
+        // NV = 2^b values: value index = the top b lane bits; one lane per value writes
+        constexpr int SH = (NV == 32) ? 0 : (NV == 16) ? 1 : (NV == 8) ? 2 : 3;
+        const int idx = lane >> SH;
+        const int u = idx / H, h = idx % H;
+        if ((lane & ((1 << SH) - 1)) == 0 && m0 + u < m_end) {
+            const float bias = has_e ? qb[(long long)n * H + h] : 0.f;
+            S[((long long)n * H + h) * M + m0 + u] = (v[0] + bias) / div;
+        }
+    }
+}
+
+// softmax over the keys and P.V for R = 2 queries per CTA (value rows fetched once for both); thread <-> channel
+template <int H>
+__global__ void __launch_bounds__(256) att_softmax_pv_kernel(const float* __restrict__ S, const float* __restrict__ v, int ldv, int N,
+                                                             int M, int C, float* __restrict__ out, int ldo) {
+    extern __shared__ float sm[];
+    float* sc = sm;                               // [R][H][M]
+    const int n0 = blockIdx.x * ATT_R;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int d = C / H;
+    for (int rh = warp; rh < ATT_R * H; rh += 8) {
+        const int r = rh / H;
+        float* s = sc + rh * M;
+        if (n0 + r >= N) {
+            for (int m = lane; m < M; m += 32) s[m] = 0.f;
+            continue;
+        }
+        const float* src = S + ((long long)(n0 + r) * H + (rh % H)) * M;
+        float mx = -INFINITY;
+        for (int m = lane; m < M; m += 32) { const float x = src[m]; s[m] = x; mx = fmaxf(mx, x); }
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (int m = lane; m < M; m += 32) {
+            const float e = expf(s[m] - mx);
+            s[m] = e;
+            sum += e;
+        }
+        sum = warp_sum(sum);
+        for (int m = lane; m < M; m += 32) s[m] = s[m] / sum;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int h = c / d;
+        const float* p0 = sc + (0 * H + h) * M;
+        const float* p1 = sc + (1 * H + h) * M;
+        float a0[8], a1[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { a0[u] = 0.f; a1[u] = 0.f; }
+        int m = 0;
+        for (; m + 7 < M; m += 8) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float vv = v[(long long)(m + u) * ldv + c];
+                a0[u] = fmaf(p0[m + u], vv, a0[u]);
+                a1[u] = fmaf(p1[m + u], vv, a1[u]);
+            }
+        }
+        for (; m < M; ++m) {
+            const float vv = v[(long long)m * ldv + c];
+            a0[0] = fmaf(p0[m], vv, a0[0]);
+            a1[0] = fmaf(p1[m], vv, a1[0]);
+        }
+        if (n0 < N) out[(long long)n0 * ldo + c] = ((a0[0] + a0[1]) + (a0[2] + a0[3])) + ((a0[4] + a0[5]) + (a0[6] + a0[7]));
+        if (n0 + 1 < N) out[(long long)(n0 + 1) * ldo + c] = ((a1[0] + a1[1]) + (a1[2] + a1[3])) + ((a1[4] + a1[5]) + (a1[6] + a1[7]));
+    }
+}
+
+template <int H, int J>
+static int launch_streaming(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, const float* qp, const float* qb,
+                            const float* E, int N, int M, float div, float* out, int ldo, float* S, cudaStream_t st) {
+    // enough CTAs to fill the GPU several times over, but at least 64 keys per CTA so that q / qp loads stay amortised
+    int chunks = (4 * num_sms() + N - 1) / N;
+    chunks = max(1, min(chunks, M / 64));
+    int kpc = (M + chunks - 1) / chunks;
+    kpc = (kpc + 4 * ATS_G - 1) / (4 * ATS_G) * (4 * ATS_G);
+    chunks = (M + kpc - 1) / kpc;
+    att_scores_kernel<H, J><<<dim3((unsigned)N, (unsigned)chunks), 128, 0, st>>>(q, ldq, k, ldk, qp, qb, E, N, M, kpc, div, S);
+    const size_t smem = sizeof(float) * ATT_R * H * M;
+    static size_t smem_set = 0;
+    if (smem > 48 * 1024 && smem > smem_set) {
+        if (cudaFuncSetAttribute(att_softmax_pv_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+        smem_set = smem;
+    }
+    att_softmax_pv_kernel<H><<<(unsigned)((N + ATT_R - 1) / ATT_R), 256, smem, st>>>(S, v, ldv, N, M, 128 * J, out, ldo);
+    return 0;
+}
+
 // qb[n][h] = sum_c q[n][h*d + c] * bp[h*d + c]
 __global__ void __launch_bounds__(256) head_bias_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ bp, int N, int C,
                                                         int H, float* __restrict__ qb) {
@@ -211,9 +382,13 @@ using namespace geob200;
 
 extern "C" {
 
+size_t geob200_attention_workspace_bytes(int64_t n_query, int64_t n_key, int64_t heads) {
+    return (size_t)n_query * (size_t)n_key * (size_t)heads * sizeof(float) + 256;
+}
+
 int geob200_attention(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv, const float* qp,
                       const float* qb, const float* embed, int64_t n_query, int64_t n_key, int64_t channels, int64_t heads,
-                      float* out, int64_t ldo, void* stream) {
+                      float* out, int64_t ldo, void* workspace, size_t workspace_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     GEOB_REQUIRE(n_query > 0 && n_key > 0, "attention: empty input");
     GEOB_REQUIRE(channels % 4 == 0 && channels <= 256 && heads > 0 && heads <= ATT_MAXH && channels % heads == 0 &&
@@ -221,6 +396,35 @@ int geob200_attention(const float* q, int64_t ldq, const float* k, int64_t ldk, 
                  "attention: unsupported channels=%lld heads=%lld", (long long)channels, (long long)heads);
     GEOB_REQUIRE((embed == nullptr) == (qp == nullptr) && (embed == nullptr) == (qb == nullptr), "attention: qp/qb/embed must come together");
     GEOB_REQUIRE(ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0, "attention: row strides must be multiples of 4 floats");
+    GEOB_REQUIRE(heads == 1 || heads == 2 || heads == 4 || heads == 8, "attention: heads must be 1, 2, 4 or 8");
+    const float div = sqrtf((float)(channels / heads));   // d_model_per_head ** 0.5
+    const size_t smem_pv = sizeof(float) * ATT_R * heads * n_key;
+    if ((channels == 128 || channels == 256) && smem_pv <= 200 * 1024 && workspace != nullptr) {
+        // streaming path: lanes <-> channels, (query, key-chunk) grid, scores through the workspace
+        GEOB_REQUIRE(workspace_bytes >= geob200_attention_workspace_bytes(n_query, n_key, heads), "attention: workspace too small");
+        GEOB_REQUIRE(((uintptr_t)q % 16) == 0 && ((uintptr_t)k % 16) == 0 && (qp == nullptr || ((uintptr_t)qp % 16) == 0) &&
+                         (embed == nullptr || ((uintptr_t)embed % 16) == 0),
+                     "attention: q, k, qp, embed must be 16-byte aligned");
+        float* S = (float*)workspace;
+        int rc = -2;
+#define LAUNCH_STREAM(HV)                                                                                                            \
+    rc = (channels == 256) ? launch_streaming<HV, 2>(q, (int)ldq, k, (int)ldk, v, (int)ldv, qp, qb, embed, (int)n_query, (int)n_key, \
+                                                     div, out, (int)ldo, S, st)                                                       \
+                           : launch_streaming<HV, 1>(q, (int)ldq, k, (int)ldk, v, (int)ldv, qp, qb, embed, (int)n_query, (int)n_key, \
+                                                     div, out, (int)ldo, S, st)
+        switch (heads) {
+            case 1: LAUNCH_STREAM(1); break;
+            case 2: LAUNCH_STREAM(2); break;
+            case 4: LAUNCH_STREAM(4); break;
+            default: LAUNCH_STREAM(8); break;
+        }
+#undef LAUNCH_STREAM
+        GEOB_REQUIRE(rc == 0, "attention: could not configure the softmax kernel");
+        GEOB_CHECK_LAUNCH();
+        count_launches(2);
+        return 0;
+    }
+    // generic path (any C <= 256 that is a multiple of 4; no workspace needed)
     const size_t smem = sizeof(float) * (ATT_R * channels + ATT_R * heads * channels + ATT_R * heads * n_key);
     GEOB_REQUIRE(smem <= 200 * 1024, "attention: too many keys (%lld)", (long long)n_key);
     static size_t smem_set = 0;
@@ -231,7 +435,6 @@ int geob200_attention(const float* q, int64_t ldq, const float* k, int64_t ldk, 
         GEOB_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
-    const float div = sqrtf((float)(channels / heads));   // d_model_per_head ** 0.5
     const unsigned grid = (unsigned)((n_query + ATT_R - 1) / ATT_R);
 #define LAUNCH_ATT(HV)                                                                                                              \
     attention_kernel<HV><<<grid, 256, smem, st>>>(q, (int)ldq, k, (int)ldk, v, (int)ldv, qp, qb, embed, (int)n_query, (int)n_key,  \
@@ -240,8 +443,7 @@ int geob200_attention(const float* q, int64_t ldq, const float* k, int64_t ldk, 
         case 1: LAUNCH_ATT(1); break;
         case 2: LAUNCH_ATT(2); break;
         case 4: LAUNCH_ATT(4); break;
-        case 8: LAUNCH_ATT(8); break;
-        default: GEOB_REQUIRE(false, "attention: heads must be 1, 2, 4 or 8");
+        default: LAUNCH_ATT(8); break;
     }
 #undef LAUNCH_ATT
     GEOB_CHECK_LAUNCH();

@@ -177,7 +177,8 @@ int geob200_backbone_forward(const geob200_backbone_t* net, const float* feats, 
 
 size_t geob200_transformer_workspace_bytes(int64_t n0, int64_t n1, int64_t channels, int64_t heads, int64_t num_layers) {
     const size_t n = (size_t)(n0 + n1), c = (size_t)channels;
-    return (n * c * 4 * (3 + 1 + heads + 12)) * (size_t)(num_layers + 1) + (1 << 20);
+    const size_t nmax = (size_t)(n0 > n1 ? n0 : n1);
+    return (n * c * 4 * (3 + 1 + heads + 12)) * (size_t)(num_layers + 1) + nmax * nmax * (size_t)heads * 4 + (2 << 20);
 }
 
 static int run_tail(Ctx& c, const geob200_tlayer_t& L, const float* hidden, const float* inp, int64_t rows, int64_t ch, float* out) {
@@ -202,6 +203,9 @@ int geob200_transformer_forward(const geob200_tlayer_t* layers, int64_t num_laye
     c.stream = stream;
     const int64_t n = n0 + n1, C = channels, H = heads;
     const float* x = x_in;
+    const int64_t nmax = n0 > n1 ? n0 : n1;
+    const size_t att_ws_bytes = geob200_attention_workspace_bytes(nmax, nmax, H);     // score scratch, reused by every layer
+    void* att_ws = c.fl((int64_t)(att_ws_bytes / 4 + 1), 1);
     for (int64_t i = 0; i < num_layers; ++i) {
         const geob200_tlayer_t& L = layers[i];
         float* y = (i == num_layers - 1) ? out : c.fl(n, C);
@@ -215,9 +219,9 @@ int geob200_transformer_forward(const geob200_tlayer_t* layers, int64_t num_laye
             const int64_t d = C / H;
             TRY(geob200_linear_batched(qkv, 3 * C, d, L.wp_t, C, d, nullptr, 0, qp, H * C, C, n, C, d, H, 0, stream));
             TRY(geob200_head_bias(qkv, 3 * C, L.bp, n, C, H, qb, stream));
-            TRY(geob200_attention(qkv, 3 * C, qkv + C, 3 * C, qkv + 2 * C, 3 * C, qp, qb, emb0, n0, n0, C, H, hidden, C, stream));
+            TRY(geob200_attention(qkv, 3 * C, qkv + C, 3 * C, qkv + 2 * C, 3 * C, qp, qb, emb0, n0, n0, C, H, hidden, C, att_ws, att_ws_bytes, stream));
             TRY(geob200_attention(qkv + n0 * 3 * C, 3 * C, qkv + n0 * 3 * C + C, 3 * C, qkv + n0 * 3 * C + 2 * C, 3 * C, qp + n0 * H * C,
-                                  qb + n0 * H, emb1, n1, n1, C, H, hidden + n0 * C, C, stream));
+                                  qb + n0 * H, emb1, n1, n1, C, H, hidden + n0 * C, C, att_ws, att_ws_bytes, stream));
             TRY(run_tail(c, L, hidden, x, n, C, y));
         } else {
             float* q0 = c.fl(n0, C);
@@ -230,12 +234,12 @@ int geob200_transformer_forward(const geob200_tlayer_t* layers, int64_t num_laye
             // feats0 <- layer(feats0, feats1)
             TRY(geob200_linear(x, C, L.w_q, L.b_q, q0, C, n0, C, C, 0, stream));
             TRY(geob200_linear(x + n0 * C, C, L.w_kv, L.b_kv, kv1, 2 * C, n1, 2 * C, C, 0, stream));
-            TRY(geob200_attention(q0, C, kv1, 2 * C, kv1 + C, 2 * C, nullptr, nullptr, nullptr, n0, n1, C, H, hid0, C, stream));
+            TRY(geob200_attention(q0, C, kv1, 2 * C, kv1 + C, 2 * C, nullptr, nullptr, nullptr, n0, n1, C, H, hid0, C, att_ws, att_ws_bytes, stream));
             TRY(run_tail(c, L, hid0, x, n0, C, y));
             // feats1 <- layer(feats1, UPDATED feats0)   (conditional_transformer.py:109-111, parallel=False)
             TRY(geob200_linear(x + n0 * C, C, L.w_q, L.b_q, q1, C, n1, C, C, 0, stream));
             TRY(geob200_linear(y, C, L.w_kv, L.b_kv, kv0, 2 * C, n0, 2 * C, C, 0, stream));
-            TRY(geob200_attention(q1, C, kv0, 2 * C, kv0 + C, 2 * C, nullptr, nullptr, nullptr, n1, n0, C, H, hid1, C, stream));
+            TRY(geob200_attention(q1, C, kv0, 2 * C, kv0 + C, 2 * C, nullptr, nullptr, nullptr, n1, n0, C, H, hid1, C, att_ws, att_ws_bytes, stream));
             TRY(run_tail(c, L, hid1, x + n0 * C, n1, C, y + n0 * C));
         }
         x = y;

@@ -248,16 +248,19 @@ def _rows(t, name):
     return t
 
 
-def attention(q, k, v, heads, qp=None, qb=None, embed=None, out=None):
-    """q, k, v may be column slices of a fused projection buffer (row stride != channels)."""
+def attention(q, k, v, heads, qp=None, qb=None, embed=None, out=None, streaming=True):
+    """q, k, v may be column slices of a fused projection buffer (row stride != channels).  streaming=False forces the
+    single-kernel path (the only one for channel counts other than 128 / 256)."""
     _rows(q, 'q'); _rows(k, 'k'); _rows(v, 'v')
     n, c = q.shape
     m = k.shape[0]
     if out is None:
         out = torch.empty((n, c), dtype=_f32, device=q.device)
-    L.check(L.lib().geob200_attention(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
-                                      L.ptr(qp), L.ptr(qb), L.ptr(embed), n, m, c, heads, out.data_ptr(), out.stride(0),
-                                      L.stream_ptr()), 'attention')
+    lib = L.lib()
+    ws = L.workspace(lib.geob200_attention_workspace_bytes(n, m, heads), q.device, tag='attention') if streaming else None
+    L.check(lib.geob200_attention(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
+                                  L.ptr(qp), L.ptr(qb), L.ptr(embed), n, m, c, heads, out.data_ptr(), out.stride(0),
+                                  L.ptr(ws), 0 if ws is None else ws.numel(), L.stream_ptr()), 'attention')
     return out
 
 

@@ -49,6 +49,19 @@ def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, 
             'neighbors': neighbors_list, 'subsampling': subsampling_list, 'upsampling': upsampling_list}
 
 
+def _stack_to_device(tensors, device):
+    """torch.cat(tensors).to(device) without the host-side concatenation"""
+    if all(t.is_cuda for t in tensors):
+        return tensors[0] if len(tensors) == 1 else torch.cat(tensors, dim=0)
+    total = sum(int(t.shape[0]) for t in tensors)
+    out = torch.empty((total,) + tuple(tensors[0].shape[1:]), dtype=tensors[0].dtype, device=device)
+    row = 0
+    for t in tensors:
+        out[row:row + t.shape[0]].copy_(t, non_blocking=True)
+        row += t.shape[0]
+    return out
+
+
 def registration_collate_fn_stack_mode(data_dicts, num_stages, voxel_size, search_radius, neighbor_limits,
                                        precompute_data=True, device='cuda'):
     """reference ``utils/data.py:139-189``: points are stacked ``[ref_1..ref_B, src_1..src_B]``."""
@@ -59,17 +72,18 @@ def registration_collate_fn_stack_mode(data_dicts, num_stages, voxel_size, searc
             if isinstance(value, np.ndarray):
                 value = torch.from_numpy(value)
             collated.setdefault(key, []).append(value)
-    feats = torch.cat(collated.pop('ref_feats') + collated.pop('src_feats'), dim=0)
+    feats_list = collated.pop('ref_feats') + collated.pop('src_feats')
     points_list = collated.pop('ref_points') + collated.pop('src_points')
     lengths = torch.LongTensor([p.shape[0] for p in points_list])
-    points = torch.cat(points_list, dim=0)
     if batch_size == 1:
         for key, value in collated.items():
             collated[key] = value[0]
-    # one H2D per tensor from pinned staging; the reference does this later in to_cuda (utils/torch.py:113-123)
+    # one H2D per tensor (asynchronous from pinned staging) straight into the stacked device tensors: no host-side
+    # torch.cat (a pageable temporary would also make the copy synchronous).  The reference stacks on the host and
+    # moves everything later in to_cuda (utils/torch.py:113-123).
     collated = {k: (v.to(device, non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in collated.items()}
-    collated['features'] = feats.to(device, non_blocking=True)
-    points = points.to(device, non_blocking=True)
+    points, feats = _stack_to_device(points_list, device), _stack_to_device(feats_list, device)
+    collated['features'] = feats
     if precompute_data:
         collated.update(precompute_data_stack_mode(points, lengths, num_stages, voxel_size, search_radius, neighbor_limits))
     else:

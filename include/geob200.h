@@ -123,10 +123,12 @@ int geob200_gse_embed(const float* d_indices, const float* a_indices, int64_t n,
 
 /* Fused multi-head attention: softmax((q.k + qp.E + qb)/sqrt(d)) v  (rpe_transformer.py:51-70 with proj_p moved onto
  * q; vanilla_transformer.py:50-68 when qp = qb = embed = NULL).  q (n_query,C), k,v (n_key,C), qp (n_query,H,C),
- * qb (n_query,H), embed (n_query,n_key,C). */
+ * qb (n_query,H), embed (n_query,n_key,C).  With a workspace and C = 128 or 256 the streaming path runs (one coalesced
+ * pass over embed on a (query, key-chunk) grid + a softmax/P.V kernel); workspace = NULL selects the single-kernel path. */
+size_t geob200_attention_workspace_bytes(int64_t n_query, int64_t n_key, int64_t heads);
 int geob200_attention(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv, const float* qp,
                       const float* qb, const float* embed, int64_t n_query, int64_t n_key, int64_t channels, int64_t heads,
-                      float* out, int64_t ldo, void* stream);
+                      float* out, int64_t ldo, void* workspace, size_t workspace_bytes, void* stream);
 int geob200_head_bias(const float* q, int64_t ldq, const float* bias_p, int64_t n, int64_t channels, int64_t heads, float* qb,
                       void* stream);
 /* y = LayerNorm(a + b) (b may be NULL) */

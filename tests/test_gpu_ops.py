@@ -282,6 +282,38 @@ def test_transformer_layers(mn, models):
     close(GF.l2_normalize(got_r), F.normalize(want_r, p=2, dim=1), 1e-4, 'normalised ref feats')
 
 
+@pytest.mark.parametrize('n,m,c,h,with_e', [(37, 53, 256, 4, True), (130, 130, 256, 4, True), (64, 201, 128, 4, True),
+                                            (33, 65, 256, 4, False), (320, 317, 256, 4, False), (5, 3, 128, 2, True),
+                                            (40, 70, 256, 8, True), (19, 23, 64, 4, True), (70, 41, 128, 1, False)])
+def test_attention_paths_vs_torch(n, m, c, h, with_e):
+    """softmax((q.k + qp.E + qb)/sqrt(d)) v : streaming (lanes <-> channels) and single-kernel paths against fp64 torch;
+    q/k/v are column slices of wider buffers like the fused projections"""
+    g = torch.Generator().manual_seed(n * 7 + m)
+    d = c // h
+    qkv_q = torch.randn(n, 3 * c, generator=g)
+    qkv_k = torch.randn(m, 3 * c, generator=g)
+    q, k, v = qkv_q[:, :c], qkv_k[:, c:2 * c], qkv_k[:, 2 * c:]
+    qp = torch.randn(n, h, c, generator=g) * 0.2 if with_e else None
+    qb = torch.randn(n, h, generator=g) if with_e else None
+    E = torch.randn(n, m, c, generator=g) if with_e else None
+    qd, kd, vd = q.double(), k.double(), v.double()
+    s = torch.einsum('nhd,mhd->hnm', qd.view(n, h, d), kd.view(m, h, d))
+    if with_e:
+        s = s + torch.einsum('nhc,nmc->hnm', qp.double(), E.double()) + qb.double().t()[:, :, None]
+    p = torch.softmax(s / math.sqrt(d), dim=-1)
+    want = torch.einsum('hnm,mhd->nhd', p, vd.view(m, h, d)).reshape(n, c).float()
+    cq, ck = qkv_q.cuda(), qkv_k.cuda()
+    args = (cq[:, :c], ck[:, c:2 * c], ck[:, 2 * c:], h)
+    kw = dict(qp=None if qp is None else qp.cuda(), qb=None if qb is None else qb.cuda(), embed=None if E is None else E.cuda())
+    got_stream = GF.attention(*args, **kw)
+    got_single = GF.attention(*args, streaming=False, **kw)
+    close(got_stream, want, 2e-5, 'attention (default path)')
+    close(got_single, want, 2e-5, 'attention (single-kernel path)')
+    out = torch.full((n, 2 * c), 7.0, device='cuda')                 # strided output, untouched columns stay
+    GF.attention(*args, out=out[:, c:], **kw)
+    assert torch.equal(out[:, c:], got_stream) and bool((out[:, :c] == 7.0).all())
+
+
 def test_superpoint_matching_separated_features():
     """well separated unit features: indices and order must match exactly (K9 in isolation)"""
     g = torch.Generator().manual_seed(11)
