@@ -226,24 +226,7 @@ __global__ void __launch_bounds__(128) att_scores_kernel(const float* __restrict
                 v[u * H + h] = a;
             }
         }
-        // transposing butterfly: after the step with `mask`, a lane keeps the half of the values selected by that lane bit
-        int cnt = NV;
-#pragma unroll
-        for (int mask = 16; mask >= 1; mask >>= 1) {
-            if (cnt > 1) {
-                const int half = cnt / 2;
-                const bool upper = (lane & mask) != 0;
-#pragma unroll
-                for (int i = 0; i < half; ++i) {
-                    const float send = upper ? v[i] : v[i + half];
-                    const float keep = upper ? v[i + half] : v[i];
-                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
-                }
-                cnt = half;
-            } else {
-                v[0] += __shfl_xor_sync(0xffffffffu, v[0], mask);
-            }
-        }
+        warp_butterfly(v, lane);      // transposing reduction: lane l ends up with value index l >> (5 - log2 NV)
         // NV = 2^b values: value index = the top b lane bits; one lane per value writes
         constexpr int SH = (NV == 32) ? 0 : (NV == 16) ? 1 : (NV == 8) ? 2 : 3;
         const int idx = lane >> SH;

@@ -42,6 +42,45 @@ void count_launches(int n);
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Transposing warp butterfly: every lane holds NV = 2^b partial values v[0..NV); afterwards v[0] of lane l is the sum over
+// all 32 lanes of value index (l >> (5 - b)) (NV - 1 exchange shuffles + (5 - b) plain ones instead of 5 per value).
+template <int CNT, int MASK>
+struct Butterfly {
+    template <int NV>
+    static __device__ __forceinline__ void run(float (&v)[NV], int lane) {
+        if constexpr (CNT > 1) {
+            constexpr int HALF = CNT / 2;
+            const bool upper = (lane & MASK) != 0;
+#pragma unroll
+            for (int i = 0; i < HALF; ++i) {
+                const float send = upper ? v[i] : v[i + HALF];
+                const float keep = upper ? v[i + HALF] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, MASK);
+            }
+            if constexpr (MASK > 1) Butterfly<HALF, MASK / 2>::run(v, lane);
+        } else {
+            v[0] += __shfl_xor_sync(0xffffffffu, v[0], MASK);
+            if constexpr (MASK > 1) Butterfly<1, MASK / 2>::run(v, lane);
+        }
+    }
+};
+template <int NV>
+__device__ __forceinline__ float warp_butterfly(float (&v)[NV], int lane) {
+    Butterfly<NV, 16>::run(v, lane);
+    return v[0];
+}
+
+// GroupNorm statistics fused into the tensor-core GEMM epilogue (linear_tc.cu): per row-tile partial (sum, sumsq) per column
+// slot in double, folded into mean_rstd[G][2] by the last CTA of the grid.  ticket must be zero on entry (self-resetting).
+struct GnFuse {
+    int groups;          // 0 = off
+    int slot_width;      // min(channels per group, 32); filled in by linear_tc
+    double eps;
+    double* partial;     // [ceil(M/128)][N / slot_width][2]
+    unsigned* ticket;
+    float* mean_rstd;    // [groups][2]
+};
+
 // Bump allocator over a caller-provided workspace.
 struct Arena {
     char* base;

@@ -570,7 +570,7 @@ using namespace geob200;
 
 namespace geob200 {
 int linear_tc(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, const float* row_scale, float* y, int64_t ldy,
-              int64_t m, int64_t n, int64_t k, int relu, cudaStream_t st);   // linear_tc.cu
+              int64_t m, int64_t n, int64_t k, int relu, cudaStream_t st, const GnFuse* gn = nullptr);   // linear_tc.cu
 static int g_linear_mode = 1;   // 1 = tcgen05 3xTF32 where the shape allows, 0 = fp32 CUDA cores only
 }
 
@@ -700,6 +700,34 @@ int geob200_linear(const float* x, int64_t ldx, const float* weight, const float
 
 size_t geob200_group_norm_workspace_bytes(int64_t groups) { return (size_t)(592 * 2 * groups * 8 + 2 * groups * 4 + 256 + 1024); }
 
+// workspace of the fused Linear/KPConv -> GroupNorm entry points: same head as group_norm's (zeroed ticket, mean_rstd), then
+// the larger of the two partial buffers (stand-alone statistics kernel / GEMM-epilogue statistics)
+size_t geob200_fused_group_norm_workspace_bytes(int64_t n_rows, int64_t channels, int64_t groups) {
+    const size_t tiles = (size_t)((n_rows + 127) / 128);
+    const size_t slots = (size_t)(channels / groups >= 32 ? channels / 32 : groups);
+    const size_t fused = tiles * slots * 2 * 8;
+    const size_t plain = (size_t)(592 * 2 * groups * 8);
+    return (fused > plain ? fused : plain) + (size_t)(2 * groups * 4) + 256 + 1024;
+}
+
+namespace geob200 {
+struct GnWs { unsigned* ticket; float* mean_rstd; double* partial; };
+static GnWs gn_carve(void* workspace, size_t bytes, int64_t groups) {
+    Arena ar(workspace, bytes);
+    GnWs w;
+    w.ticket = ar.take<unsigned>(64);                   // must be zero on first use: the caller provides a zeroed workspace once
+    w.mean_rstd = ar.take<float>(2 * groups);
+    w.partial = ar.take<double>(1);
+    return w;
+}
+static void launch_gn_apply(const float* x, const GnWs& w, const float* gamma, const float* beta, const float* residual, float* y,
+                            int64_t n_rows, int64_t channels, int64_t groups, int leaky, float slope, cudaStream_t st) {
+    const long long total4 = n_rows * channels / 4;
+    gn_apply_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(x, w.mean_rstd, gamma, beta, residual, y, total4, (int)channels,
+                                                                     (int)(channels / groups), leaky, slope);
+}
+}  // namespace geob200
+
 int geob200_group_norm(const float* x, int64_t n_rows, int64_t channels, int64_t groups, const float* gamma,
                        const float* beta, float eps, const float* residual, int leaky, float slope, float* y,
                        void* workspace, size_t workspace_bytes, void* stream) {
@@ -740,6 +768,80 @@ int geob200_upsample_concat(const float* x, const int64_t* up_indices, int64_t u
     GEOB_CHECK_LAUNCH();
     count_launches(1);
     return 0;
+}
+
+// Linear -> GroupNorm (+ residual) (+ LeakyReLU): UnaryBlock / the unary parts of ResidualBlock (modules.py:33-104,150-225).
+// On the tensor-core path the GroupNorm statistics come out of the GEMM epilogue (no pass over the activations for them).
+// pre_norm (m, n) receives the Linear output, y (m, n) the normalised result.
+int geob200_linear_group_norm(const float* x, int64_t ldx, const float* weight, const float* bias, int64_t m, int64_t n, int64_t k,
+                              int64_t groups, const float* gamma, const float* beta, float eps, const float* residual, int leaky,
+                              float slope, float* pre_norm, float* y, void* workspace, size_t workspace_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    GEOB_REQUIRE(m > 0 && n > 0 && k > 0 && groups > 0 && n % groups == 0 && n % 4 == 0, "linear_group_norm: bad shape");
+    GEOB_REQUIRE(workspace_bytes >= geob200_fused_group_norm_workspace_bytes(m, n, groups), "linear_group_norm: workspace too small");
+    if (g_linear_mode == 1) {
+        const GnWs w = gn_carve(workspace, workspace_bytes, groups);
+        GnFuse gn{(int)groups, 0, (double)eps, w.partial, w.ticket, w.mean_rstd};
+        const int rc = linear_tc(x, ldx, weight, k, bias, nullptr, pre_norm, n, m, n, k, 0, st, &gn);
+        if (rc < 0) return rc;
+        if (rc == 0) {
+            launch_gn_apply(pre_norm, w, gamma, beta, residual, y, m, n, groups, leaky, slope, st);
+            GEOB_CHECK_LAUNCH();
+            count_launches(1);
+            return 0;
+        }
+    }
+    int rc = geob200_linear(x, ldx, weight, bias, pre_norm, n, m, n, k, 0, stream);
+    if (rc != 0) return rc;
+    return geob200_group_norm(pre_norm, m, n, groups, gamma, beta, eps, residual, leaky, slope, y, workspace, workspace_bytes, stream);
+}
+
+// KPConv (gather + tcgen05 GEMM) -> GroupNorm (+ LeakyReLU): ConvBlock / the conv part of ResidualBlock (modules.py:107-147,205-207)
+size_t geob200_kpconv_group_norm_workspace_bytes(int64_t n_query, int64_t n_support, int64_t c_in, int64_t c_out, int64_t groups) {
+    return align_up(geob200_fused_group_norm_workspace_bytes(n_query, c_out, groups), 256) +
+           geob200_kpconv_tc_workspace_bytes(n_query, n_support, c_in);
+}
+
+int geob200_kpconv_group_norm(const float* s_feats, const float* q_points, const float* s_points, const int64_t* neighbors,
+                              int64_t n_query, int64_t n_support, int64_t n_neighbors, const float* kernel_points, int64_t n_kernel,
+                              const float* weights_t, const float* bias, int64_t c_in, int64_t c_out, float sigma, int64_t groups,
+                              const float* gamma, const float* beta, float eps, int leaky, float slope, float* pre_norm, float* y,
+                              void* gn_workspace, size_t gn_workspace_bytes, void* workspace, size_t workspace_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    GEOB_REQUIRE(n_kernel == KP, "kpconv_group_norm: kernel_size %lld unsupported", (long long)n_kernel);
+    GEOB_REQUIRE(n_query > 0 && n_support > 0 && n_neighbors > 0, "kpconv_group_norm: empty input");
+    GEOB_REQUIRE(c_in % 32 == 0 && c_out % 16 == 0 && c_out >= 32 && (c_out <= 128 || c_out % 128 == 0) && n_query >= 64,
+                 "kpconv_group_norm: unsupported shape (%lld -> %lld, %lld queries)", (long long)c_in, (long long)c_out,
+                 (long long)n_query);
+    GEOB_REQUIRE(groups > 0 && c_out % groups == 0, "kpconv_group_norm: bad group count");
+    GEOB_REQUIRE(gn_workspace_bytes >= geob200_fused_group_norm_workspace_bytes(n_query, c_out, groups),
+                 "kpconv_group_norm: GroupNorm workspace too small");
+    GEOB_REQUIRE(workspace_bytes >= geob200_kpconv_tc_workspace_bytes(n_query, n_support, c_in), "kpconv_group_norm: workspace too small");
+    Arena ar(workspace, workspace_bytes);
+    unsigned char* pos = ar.take<unsigned char>(n_support);
+    float* inv_count = ar.take<float>(n_query);
+    float* wf = ar.take<float>((size_t)n_query * KP * c_in);
+    row_positive_kernel<<<(unsigned)((n_support + 7) / 8), 256, 0, st>>>(s_feats, (int)n_support, (int)c_in, pos);
+    kpconv_gather_kernel<<<(unsigned)((n_query + 7) / 8), 256, 0, st>>>(s_feats, pos, q_points, s_points, (const long long*)neighbors,
+                                                                       (int)n_neighbors, kernel_points, sigma, (int)n_support,
+                                                                       (int)n_query, (int)c_in, wf, inv_count);
+    GEOB_CHECK_LAUNCH();
+    count_launches(2);
+    const GnWs w = gn_carve(gn_workspace, gn_workspace_bytes, groups);
+    GnFuse gn{(int)groups, 0, (double)eps, w.partial, w.ticket, w.mean_rstd};
+    int rc = linear_tc(wf, KP * c_in, weights_t, KP * c_in, bias, inv_count, pre_norm, c_out, n_query, c_out, KP * c_in, 0, st, &gn);
+    if (rc < 0) return rc;
+    if (rc == 0) {
+        launch_gn_apply(pre_norm, w, gamma, beta, nullptr, y, n_query, c_out, groups, leaky, slope, st);
+        GEOB_CHECK_LAUNCH();
+        count_launches(1);
+        return 0;
+    }
+    // group layout not expressible in the epilogue: plain GEMM, then the stand-alone statistics kernel
+    rc = linear_tc(wf, KP * c_in, weights_t, KP * c_in, bias, inv_count, pre_norm, c_out, n_query, c_out, KP * c_in, 0, st);
+    GEOB_REQUIRE(rc == 0, "kpconv_group_norm: tensor-core GEMM rejected the shape");
+    return geob200_group_norm(pre_norm, n_query, c_out, groups, gamma, beta, eps, nullptr, leaky, slope, y, gn_workspace,
+                              gn_workspace_bytes, stream);
 }
 
 }  // extern "C"

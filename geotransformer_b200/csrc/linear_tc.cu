@@ -10,7 +10,9 @@
 //   warps 1-4   splitters    : in-place hi = tf32_rn(x), lo = x - hi into a second buffer (generic proxy ->
 //                              fence.proxy.async), so the MMA sees exact tf32 operands
 //   warp 5      MMA issuer   : tcgen05.mma.cta_group::1.kind::tf32 M128 N{BN} K8, 3 per K-step; tcgen05.commit frees the stage
-//   warps 6-9   epilogue     : tcgen05.ld 32x32b, + bias, ReLU, direct row-segment stores (each thread owns one output row)
+//   warps 6-9   epilogue     : tcgen05.ld 32x32b, + bias, ReLU, direct row-segment stores (each thread owns one output row);
+//                              optionally the GroupNorm statistics of the output (per-tile column sums through a transposing
+//                              warp butterfly, per-tile partials in double, last CTA folds them into mean / rstd)
 #include <cuda.h>
 
 #include "common.cuh"
@@ -26,7 +28,8 @@ constexpr int TILE_B = 128 * 128;      // 16 KB (BN <= 128 rows)
 constexpr int STAGE = 2 * TILE_A + 2 * TILE_B;   // raw/hi + lo for both operands = 64 KB
 constexpr int NSTAGE = 3;
 constexpr int NTHREADS = 320;
-constexpr int SMEM = NSTAGE * STAGE + 1024 + 256;
+constexpr int GN_SM = 4 * 128 * 8;      // per epilogue warp: (sum, sumsq) of up to 128 column slots
+constexpr int SMEM = NSTAGE * STAGE + 1024 + 256 + GN_SM;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -78,7 +81,8 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const __grid_constant__ CUtensorMap map_x,
                                                                 const __grid_constant__ CUtensorMap map_w,
                                                                 const float* __restrict__ bias, const float* __restrict__ row_scale,
-                                                                float* __restrict__ Y, int ldy, int M, int N, int K, int BN, int relu) {
+                                                                float* __restrict__ Y, int ldy, int M, int N, int K, int BN, int relu,
+                                                                GnFuse gn) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = (uint64_t*)(smem + NSTAGE * STAGE);
@@ -87,6 +91,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const __grid_con
     uint64_t* empty = bars + 2 * NSTAGE;        // MMAs done with the stage
     uint64_t* acc_full = bars + 3 * NSTAGE;
     uint32_t* tmem_slot = (uint32_t*)(acc_full + 1);
+    unsigned* gn_last = (unsigned*)(tmem_slot + 1);
+    float2* gn_sm = (float2*)(smem + NSTAGE * STAGE + 256);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int nk = (K + KC - 1) / KC;
@@ -202,31 +208,90 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const __grid_con
                 : "r"(taddr + 128));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             const float rs = (row_scale != nullptr && m < M) ? row_scale[m] : 1.0f;   // KPConv: 1 / neighbour count
+            const int nvalid = min(32, N - (n0 + cc));
+            float o[32];
 #pragma unroll
-            for (int c = 0; c < 32; ++c) v[c] = __float_as_uint((__uint_as_float(v[c]) + __uint_as_float(w2[c])) * rs);
+            for (int c = 0; c < 32; ++c) {
+                float t = (__uint_as_float(v[c]) + __uint_as_float(w2[c])) * rs;
+                if (c < nvalid) {
+                    t += (bias ? __ldg(bias + n0 + cc + c) : 0.f);
+                    if (relu) t = fmaxf(t, 0.f);
+                }
+                o[c] = t;
+            }
             if (m < M) {
                 float* yr = Y + (long long)m * ldy + n0 + cc;
-                const int nvalid = min(32, N - (n0 + cc));
                 if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(yr) & 15) == 0)) {
 #pragma unroll
-                    for (int c = 0; c < 32; c += 4) {
-                        float4 o;
-                        o.x = __uint_as_float(v[c]) + (bias ? __ldg(bias + n0 + cc + c) : 0.f);
-                        o.y = __uint_as_float(v[c + 1]) + (bias ? __ldg(bias + n0 + cc + c + 1) : 0.f);
-                        o.z = __uint_as_float(v[c + 2]) + (bias ? __ldg(bias + n0 + cc + c + 2) : 0.f);
-                        o.w = __uint_as_float(v[c + 3]) + (bias ? __ldg(bias + n0 + cc + c + 3) : 0.f);
-                        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                        *reinterpret_cast<float4*>(yr + c) = o;
-                    }
+                    for (int c = 0; c < 32; c += 4) *reinterpret_cast<float4*>(yr + c) = make_float4(o[c], o[c + 1], o[c + 2], o[c + 3]);
                 } else {
 #pragma unroll
                     for (int c = 0; c < 32; ++c)
-                        if (c < nvalid) {
-                            float o = __uint_as_float(v[c]) + (bias ? __ldg(bias + n0 + cc + c) : 0.f);
-                            if (relu) o = fmaxf(o, 0.f);
-                            yr[c] = o;
-                        }
+                        if (c < nvalid) yr[c] = o[c];
                 }
+            }
+            if (gn.groups > 0) {
+                // column sums over this warp's 32 rows (rows past M and columns past N contribute nothing)
+                float s1[32], s2[32];
+                const bool rv = m < M;
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const float t = (rv && c < nvalid) ? o[c] : 0.f;
+                    s1[c] = t;
+                    s2[c] = t * t;
+                }
+                float a = warp_butterfly(s1, lane), b2 = warp_butterfly(s2, lane);
+                for (int off = 1; off < gn.slot_width; off <<= 1) {
+                    a += __shfl_xor_sync(0xffffffffu, a, off);
+                    b2 += __shfl_xor_sync(0xffffffffu, b2, off);
+                }
+                if ((lane & (gn.slot_width - 1)) == 0) gn_sm[q * 128 + (cc + lane) / gn.slot_width] = make_float2(a, b2);
+            }
+        }
+        if (gn.groups > 0) {
+            // 4 epilogue warps -> per-tile partial (fixed order), then the last CTA of the grid folds all tiles
+            const int et = threadIdx.x - 6 * 32;
+            const int slots_tile = BN / gn.slot_width, slots_total = N / gn.slot_width;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (et < slots_tile) {
+                const float2 p0 = gn_sm[et], p1 = gn_sm[128 + et], p2 = gn_sm[256 + et], p3 = gn_sm[384 + et];
+                double* dst = gn.partial + ((long long)blockIdx.y * slots_total + n0 / gn.slot_width + et) * 2;
+                dst[0] = ((double)p0.x + (double)p1.x) + ((double)p2.x + (double)p3.x);
+                dst[1] = ((double)p0.y + (double)p1.y) + ((double)p2.y + (double)p3.y);
+            }
+            __threadfence();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (et == 0) *gn_last = (atomicAdd(gn.ticket, 1u) == gridDim.x * gridDim.y - 1) ? 1u : 0u;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (*gn_last) {
+                __threadfence();
+                const int cpg = N / gn.groups;
+                const int spg = cpg / gn.slot_width;             // slots per group (1 unless a group is wider than 32 channels)
+                for (int g0 = 0; g0 < gn.groups; g0 += 32) {
+                    const int g = g0 + (et >> 2), u = et & 3;
+                    double sa = 0.0, sb = 0.0;
+                    if (g < gn.groups)
+                        for (unsigned t = u; t < gridDim.y; t += 4)
+                            for (int sl = 0; sl < spg; ++sl) {
+                                const double* src = gn.partial + ((long long)t * slots_total + g * spg + sl) * 2;
+                                sa += __ldcg(src);
+                                sb += __ldcg(src + 1);
+                            }
+#pragma unroll
+                    for (int off = 2; off > 0; off >>= 1) {
+                        sa += __shfl_xor_sync(0xffffffffu, sa, off);
+                        sb += __shfl_xor_sync(0xffffffffu, sb, off);
+                    }
+                    if (g < gn.groups && u == 0) {
+                        const double cnt = (double)cpg * (double)M;
+                        const double mean = sa / cnt;
+                        double var = sb / cnt - mean * mean;
+                        if (var < 0.0) var = 0.0;
+                        gn.mean_rstd[2 * g] = (float)mean;
+                        gn.mean_rstd[2 * g + 1] = (float)(1.0 / sqrt(var + gn.eps));
+                    }
+                }
+                if (et == 0) *gn.ticket = 0u;                    // self-reset for the next launch on this stream
             }
         }
     }
@@ -271,7 +336,7 @@ static int encode_map(CUtensorMap* map, const float* base, int64_t rows, int64_t
 
 // returns 1 when the shape/alignment is not handled by the tensor-core path (caller falls back to the fp32 kernel)
 int linear_tc(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, const float* row_scale, float* y, int64_t ldy,
-              int64_t m, int64_t n, int64_t k, int relu, cudaStream_t st) {
+              int64_t m, int64_t n, int64_t k, int relu, cudaStream_t st, const GnFuse* gn) {
     if (m < 64 || n < 32 || (n % 16) != 0 || (k % 4) != 0 || (ldx % 4) != 0 || (ldw % 4) != 0) return 1;
     if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15)) return 1;
     if (n > 128 && (n % 128) != 0) return 1;
@@ -285,7 +350,15 @@ int linear_tc(const float* x, int64_t ldx, const float* w, int64_t ldw, const fl
         set = true;
     }
     dim3 grid((unsigned)(n / BN), (unsigned)((m + ltc::BM - 1) / ltc::BM));
-    ltc::linear_tc_kernel<<<grid, ltc::NTHREADS, ltc::SMEM, st>>>(mx, mw, bias, row_scale, y, (int)ldy, (int)m, (int)n, (int)k, BN, relu);
+    GnFuse g{};
+    if (gn != nullptr) {
+        g = *gn;
+        const int64_t cpg = n / g.groups;
+        // groups must tile the 32-column epilogue chunks: cpg in {1,2,4,...,32} or a multiple of 32 dividing the column tile
+        if (g.groups <= 0 || n % g.groups != 0 || (cpg < 32 ? (32 % cpg) != 0 : (cpg % 32) != 0 || (BN % cpg) != 0) || relu) return 1;
+        g.slot_width = (int)(cpg < 32 ? cpg : 32);
+    }
+    ltc::linear_tc_kernel<<<grid, ltc::NTHREADS, ltc::SMEM, st>>>(mx, mw, bias, row_scale, y, (int)ldy, (int)m, (int)n, (int)k, BN, relu, g);
     GEOB_CHECK_LAUNCH();
     count_launches(1);
     return 0;

@@ -54,13 +54,34 @@ static int run_kpconv(Ctx& c, const geob200_kpconv_t& k, const float* s_feats, c
     return 0;
 }
 
+// KPConv -> GroupNorm -> LeakyReLU (ConvBlock / conv part of ResidualBlock); out = normalised activations
+static int run_kpconv_norm(Ctx& c, const geob200_kpconv_t& k, const geob200_norm_t& n, const float* s_feats, const float* q_pts,
+                           const float* s_pts, const int64_t* nbr, int64_t m, int64_t ns, int64_t h, float* out) {
+    float* y = c.fl(m, k.c_out);
+    GEOB_REQUIRE(c.ar.ok(), "native: arena too small (kpconv output)");
+    const bool tc = (k.c_in % 32 == 0) && (k.c_out % 16 == 0) && k.c_out >= 32 && (k.c_out <= 128 || k.c_out % 128 == 0) && m >= 64 &&
+                    k.weights_t != nullptr;
+    if (tc) {
+        const size_t wb = geob200_kpconv_tc_workspace_bytes(m, ns, k.c_in);
+        const size_t mark = c.ar.off;
+        void* ws = c.ar.take<char>(wb);
+        GEOB_REQUIRE(c.ar.ok(), "native: arena too small (kpconv)");
+        TRY(geob200_kpconv_group_norm(s_feats, q_pts, s_pts, nbr, m, ns, h, k.kernel_points, 15, k.weights_t, k.bias, k.c_in, k.c_out,
+                                      k.sigma, c.groups, n.gamma, n.beta, 1e-5f, 1, 0.1f, y, out, c.gn_ws, c.gn_ws_bytes, ws, wb, c.stream));
+        c.ar.off = mark;     // stream-ordered reuse: the next kernel that touches this scratch runs after the GEMM
+        return 0;
+    }
+    TRY(run_kpconv(c, k, s_feats, q_pts, s_pts, nbr, m, ns, h, y));
+    return geob200_group_norm(y, m, k.c_out, c.groups, n.gamma, n.beta, 1e-5f, nullptr, 1, 0.1f, out, c.gn_ws, c.gn_ws_bytes, c.stream);
+}
+
 // Linear -> GroupNorm (+ residual) (+ LeakyReLU)
 static int run_unary(Ctx& c, const geob200_linear_t& l, const geob200_norm_t& n, const float* x, int64_t rows, const float* residual,
                      int leaky, float* out) {
     float* t = c.fl(rows, l.c_out);
     GEOB_REQUIRE(c.ar.ok(), "native: arena too small (unary)");
-    TRY(geob200_linear(x, l.c_in, l.weight, l.bias, t, l.c_out, rows, l.c_out, l.c_in, 0, c.stream));
-    TRY(geob200_group_norm(t, rows, l.c_out, c.groups, n.gamma, n.beta, 1e-5f, residual, leaky, 0.1f, out, c.gn_ws, c.gn_ws_bytes, c.stream));
+    TRY(geob200_linear_group_norm(x, l.c_in, l.weight, l.bias, rows, l.c_out, l.c_in, c.groups, n.gamma, n.beta, 1e-5f, residual, leaky,
+                                  0.1f, t, out, c.gn_ws, c.gn_ws_bytes, c.stream));
     return 0;
 }
 
@@ -72,12 +93,9 @@ static int run_resblock(Ctx& c, const geob200_resblock_t& b, const float* feats,
         TRY(run_unary(c, b.unary1, b.norm1, feats, ns, nullptr, 1, u));
         x = u;
     }
-    float* y = c.fl(m, b.conv.c_out);
-    TRY(run_kpconv(c, b.conv, x, q_pts, s_pts, nbr, m, ns, h, y));
     float* yn = c.fl(m, b.conv.c_out);
     GEOB_REQUIRE(c.ar.ok(), "native: arena too small (resblock)");
-    TRY(geob200_group_norm(y, m, b.conv.c_out, c.groups, b.norm_conv.gamma, b.norm_conv.beta, 1e-5f, nullptr, 1, 0.1f, yn, c.gn_ws,
-                           c.gn_ws_bytes, c.stream));
+    TRY(run_kpconv_norm(c, b.conv, b.norm_conv, x, q_pts, s_pts, nbr, m, ns, h, yn));
     const float* sc = feats;
     if (b.strided) {
         float* mp = c.fl(m, b.c_in);
@@ -125,12 +143,9 @@ int geob200_backbone_forward(const geob200_backbone_t* net, const float* feats, 
     // encoder1_1 (ConvBlock) + encoder1_2
     {
         const int64_t n0 = level_rows[0];
-        float* y = c.fl(n0, net->conv1.c_out);
-        TRY(run_kpconv(c, net->conv1, feats, points[0], points[0], neighbors[0], n0, n0, neighbor_width[0], y));
         float* yn = c.fl(n0, net->conv1.c_out);
         GEOB_REQUIRE(c.ar.ok(), "native: arena too small (encoder1_1)");
-        TRY(geob200_group_norm(y, n0, net->conv1.c_out, c.groups, net->norm1.gamma, net->norm1.beta, 1e-5f, nullptr, 1, 0.1f, yn, c.gn_ws,
-                               c.gn_ws_bytes, stream));
+        TRY(run_kpconv_norm(c, net->conv1, net->norm1, feats, points[0], points[0], neighbors[0], n0, n0, neighbor_width[0], yn));
         const geob200_resblock_t& b = net->blocks[0];
         float* o = c.fl(n0, b.unary2.c_out);
         TRY(run_resblock(c, b, yn, n0, points[0], points[0], neighbors[0], n0, neighbor_width[0], o));

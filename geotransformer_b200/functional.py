@@ -51,11 +51,15 @@ def _detach(t):
 _GN_WS = {}
 
 
-def _gn_workspace(device, groups):
+def _gn_workspace(device, groups, rows=0, channels=0):
+    """zero-initialised (ticket) GroupNorm scratch per (device, stream, groups); large enough for the statistics of a
+    (rows, channels) activation produced by the GEMM epilogue (geob200_fused_group_norm_workspace_bytes)"""
     key = (device.index, L.stream_ptr(), groups)
+    lib = L.lib()
+    need = lib.geob200_fused_group_norm_workspace_bytes(rows, channels, groups) if rows else lib.geob200_group_norm_workspace_bytes(groups)
     ws = _GN_WS.get(key)
-    if ws is None:
-        ws = torch.zeros(L.lib().geob200_group_norm_workspace_bytes(groups), dtype=_u8, device=device)
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros(max(int(need * 1.5), 1 << 20), dtype=_u8, device=device)
         _GN_WS[key] = ws
     return ws
 
@@ -117,6 +121,53 @@ def group_norm(x, weight, bias, groups, eps=1e-5, negative_slope=None, residual=
                                        L.ptr(residual), int(negative_slope is not None),
                                        float(negative_slope or 0.0), y.data_ptr(), ws.data_ptr(), ws.numel(),
                                        L.stream_ptr()), 'group_norm')
+    return y
+
+
+def linear_group_norm(x, weight, bias, gn_weight, gn_bias, groups, eps=1e-5, negative_slope=None, residual=None):
+    """UnaryBlock: leaky(GroupNorm(x @ weight.T + bias) + residual); statistics from the GEMM epilogue on the tcgen05 path"""
+    x, weight, bias, gn_weight, gn_bias = _detach(x), _detach(weight), _detach(bias), _detach(gn_weight), _detach(gn_bias)
+    if not x.is_cuda or x.dtype != _f32 or x.stride(1) != 1:
+        raise RuntimeError('linear_group_norm: x must be a float32 CUDA tensor with unit inner stride')
+    L.require_cuda(weight, 'weight', _f32)
+    m, k = x.shape
+    n = weight.shape[0]
+    pre = scratch((m, n), x.device, 'pre_norm')
+    y = torch.empty((m, n), dtype=_f32, device=x.device)
+    ws = _gn_workspace(x.device, groups, m, n)
+    L.check(L.lib().geob200_linear_group_norm(x.data_ptr(), x.stride(0), weight.data_ptr(), L.ptr(bias), m, n, k, groups,
+                                              gn_weight.data_ptr(), gn_bias.data_ptr(), float(eps), L.ptr(residual),
+                                              int(negative_slope is not None), float(negative_slope or 0.0), pre.data_ptr(),
+                                              y.data_ptr(), ws.data_ptr(), ws.numel(), L.stream_ptr()), 'linear_group_norm')
+    return y
+
+
+def kpconv_group_norm(s_feats, q_points, s_points, neighbor_indices, kernel_points, weights, bias, sigma, gn_weight, gn_bias, groups,
+                      eps=1e-5, negative_slope=0.1, weights_t=None):
+    """ConvBlock / conv part of ResidualBlock: leaky(GroupNorm(KPConv(...)))"""
+    m, h = neighbor_indices.shape
+    k, cin, cout = weights.shape
+    if not (KPCONV_MODE == 'tc' and cin % 32 == 0 and cout % 16 == 0 and cout >= 32 and (cout <= 128 or cout % 128 == 0) and m >= 64):
+        x = kpconv(s_feats, q_points, s_points, neighbor_indices, kernel_points, weights, bias, sigma, weights_t=weights_t)
+        return group_norm(x, gn_weight, gn_bias, groups, eps, negative_slope=negative_slope)
+    s_feats, weights, bias, gn_weight, gn_bias = _detach(s_feats), _detach(weights), _detach(bias), _detach(gn_weight), _detach(gn_bias)
+    _f(s_feats, 's_feats'); _f(q_points, 'q_points'); _f(s_points, 's_points')
+    L.require_cuda(neighbor_indices, 'neighbor_indices', _i64)
+    ns = s_points.shape[0]
+    dev = s_feats.device
+    if weights_t is None:
+        weights_t = weights.reshape(k * cin, cout).t().contiguous()
+    lib = L.lib()
+    pre = scratch((m, cout), dev, 'pre_norm')
+    y = torch.empty((m, cout), dtype=_f32, device=dev)
+    gws = _gn_workspace(dev, groups, m, cout)
+    ws = L.workspace(lib.geob200_kpconv_tc_workspace_bytes(m, ns, cin), dev, 'kpconv_tc')
+    L.check(lib.geob200_kpconv_group_norm(s_feats.data_ptr(), q_points.data_ptr(), s_points.data_ptr(), neighbor_indices.data_ptr(),
+                                          m, ns, h, kernel_points.data_ptr(), k, weights_t.data_ptr(), L.ptr(bias), cin, cout,
+                                          float(sigma), groups, gn_weight.data_ptr(), gn_bias.data_ptr(), float(eps),
+                                          int(negative_slope is not None), float(negative_slope or 0.0), pre.data_ptr(),
+                                          y.data_ptr(), gws.data_ptr(), gws.numel(), ws.data_ptr(), ws.numel(), L.stream_ptr()),
+            'kpconv_group_norm')
     return y
 
 

@@ -28,14 +28,23 @@ class KPConv(nn.Module):
             nn.init.uniform_(self.bias, -1 / math.sqrt(in_channels * out_channels), 1 / math.sqrt(in_channels * out_channels))
         self.register_buffer('kernel_points', default_kernel_points(kernel_size, radius))
 
-    def forward(self, s_feats, q_points, s_points, neighbor_indices):
+    def _weights_t(self):
         w = self.weights
         key = (w.data_ptr(), w._version)
         if getattr(self, '_wt_key', None) != key:     # (c_out, 15*c_in) copy for the tensor-core GEMM, rebuilt if weights change
             self._wt = w.detach().reshape(-1, w.shape[2]).t().contiguous()
             self._wt_key = key
+        return self._wt
+
+    def forward(self, s_feats, q_points, s_points, neighbor_indices):
         return GF.kpconv(s_feats, q_points, s_points, neighbor_indices, self.kernel_points, self.weights, self.bias,
-                         self.sigma, weights_t=self._wt)
+                         self.sigma, weights_t=self._weights_t())
+
+    def forward_norm(self, s_feats, q_points, s_points, neighbor_indices, norm, negative_slope):
+        """KPConv -> GroupNorm -> LeakyReLU as one fused op (GroupNorm statistics from the GEMM epilogue)"""
+        return GF.kpconv_group_norm(s_feats, q_points, s_points, neighbor_indices, self.kernel_points, self.weights, self.bias,
+                                    self.sigma, norm.norm.weight, norm.norm.bias, norm.num_groups, norm.norm.eps,
+                                    negative_slope=negative_slope, weights_t=self._weights_t())
 
     def __repr__(self):
         return (f'KPConv(kernel_size: {self.kernel_size}, in_channels: {self.in_channels}, out_channels: '
@@ -86,11 +95,12 @@ class UnaryBlock(nn.Module):
         self.leaky_relu = nn.LeakyReLU(0.1) if has_relu else None
 
     def forward(self, x, residual=None, residual_slope=None):
-        x = GF.linear(x, self.mlp.weight, self.mlp.bias)
         slope = self.leaky_relu.negative_slope if self.leaky_relu is not None else None
         if residual is not None:      # fused tail of ResidualBlock: leaky(norm(x) + shortcut)
-            return self.norm(x, negative_slope=residual_slope, residual=residual)
-        return self.norm(x, negative_slope=slope)
+            slope = residual_slope
+        n = self.norm
+        return GF.linear_group_norm(x, self.mlp.weight, self.mlp.bias, n.norm.weight, n.norm.bias, n.num_groups, n.norm.eps,
+                                    negative_slope=slope, residual=residual)
 
 
 class LastUnaryBlock(nn.Module):
@@ -119,8 +129,7 @@ class ConvBlock(nn.Module):
         self.leaky_relu = nn.LeakyReLU(negative_slope=negative_slope)
 
     def forward(self, s_feats, q_points, s_points, neighbor_indices):
-        x = self.KPConv(s_feats, q_points, s_points, neighbor_indices)
-        return self.norm(x, negative_slope=self.leaky_relu.negative_slope)
+        return self.KPConv.forward_norm(s_feats, q_points, s_points, neighbor_indices, self.norm, self.leaky_relu.negative_slope)
 
 
 class ResidualBlock(nn.Module):
@@ -145,8 +154,7 @@ class ResidualBlock(nn.Module):
 
     def forward(self, s_feats, q_points, s_points, neighbor_indices):
         x = self.unary1(s_feats)
-        x = self.KPConv(x, q_points, s_points, neighbor_indices)
-        x = self.norm_conv(x, negative_slope=self.leaky_relu.negative_slope)
+        x = self.KPConv.forward_norm(x, q_points, s_points, neighbor_indices, self.norm_conv, self.leaky_relu.negative_slope)
         shortcut = GF.maxpool(s_feats, neighbor_indices) if self.strided else s_feats
         shortcut = self.unary_shortcut(shortcut)
         # unary2 (Linear+GroupNorm) + shortcut add + LeakyReLU in one normalisation pass

@@ -153,7 +153,7 @@ class NativeModel:
         oarr = (P * len(outs))(*[o.data_ptr() for o in outs])
         ws_bytes = lib.geob200_backbone_workspace_bytes(ctypes.byref(self.backbone), rows)
         ws = L.workspace(ws_bytes, dev, 'native_backbone')
-        gn = GF._gn_workspace(dev, self.backbone.groups)
+        gn = GF._gn_workspace(dev, self.backbone.groups, pts[0].shape[0], self.backbone.init_dim << S)
         L.check(lib.geob200_backbone_forward(ctypes.byref(self.backbone), feats.data_ptr(), parr, rows, narr, nw, sarr, sw, uarr, uw, oarr,
                                              gn.data_ptr(), gn.numel(), ws.data_ptr(), ws.numel(), L.stream_ptr()), 'backbone_forward')
         outs.reverse()

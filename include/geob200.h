@@ -85,6 +85,22 @@ int geob200_group_norm(const float* x, int64_t n_rows, int64_t channels, int64_t
                        const float* beta, float eps, const float* residual, int leaky, float slope, float* y,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* Fused blocks: Linear -> GroupNorm (+ residual) (+ LeakyReLU) = UnaryBlock and the unary parts of ResidualBlock
+ * (modules/kpconv/modules.py:33-104,150-225); KPConv -> GroupNorm -> LeakyReLU = ConvBlock and the conv part of
+ * ResidualBlock (modules.py:107-147,205-207).  On the tcgen05 path the GroupNorm statistics are produced by the GEMM
+ * epilogue, so the activations are not re-read for them.  pre_norm receives the Linear / KPConv output, y the result.
+ * The GroupNorm workspace (>= geob200_fused_group_norm_workspace_bytes) must be zero-filled once before first use. */
+size_t geob200_fused_group_norm_workspace_bytes(int64_t n_rows, int64_t channels, int64_t groups);
+int geob200_linear_group_norm(const float* x, int64_t ldx, const float* weight, const float* bias, int64_t m, int64_t n, int64_t k,
+                              int64_t groups, const float* gamma, const float* beta, float eps, const float* residual, int leaky,
+                              float slope, float* pre_norm, float* y, void* workspace, size_t workspace_bytes, void* stream);
+size_t geob200_kpconv_group_norm_workspace_bytes(int64_t n_query, int64_t n_support, int64_t c_in, int64_t c_out, int64_t groups);
+int geob200_kpconv_group_norm(const float* s_feats, const float* q_points, const float* s_points, const int64_t* neighbors,
+                              int64_t n_query, int64_t n_support, int64_t n_neighbors, const float* kernel_points, int64_t n_kernel,
+                              const float* weights_t, const float* bias, int64_t c_in, int64_t c_out, float sigma, int64_t groups,
+                              const float* gamma, const float* beta, float eps, int leaky, float slope, float* pre_norm, float* y,
+                              void* gn_workspace, size_t gn_workspace_bytes, void* workspace, size_t workspace_bytes, void* stream);
+
 /* maxpool over neighbour rows with a zero shadow row (functional.py:54-67) */
 int geob200_maxpool(const float* x, const int64_t* neighbors, int64_t n_query, int64_t n_support, int64_t n_neighbors,
                     int64_t channels, float* y, void* stream);

@@ -128,6 +128,54 @@ def test_group_norm_variants(n, c):
     close(GF.group_norm(x.cuda(), w.cuda(), b.cuda(), 32), ref, 1e-5, 'gn again')
 
 
+@pytest.mark.parametrize('m,k,n,groups', [(4100, 64, 32, 32), (1434, 128, 64, 32), (333, 64, 128, 32), (20011, 32, 128, 32),
+                                          (700, 256, 256, 32), (130, 512, 1024, 32), (257, 256, 2048, 32), (640, 64, 512, 8),
+                                          (37, 64, 128, 32), (300, 100, 48, 4)])
+def test_linear_group_norm_fused_statistics(m, k, n, groups):
+    """UnaryBlock as one op: GroupNorm statistics produced by the tcgen05 GEMM epilogue (channels per group 1..64, ragged last
+    row tile, several column tiles) against torch; shapes the tensor-core path rejects fall back to the stand-alone kernels"""
+    g = torch.Generator().manual_seed(m + n)
+    x = torch.randn(m, k, generator=g)
+    w, b = torch.randn(n, k, generator=g) / math.sqrt(k), torch.randn(n, generator=g)
+    gw, gb = torch.rand(n, generator=g) + 0.5, torch.randn(n, generator=g)
+    res = torch.randn(m, n, generator=g)
+    y = F.linear(x.double(), w.double(), b.double())
+    ref = F.group_norm(y.t().unsqueeze(0), groups, gw.double(), gb.double(), 1e-5).squeeze(0).t().float()
+    c = lambda t: t.cuda()
+    tol = 3e-5
+    close(GF.linear_group_norm(c(x), c(w), c(b), c(gw), c(gb), groups), ref, tol, 'linear+gn')
+    close(GF.linear_group_norm(c(x), c(w), c(b), c(gw), c(gb), groups, negative_slope=0.1, residual=c(res)),
+          F.leaky_relu(ref + res, 0.1), tol, 'linear+gn+res+lrelu')
+    # interleaved with the stand-alone GroupNorm on the same stream (shared ticket) and repeated: deterministic
+    plain = GF.group_norm(GF.linear(c(x), c(w), c(b)), c(gw), c(gb), groups)
+    close(plain, ref, tol, 'linear, gn')
+    a1 = GF.linear_group_norm(c(x), c(w), c(b), c(gw), c(gb), groups)
+    a2 = GF.linear_group_norm(c(x), c(w), c(b), c(gw), c(gb), groups)
+    assert torch.equal(a1, a2)
+    assert float((a1 - plain).abs().max()) < 2e-5 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize('cin,cout,h', [(32, 32, 21), (64, 64, 38), (128, 128, 27)])
+def test_kpconv_group_norm_fused(cin, cout, h):
+    g = torch.Generator().manual_seed(cin + h)
+    ns, m = 900, 517
+    s_pts = torch.rand(ns, 3, generator=g)
+    q_pts = s_pts[torch.randperm(ns, generator=g)[:m]] + 0.01 * torch.randn(m, 3, generator=g)
+    d = torch.cdist(q_pts, s_pts)
+    nbr = d.argsort(dim=1)[:, :h].contiguous()
+    nbr[d.gather(1, nbr) > 0.25] = ns
+    feats = torch.randn(ns, cin, generator=g)
+    sd = {'w.weights': torch.randn(15, cin, cout, generator=g) * 0.1, 'w.bias': torch.randn(cout, generator=g) * 0.1,
+          'w.kernel_points': (torch.rand(15, 3, generator=g) - 0.5) * 0.3}
+    sd['w.kernel_points'][0] = 0
+    gw, gb = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g)
+    y = G.kpconv(sd, 'w.', feats, q_pts, s_pts, nbr, 0.12)
+    want = F.leaky_relu(F.group_norm(y.t().unsqueeze(0), 32, gw, gb, 1e-5).squeeze(0).t(), 0.1)
+    args = (feats.cuda(), q_pts.cuda(), s_pts.cuda(), nbr.cuda(), sd['w.kernel_points'].cuda(), sd['w.weights'].cuda(),
+            sd['w.bias'].cuda(), 0.12, gw.cuda(), gb.cuda(), 32)
+    close(GF.kpconv_group_norm(*args), want, 1e-4, f'kpconv+gn {cin}->{cout}')
+
+
 def test_maxpool_and_upsample(mn):
     cfg, sd, data = mn
     g = torch.Generator().manual_seed(0)
