@@ -268,29 +268,50 @@ __global__ void __launch_bounds__(256) att_softmax_pv_kernel(const float* __rest
         for (int m = lane; m < M; m += 32) s[m] = s[m] / sum;
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const int h = c / d;
+    // P.V: thread = (4 channels, quarter of the keys); 16-byte value loads, 4 of them in flight; quarters folded through smem
+    float4* red = reinterpret_cast<float4*>(sc + ((ATT_R * H * M + 3) & ~3));      // [4][R][C/4]
+    const int C4 = C >> 2;
+    const int kq = threadIdx.x / 64, c4 = threadIdx.x % 64;
+    if (c4 < C4) {
+        const int h = (4 * c4) / d;
         const float* p0 = sc + (0 * H + h) * M;
         const float* p1 = sc + (1 * H + h) * M;
-        float a0[8], a1[8];
+        const int per = (M + 3) / 4, mb = kq * per, me = min(M, mb + per);
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
+        int m = mb;
+        for (; m + 3 < me; m += 4) {
+            float4 vv[4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { a0[u] = 0.f; a1[u] = 0.f; }
-        int m = 0;
-        for (; m + 7 < M; m += 8) {
+            for (int u = 0; u < 4; ++u) vv[u] = __ldg(reinterpret_cast<const float4*>(v + (long long)(m + u) * ldv) + c4);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const float vv = v[(long long)(m + u) * ldv + c];
-                a0[u] = fmaf(p0[m + u], vv, a0[u]);
-                a1[u] = fmaf(p1[m + u], vv, a1[u]);
+            for (int u = 0; u < 4; u += 2) {
+                const float w0 = p0[m + u], w1 = p1[m + u], x0 = p0[m + u + 1], x1 = p1[m + u + 1];
+                a0.x = fmaf(w0, vv[u].x, a0.x); a0.y = fmaf(w0, vv[u].y, a0.y); a0.z = fmaf(w0, vv[u].z, a0.z); a0.w = fmaf(w0, vv[u].w, a0.w);
+                a1.x = fmaf(w1, vv[u].x, a1.x); a1.y = fmaf(w1, vv[u].y, a1.y); a1.z = fmaf(w1, vv[u].z, a1.z); a1.w = fmaf(w1, vv[u].w, a1.w);
+                b0.x = fmaf(x0, vv[u + 1].x, b0.x); b0.y = fmaf(x0, vv[u + 1].y, b0.y); b0.z = fmaf(x0, vv[u + 1].z, b0.z); b0.w = fmaf(x0, vv[u + 1].w, b0.w);
+                b1.x = fmaf(x1, vv[u + 1].x, b1.x); b1.y = fmaf(x1, vv[u + 1].y, b1.y); b1.z = fmaf(x1, vv[u + 1].z, b1.z); b1.w = fmaf(x1, vv[u + 1].w, b1.w);
             }
         }
-        for (; m < M; ++m) {
-            const float vv = v[(long long)m * ldv + c];
-            a0[0] = fmaf(p0[m], vv, a0[0]);
-            a1[0] = fmaf(p1[m], vv, a1[0]);
+        for (; m < me; ++m) {
+            const float4 vv = __ldg(reinterpret_cast<const float4*>(v + (long long)m * ldv) + c4);
+            const float w0 = p0[m], w1 = p1[m];
+            a0.x = fmaf(w0, vv.x, a0.x); a0.y = fmaf(w0, vv.y, a0.y); a0.z = fmaf(w0, vv.z, a0.z); a0.w = fmaf(w0, vv.w, a0.w);
+            a1.x = fmaf(w1, vv.x, a1.x); a1.y = fmaf(w1, vv.y, a1.y); a1.z = fmaf(w1, vv.z, a1.z); a1.w = fmaf(w1, vv.w, a1.w);
         }
-        if (n0 < N) out[(long long)n0 * ldo + c] = ((a0[0] + a0[1]) + (a0[2] + a0[3])) + ((a0[4] + a0[5]) + (a0[6] + a0[7]));
-        if (n0 + 1 < N) out[(long long)(n0 + 1) * ldo + c] = ((a1[0] + a1[1]) + (a1[2] + a1[3])) + ((a1[4] + a1[5]) + (a1[6] + a1[7]));
+        red[(kq * ATT_R + 0) * C4 + c4] = make_float4(a0.x + b0.x, a0.y + b0.y, a0.z + b0.z, a0.w + b0.w);
+        red[(kq * ATT_R + 1) * C4 + c4] = make_float4(a1.x + b1.x, a1.y + b1.y, a1.z + b1.z, a1.w + b1.w);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < ATT_R * C4; t += blockDim.x) {
+        const int r = t / C4, cc = t % C4;
+        if (n0 + r >= N) continue;
+        const float4 q0 = red[(0 * ATT_R + r) * C4 + cc], q1 = red[(1 * ATT_R + r) * C4 + cc];
+        const float4 q2 = red[(2 * ATT_R + r) * C4 + cc], q3 = red[(3 * ATT_R + r) * C4 + cc];
+        float* o = out + (long long)(n0 + r) * ldo + 4 * cc;
+        o[0] = (q0.x + q1.x) + (q2.x + q3.x);
+        o[1] = (q0.y + q1.y) + (q2.y + q3.y);
+        o[2] = (q0.z + q1.z) + (q2.z + q3.z);
+        o[3] = (q0.w + q1.w) + (q2.w + q3.w);
     }
 }
 
@@ -304,7 +325,7 @@ static int launch_streaming(const float* q, int ldq, const float* k, int ldk, co
     kpc = (kpc + 4 * ATS_G - 1) / (4 * ATS_G) * (4 * ATS_G);
     chunks = (M + kpc - 1) / kpc;
     att_scores_kernel<H, J><<<dim3((unsigned)N, (unsigned)chunks), 128, 0, st>>>(q, ldq, k, ldk, qp, qb, E, N, M, kpc, div, S);
-    const size_t smem = sizeof(float) * ATT_R * H * M;
+    const size_t smem = sizeof(float) * (ATT_R * H * (size_t)((M + 3) / 4 * 4) + 4 * ATT_R * 128 * J);     // scores + the 4 partial outputs
     static size_t smem_set = 0;
     if (smem > 48 * 1024 && smem > smem_set) {
         if (cudaFuncSetAttribute(att_softmax_pv_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
@@ -381,13 +402,14 @@ int geob200_attention(const float* q, int64_t ldq, const float* k, int64_t ldk, 
     GEOB_REQUIRE(ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0, "attention: row strides must be multiples of 4 floats");
     GEOB_REQUIRE(heads == 1 || heads == 2 || heads == 4 || heads == 8, "attention: heads must be 1, 2, 4 or 8");
     const float div = sqrtf((float)(channels / heads));   // d_model_per_head ** 0.5
-    const size_t smem_pv = sizeof(float) * ATT_R * heads * n_key;
+    const size_t smem_pv = sizeof(float) * (ATT_R * heads * (size_t)((n_key + 3) / 4 * 4) + 4 * ATT_R * channels);
     if ((channels == 128 || channels == 256) && smem_pv <= 200 * 1024 && workspace != nullptr) {
         // streaming path: lanes <-> channels, (query, key-chunk) grid, scores through the workspace
         GEOB_REQUIRE(workspace_bytes >= geob200_attention_workspace_bytes(n_query, n_key, heads), "attention: workspace too small");
-        GEOB_REQUIRE(((uintptr_t)q % 16) == 0 && ((uintptr_t)k % 16) == 0 && (qp == nullptr || ((uintptr_t)qp % 16) == 0) &&
+        GEOB_REQUIRE(((uintptr_t)q % 16) == 0 && ((uintptr_t)k % 16) == 0 && ((uintptr_t)v % 16) == 0 &&
+                         (qp == nullptr || ((uintptr_t)qp % 16) == 0) &&
                          (embed == nullptr || ((uintptr_t)embed % 16) == 0),
-                     "attention: q, k, qp, embed must be 16-byte aligned");
+                     "attention: q, k, v, qp, embed must be 16-byte aligned");
         float* S = (float*)workspace;
         int rc = -2;
 #define LAUNCH_STREAM(HV)                                                                                                            \

@@ -71,14 +71,11 @@ __device__ __forceinline__ float warp_butterfly(float (&v)[NV], int lane) {
 }
 
 // GroupNorm statistics fused into the tensor-core GEMM epilogue (linear_tc.cu): per row-tile partial (sum, sumsq) per column
-// slot in double, folded into mean_rstd[G][2] by the last CTA of the grid.  ticket must be zero on entry (self-resetting).
+// slot in double; gn_finalize_kernel (kpconv.cu) folds them into mean / rstd.
 struct GnFuse {
     int groups;          // 0 = off
     int slot_width;      // min(channels per group, 32); filled in by linear_tc
-    double eps;
     double* partial;     // [ceil(M/128)][N / slot_width][2]
-    unsigned* ticket;
-    float* mean_rstd;    // [groups][2]
 };
 
 // Bump allocator over a caller-provided workspace.

@@ -123,21 +123,33 @@ __global__ void __launch_bounds__(1024) nc_compact_kernel(const float* __restric
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
     const long long total = (long long)M * N;
-    for (long long base = 0; base < total; base += 1024) {
-        const long long t = base + threadIdx.x;
-        const float v = (t < total) ? overlap[t] : 0.f;
-        const int f = v > 0.f ? 1 : 0;
-        const unsigned bal = __ballot_sync(0xffffffffu, f);
-        if (lane == 0) warp_tot[warp] = __popc(bal);
-        __syncthreads();
-        int off = carry;
-        for (int w = 0; w < warp; ++w) off += warp_tot[w];
-        if (f) {
-            const int o = off + __popc(bal & ((1u << lane) - 1u));
-            idx[2ll * o] = t / N;
-            idx[2ll * o + 1] = t % N;
-            ov_out[o] = v;
+    for (long long base = 0; base < total; base += 4096) {                       // 4 consecutive entries per thread
+        const long long t0 = base + 4ll * threadIdx.x;
+        float v[4];
+        int f = 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            v[u] = (t0 + u < total) ? overlap[t0 + u] : 0.f;
+            f += v[u] > 0.f ? 1 : 0;
         }
+        int incl = f;                                                            // inclusive scan of the counts inside the warp
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        int off = carry + incl - f;
+        for (int w = 0; w < warp; ++w) off += warp_tot[w];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (v[u] > 0.f) {
+                idx[2ll * off] = (t0 + u) / N;
+                idx[2ll * off + 1] = (t0 + u) % N;
+                ov_out[off] = v[u];
+                ++off;
+            }
         __syncthreads();
         if (threadIdx.x == 0) { int s = 0; for (int w = 0; w < 32; ++w) s += warp_tot[w]; carry += s; }
         __syncthreads();
@@ -173,12 +185,13 @@ __global__ void __launch_bounds__(1024) evaluate_kernel(const long long* __restr
     const double nan = __longlong_as_double(0x7ff8000000000000LL);        // mean of an empty tensor, as torch reports it
     // PIR: fraction of predicted superpoint pairs that are ground-truth pairs with overlap > acc_overlap (loss.py:103-120)
     double hit = 0.0;
-    for (int c = threadIdx.x; c < n_node_corr; c += blockDim.x) {
+    for (int c = warp; c < n_node_corr; c += (int)(blockDim.x >> 5)) {          // one warp per predicted pair, lanes over the gt list
         const long long r = ref_corr_idx[c], s = src_corr_idx[c];
         int found = 0;
-        for (int g = 0; g < n_gt; ++g)
-            if (gt_idx[2ll * g] == r && gt_idx[2ll * g + 1] == s && gt_ov[g] > acc_overlap) { found = 1; break; }
-        hit += found;
+        for (int g = lane; g < n_gt; g += 32)
+            if (gt_idx[2ll * g] == r && gt_idx[2ll * g + 1] == s && gt_ov[g] > acc_overlap) found = 1;
+        found = __any_sync(0xffffffffu, found);
+        if (lane == 0) hit += found;
     }
     const double hits = block_sum(hit);
     const double pir = n_node_corr > 0 ? hits / n_node_corr : nan;

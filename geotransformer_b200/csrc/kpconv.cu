@@ -510,6 +510,35 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
     }
 }
 
+// Folds the per-tile (sum, sumsq) partials written by the tensor-core GEMM epilogue (linear_tc.cu) into mean / rstd.
+// One CTA; 32 lanes per group pass (warp w handles groups w, w+32, ...), tiles strided over the lanes, fixed-order tree.
+__global__ void __launch_bounds__(1024) gn_finalize_kernel(const double* __restrict__ partial, int tiles, int slots_total, int spg, int G,
+                                                           double count, double eps, float* __restrict__ mean_rstd) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double2* part = reinterpret_cast<const double2*>(partial);
+    for (int g = warp; g < G; g += 32) {
+        double sa = 0.0, sb = 0.0;
+        for (int sl = 0; sl < spg; ++sl)
+            for (int t = lane; t < tiles; t += 32) {
+                const double2 x = part[(long long)t * slots_total + (long long)g * spg + sl];
+                sa += x.x;
+                sb += x.y;
+            }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sa += __shfl_xor_sync(0xffffffffu, sa, o);
+            sb += __shfl_xor_sync(0xffffffffu, sb, o);
+        }
+        if (lane == 0) {
+            const double mean = sa / count;
+            double var = sb / count - mean * mean;
+            if (var < 0.0) var = 0.0;
+            mean_rstd[2 * g] = (float)mean;
+            mean_rstd[2 * g + 1] = (float)(1.0 / sqrt(var + eps));
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean_rstd,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        const float* __restrict__ residual, float* __restrict__ y,
@@ -720,8 +749,13 @@ static GnWs gn_carve(void* workspace, size_t bytes, int64_t groups) {
     w.partial = ar.take<double>(1);
     return w;
 }
+// statistics came out of the GEMM epilogue as per-tile partials: fold them (one small CTA), then normalise
 static void launch_gn_apply(const float* x, const GnWs& w, const float* gamma, const float* beta, const float* residual, float* y,
-                            int64_t n_rows, int64_t channels, int64_t groups, int leaky, float slope, cudaStream_t st) {
+                            int64_t n_rows, int64_t channels, int64_t groups, float eps, int leaky, float slope, cudaStream_t st) {
+    const int cpg = (int)(channels / groups);
+    const int slot_width = cpg < 32 ? cpg : 32;
+    gn_finalize_kernel<<<1, 1024, 0, st>>>(w.partial, (int)((n_rows + 127) / 128), (int)(channels / slot_width), cpg / slot_width,
+                                           (int)groups, (double)cpg * (double)n_rows, (double)eps, w.mean_rstd);
     const long long total4 = n_rows * channels / 4;
     gn_apply_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(x, w.mean_rstd, gamma, beta, residual, y, total4, (int)channels,
                                                                      (int)(channels / groups), leaky, slope);
@@ -781,13 +815,13 @@ int geob200_linear_group_norm(const float* x, int64_t ldx, const float* weight, 
     GEOB_REQUIRE(workspace_bytes >= geob200_fused_group_norm_workspace_bytes(m, n, groups), "linear_group_norm: workspace too small");
     if (g_linear_mode == 1) {
         const GnWs w = gn_carve(workspace, workspace_bytes, groups);
-        GnFuse gn{(int)groups, 0, (double)eps, w.partial, w.ticket, w.mean_rstd};
+        GnFuse gn{(int)groups, 0, w.partial};
         const int rc = linear_tc(x, ldx, weight, k, bias, nullptr, pre_norm, n, m, n, k, 0, st, &gn);
         if (rc < 0) return rc;
         if (rc == 0) {
-            launch_gn_apply(pre_norm, w, gamma, beta, residual, y, m, n, groups, leaky, slope, st);
+            launch_gn_apply(pre_norm, w, gamma, beta, residual, y, m, n, groups, eps, leaky, slope, st);
             GEOB_CHECK_LAUNCH();
-            count_launches(1);
+            count_launches(2);
             return 0;
         }
     }
@@ -828,13 +862,13 @@ int geob200_kpconv_group_norm(const float* s_feats, const float* q_points, const
     GEOB_CHECK_LAUNCH();
     count_launches(2);
     const GnWs w = gn_carve(gn_workspace, gn_workspace_bytes, groups);
-    GnFuse gn{(int)groups, 0, (double)eps, w.partial, w.ticket, w.mean_rstd};
+    GnFuse gn{(int)groups, 0, w.partial};
     int rc = linear_tc(wf, KP * c_in, weights_t, KP * c_in, bias, inv_count, pre_norm, c_out, n_query, c_out, KP * c_in, 0, st, &gn);
     if (rc < 0) return rc;
     if (rc == 0) {
-        launch_gn_apply(pre_norm, w, gamma, beta, nullptr, y, n_query, c_out, groups, leaky, slope, st);
+        launch_gn_apply(pre_norm, w, gamma, beta, nullptr, y, n_query, c_out, groups, eps, leaky, slope, st);
         GEOB_CHECK_LAUNCH();
-        count_launches(1);
+        count_launches(2);
         return 0;
     }
     // group layout not expressible in the epilogue: plain GEMM, then the stand-alone statistics kernel

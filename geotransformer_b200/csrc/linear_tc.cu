@@ -12,7 +12,7 @@
 //   warp 5      MMA issuer   : tcgen05.mma.cta_group::1.kind::tf32 M128 N{BN} K8, 3 per K-step; tcgen05.commit frees the stage
 //   warps 6-9   epilogue     : tcgen05.ld 32x32b, + bias, ReLU, direct row-segment stores (each thread owns one output row);
 //                              optionally the GroupNorm statistics of the output (per-tile column sums through a transposing
-//                              warp butterfly, per-tile partials in double, last CTA folds them into mean / rstd)
+//                              warp butterfly, written as per-tile partials in double)
 #include <cuda.h>
 
 #include "common.cuh"
@@ -28,8 +28,9 @@ constexpr int TILE_B = 128 * 128;      // 16 KB (BN <= 128 rows)
 constexpr int STAGE = 2 * TILE_A + 2 * TILE_B;   // raw/hi + lo for both operands = 64 KB
 constexpr int NSTAGE = 3;
 constexpr int NTHREADS = 320;
-constexpr int GN_SM = 4 * 128 * 8;      // per epilogue warp: (sum, sumsq) of up to 128 column slots
-constexpr int SMEM = NSTAGE * STAGE + 1024 + 256 + GN_SM;
+// 193.25 KB + the 1 KB the system reserves per CTA fits the 196 KB shared-memory carve-out; anything larger forces the 228 KB
+// configuration and costs ~8 us per launch in carve-out switches against the neighbouring kernels (measured)
+constexpr int SMEM = NSTAGE * STAGE + 1024 + 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -91,8 +92,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const __grid_con
     uint64_t* empty = bars + 2 * NSTAGE;        // MMAs done with the stage
     uint64_t* acc_full = bars + 3 * NSTAGE;
     uint32_t* tmem_slot = (uint32_t*)(acc_full + 1);
-    unsigned* gn_last = (unsigned*)(tmem_slot + 1);
-    float2* gn_sm = (float2*)(smem + NSTAGE * STAGE + 256);
+    float2* gn_sm = (float2*)smem;      // GroupNorm column sums [4 warps][128 slots]: stage 0 is idle once acc_full has fired
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int nk = (K + KC - 1) / KC;
@@ -249,7 +249,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const __grid_con
             }
         }
         if (gn.groups > 0) {
-            // 4 epilogue warps -> per-tile partial (fixed order), then the last CTA of the grid folds all tiles
+            // 4 epilogue warps -> per-tile partial in a fixed order; gn_finalize_kernel (kpconv.cu) folds the tiles afterwards
+            // (no fence / ticket here: the CTA must not wait for its output stores to drain)
             const int et = threadIdx.x - 6 * 32;
             const int slots_tile = BN / gn.slot_width, slots_total = N / gn.slot_width;
             asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -258,40 +259,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const __grid_con
                 double* dst = gn.partial + ((long long)blockIdx.y * slots_total + n0 / gn.slot_width + et) * 2;
                 dst[0] = ((double)p0.x + (double)p1.x) + ((double)p2.x + (double)p3.x);
                 dst[1] = ((double)p0.y + (double)p1.y) + ((double)p2.y + (double)p3.y);
-            }
-            __threadfence();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (et == 0) *gn_last = (atomicAdd(gn.ticket, 1u) == gridDim.x * gridDim.y - 1) ? 1u : 0u;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (*gn_last) {
-                __threadfence();
-                const int cpg = N / gn.groups;
-                const int spg = cpg / gn.slot_width;             // slots per group (1 unless a group is wider than 32 channels)
-                for (int g0 = 0; g0 < gn.groups; g0 += 32) {
-                    const int g = g0 + (et >> 2), u = et & 3;
-                    double sa = 0.0, sb = 0.0;
-                    if (g < gn.groups)
-                        for (unsigned t = u; t < gridDim.y; t += 4)
-                            for (int sl = 0; sl < spg; ++sl) {
-                                const double* src = gn.partial + ((long long)t * slots_total + g * spg + sl) * 2;
-                                sa += __ldcg(src);
-                                sb += __ldcg(src + 1);
-                            }
-#pragma unroll
-                    for (int off = 2; off > 0; off >>= 1) {
-                        sa += __shfl_xor_sync(0xffffffffu, sa, off);
-                        sb += __shfl_xor_sync(0xffffffffu, sb, off);
-                    }
-                    if (g < gn.groups && u == 0) {
-                        const double cnt = (double)cpg * (double)M;
-                        const double mean = sa / cnt;
-                        double var = sb / cnt - mean * mean;
-                        if (var < 0.0) var = 0.0;
-                        gn.mean_rstd[2 * g] = (float)mean;
-                        gn.mean_rstd[2 * g + 1] = (float)(1.0 / sqrt(var + gn.eps));
-                    }
-                }
-                if (et == 0) *gn.ticket = 0u;                    // self-reset for the next launch on this stream
             }
         }
     }

@@ -459,20 +459,28 @@ def local_global_registration(cfg, ref_knn_pts, src_knn_pts, ref_masks, src_mask
             br[i, :y - x], bs[i, :y - x], bw[i, :y - x] = ref_c[x:y], src_c[x:y], sc[x:y]
         Ts = weighted_procrustes(bs, br, bw)
         aligned = apply_transform(src_c.unsqueeze(0), Ts)
-        inl = torch.lt(torch.linalg.norm(ref_c.unsqueeze(0) - aligned, dim=2), fm.acceptance_radius)
+        res_all = torch.linalg.norm(ref_c.unsqueeze(0) - aligned, dim=2)
+        inl = torch.lt(res_all, fm.acceptance_radius)
         best = inl.sum(dim=1).argmax()
         cur = sc * inl[best].float()
+        margins = [float((res_all[best] - fm.acceptance_radius).abs().min())]
         if taps is not None:
             taps['patch_transforms'], taps['inlier_counts'], taps['best_index'] = Ts, inl.sum(dim=1), best
     else:
         T = weighted_procrustes(src_c, ref_c, sc)
         res = torch.linalg.norm(ref_c - apply_transform(src_c, T), dim=1)
         cur = sc * torch.lt(res, fm.acceptance_radius).float()
+        margins = [float((res - fm.acceptance_radius).abs().min())]
     T = weighted_procrustes(src_c, ref_c, cur)
     for _ in range(fm.num_refinement_steps - 1):
         res = torch.linalg.norm(ref_c - apply_transform(src_c, T), dim=1)
+        margins.append(float((res - fm.acceptance_radius).abs().min()))
         cur = sc * torch.lt(res, fm.acceptance_radius).float()
         T = weighted_procrustes(src_c, ref_c, cur)
+    if taps is not None:
+        # distance of the closest residual to the hard inlier threshold over the hypothesis test and every refinement
+        # step: below float noise the selected inlier set (hence T) is not reproducible between implementations
+        taps['threshold_margin'] = min(margins)
     return ref_c, src_c, sc, T
 
 

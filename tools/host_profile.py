@@ -25,7 +25,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 48
 pairs = [{k: torch.from_numpy(make_pair('3dmatch20k', i)[k]).pin_memory() for k in keys} for i in range(n)]
 ev = Evaluator(cfg)
 
-for s in (1, 2, 4, 6, 8, 12):
+for s in (1, 4, 6, 8):
     eng = RegistrationEngine(model, cfg, limits, num_streams=s, evaluator=ev)
     eng.register(pairs[:max(8, 2 * s)])
     torch.cuda.synchronize()
@@ -35,6 +35,21 @@ for s in (1, 2, 4, 6, 8, 12):
     dt = time.perf_counter() - t0
     print(f'streams {s:2d}: {n / dt:7.1f} pairs/s  ({dt / n * 1e3:.2f} ms per pair)')
     eng.close()
+
+# is the GPU the limit?  triple the Sinkhorn work (+1.1 ms of full-GPU kernels per pair) and compare
+it0 = model.optimal_transport.num_iterations
+for s, iters in ((4, it0), (4, 3 * it0), (6, it0), (6, 3 * it0)):
+    model.optimal_transport.num_iterations = iters
+    eng = RegistrationEngine(model, cfg, limits, num_streams=s, evaluator=ev)
+    eng.register(pairs[:16])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    eng.register(pairs)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    print(f'streams {s:2d}, sinkhorn iterations {iters}: {n / dt:7.1f} pairs/s  ({dt / n * 1e3:.2f} ms per pair)')
+    eng.close()
+model.optimal_transport.num_iterations = it0
 
 eng = RegistrationEngine(model, cfg, limits, num_streams=1, evaluator=ev)
 eng.register(pairs[:8])
