@@ -348,6 +348,111 @@ __global__ void __launch_bounds__(1024) sinkhorn_kernel(const float* __restrict_
     }
 }
 
+// Register-resident variant (K+1 <= MAXT / LPR rows): every thread keeps its NE entries of its row AND its NE entries of its
+// column in registers for all iterations, in the log2 domain (Z * log2 e), so that a half-iteration is one shared-memory load
+// (the other potential), one ex2 and ~4 ALU instructions per entry.  The generic kernel above re-reads Z from shared memory
+// twice per entry and pays expf's range reduction; it is issue-bound at 64 resident warps per SM.
+template <int LPR, int NE, int MAXT>
+__global__ void __launch_bounds__(MAXT) sinkhorn_reg_kernel(const float* __restrict__ scores, const unsigned char* __restrict__ row_masks,
+                                                           const unsigned char* __restrict__ col_masks, const float* __restrict__ alpha_p,
+                                                           int K, int iters, float inf, float* __restrict__ out) {
+    extern __shared__ float sm[];
+    const int K1 = K + 1;
+    const int ld = K1 | 1;
+    float* Z = sm;                           // [K1][ld], natural-log domain (also the source of the final output)
+    float* u = Z + K1 * ld;                  // log2 domain
+    float* v = u + K1;
+    __shared__ float norm_s;
+    __shared__ int cnt_s[2];
+    const int p = blockIdx.x;
+    const float alpha = *alpha_p;
+    constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+    if (threadIdx.x < 2) cnt_s[threadIdx.x] = 0;
+    __syncthreads();
+    {
+        int cr = 0, cc = 0;
+        for (int i = threadIdx.x; i < K; i += blockDim.x) { cr += row_masks[(long long)p * K + i] ? 1 : 0; cc += col_masks[(long long)p * K + i] ? 1 : 0; }
+        if (cr) atomicAdd(&cnt_s[0], cr);
+        if (cc) atomicAdd(&cnt_s[1], cc);
+    }
+    __syncthreads();
+    const float nvr = (float)cnt_s[0], nvc = (float)cnt_s[1];
+    if (threadIdx.x == 0) norm_s = -logf(nvr + nvc);
+    __syncthreads();
+    const float norm = norm_s;
+    for (int e = threadIdx.x; e < K1 * K1; e += blockDim.x) {
+        const int i = e / K1, j = e % K1;
+        float z = (i < K && j < K) ? scores[((long long)p * K + i) * K + j] : alpha;
+        const bool rm = (i < K) && !row_masks[(long long)p * K + i];
+        const bool cm = (j < K) && !col_masks[(long long)p * K + j];
+        if (rm || cm) z = -inf;
+        Z[i * ld + j] = z;
+    }
+    for (int i = threadIdx.x; i < K1; i += blockDim.x) { u[i] = 0.f; v[i] = 0.f; }
+    __syncthreads();
+    const int slot = threadIdx.x / LPR, sub = threadIdx.x % LPR;
+    const bool act = slot < K1;
+    const int ij = act ? slot : K1 - 1;
+    float zr[NE], zc[NE];
+#pragma unroll
+    for (int k = 0; k < NE; ++k) {
+        const int o = sub + LPR * k;
+        zr[k] = (o < K1) ? Z[ij * ld + o] * LOG2E : -INFINITY;      // row ij, column o
+        zc[k] = (o < K1) ? Z[o * ld + ij] * LOG2E : -INFINITY;      // column ij, row o
+    }
+    float lmu2, lnu2;                                               // log2-domain marginals of row / column ij
+    {
+        float mu = (ij < K) ? norm : logf(nvc) + norm;
+        float nu = (ij < K) ? norm : logf(nvr) + norm;
+        if (ij < K && !row_masks[(long long)p * K + ij]) mu = -inf;
+        if (ij < K && !col_masks[(long long)p * K + ij]) nu = -inf;
+        lmu2 = mu * LOG2E;
+        lnu2 = nu * LOG2E;
+    }
+    for (int it = 0; it < iters; ++it) {
+        {
+            float t[NE], mx = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < NE; ++k) {
+                const int o = sub + LPR * k;
+                t[k] = zr[k] + v[o < K1 ? o : 0];
+                mx = fmaxf(mx, t[k]);
+            }
+#pragma unroll
+            for (int o = LPR / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < NE; ++k) s += exp2f(t[k] - mx);
+#pragma unroll
+            for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (act && sub == 0) u[ij] = lmu2 - (log2f(s) + mx);
+        }
+        __syncthreads();
+        {
+            float t[NE], mx = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < NE; ++k) {
+                const int o = sub + LPR * k;
+                t[k] = zc[k] + u[o < K1 ? o : 0];
+                mx = fmaxf(mx, t[k]);
+            }
+#pragma unroll
+            for (int o = LPR / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < NE; ++k) s += exp2f(t[k] - mx);
+#pragma unroll
+            for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (act && sub == 0) v[ij] = lnu2 - (log2f(s) + mx);
+        }
+        __syncthreads();
+    }
+    for (int e = threadIdx.x; e < K1 * K1; e += blockDim.x) {
+        const int i = e / K1, j = e % K1;
+        out[(long long)p * K1 * K1 + e] = Z[i * ld + j] + (u[i] + v[j]) * LN2 - norm;
+    }
+}
+
 }  // namespace geob200
 
 using namespace geob200;
@@ -437,7 +542,23 @@ int geob200_sinkhorn(const float* scores, const uint8_t* row_masks, const uint8_
         GEOB_CHECK_CUDA(cudaFuncSetAttribute(sinkhorn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
-    sinkhorn_kernel<<<(unsigned)n_patches, (k >= 48 ? 1024 : 512), smem, st>>>(scores, row_masks, col_masks, alpha, (int)k, (int)num_iterations, inf, out);
+#define LAUNCH_SK_REG(LPRV, NEV, MT)                                                                                                  \
+    {                                                                                                                            \
+        static size_t set_bytes = 0;                                                                                             \
+        if (smem > 48 * 1024 && smem > set_bytes) {                                                                              \
+            GEOB_CHECK_CUDA(cudaFuncSetAttribute(sinkhorn_reg_kernel<LPRV, NEV, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            set_bytes = smem;                                                                                                    \
+        }                                                                                                                        \
+        const int threads = ((K1 * LPRV + 31) / 32) * 32;                                                                        \
+        sinkhorn_reg_kernel<LPRV, NEV, MT><<<(unsigned)n_patches, threads, smem, st>>>(scores, row_masks, col_masks, alpha, (int)k,  \
+                                                                                  (int)num_iterations, inf, out);               \
+    }
+    if (K1 <= 40) LAUNCH_SK_REG(8, 5, 320)
+    else if (K1 <= 72) LAUNCH_SK_REG(8, 9, 576)
+    else if (K1 <= 132) LAUNCH_SK_REG(4, 33, 544)
+    else
+        sinkhorn_kernel<<<(unsigned)n_patches, 1024, smem, st>>>(scores, row_masks, col_masks, alpha, (int)k, (int)num_iterations, inf, out);
+#undef LAUNCH_SK_REG
     GEOB_CHECK_LAUNCH();
     count_launches(1);
     return 0;

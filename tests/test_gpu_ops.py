@@ -411,6 +411,25 @@ def test_patch_scores_and_sinkhorn(k):
     assert (rows[ok] - 1).abs().max() < 1e-3
 
 
+@pytest.mark.parametrize('k', [5, 39, 40, 71, 72, 131, 200])
+def test_sinkhorn_kernel_variants(k):
+    """register-resident kernels (K+1 <= 40 / 72 / 132) and the generic shared-memory kernel against the oracle"""
+    g = torch.Generator().manual_seed(k)
+    p = 7
+    scores = torch.randn(p, k, k, generator=g) * 3.0
+    rm, cm = torch.rand(p, k, generator=g) > 0.2, torch.rand(p, k, generator=g) > 0.2
+    rm[:, 0] = True
+    cm[:, 0] = True
+    rm[2] = False
+    alpha = torch.tensor(0.7)
+    want = G.optimal_transport(alpha, scores, rm, cm, 100)
+    got = GF.sinkhorn(scores.cuda(), rm.cuda(), cm.cuda(), alpha.cuda(), 100).cpu()
+    fin = torch.isfinite(want) & (want > -1e11)
+    assert torch.equal(torch.isfinite(got) & (got > -1e11), fin)
+    err = (got[fin] - want[fin]).abs().max().item()
+    assert err <= 1e-4, f'k={k}: sinkhorn log-assignment max abs err {err:.3e}'
+
+
 def test_weighted_procrustes_and_edge_cases():
     g = torch.Generator().manual_seed(2)
     b, n = 9, 50
