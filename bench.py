@@ -8,13 +8,15 @@ Sinkhorn -> local-to-global registration) over a batch of --streams synthetic pa
 geotransformer_b200.engine.RegistrationEngine (weak scaling: pair i of rank r is synth.make_pair(workload, r + i*W)).  Prints ONE JSON line (see the task contract):
   value     pairs/s with the raw pair already resident in HBM when the timed region starts
   e2e       pairs/s through the public API with HOST (pinned) inputs: H2D + collate + forward + D2H of the transform
-  roofline  the dominant kernel (structure-embedding contraction), algorithmic FLOPs / CUDA-event time
+  roofline  the dominant kernel by GPU-time share (tcgen05 GEMM family), algorithmic FLOPs / CUDA-event time; the
+            structure-embedding contraction (largest single launch) is reported beside it as roofline_gse_embed
   cpu_baseline  the reference's CPU path on this box's host cores, bounded sample (N=1 only)
 --impl reference times that CPU path alone (oracle port of the forward + the reference's own C++ collate ops).
 """
 import argparse
 import json
 import os
+
 import subprocess
 import sys
 import threading
@@ -234,8 +236,15 @@ def main():
     GF.EVENTS = {}
     barrier()
     n_solo = min(K * S, 8)
+    lib.geob200_linear_profile_enable(1)          # CUDA events around every tcgen05 GEMM launch of these pairs
     solo.register(resident[W * S:W * S + n_solo])
     barrier()
+    import ctypes
+    cap = 400 * n_solo
+    shp, gms = (ctypes.c_int64 * (3 * cap))(), (ctypes.c_float * cap)()
+    n_gemm = int(lib.geob200_linear_profile_read(cap, shp, gms))
+    lib.geob200_linear_profile_enable(0)
+    gemm = [(int(shp[3 * i]), int(shp[3 * i + 1]), int(shp[3 * i + 2]), float(gms[i])) for i in range(n_gemm)]
     events_solo = GF.EVENTS
     GF.EVENTS = None
     solo.close()
@@ -272,13 +281,33 @@ def main():
     achieved = flops / (avg_ms * 1e-3) / 1e12 if avg_ms else None
     avg_ms_concurrent = float(np.mean(gse_ms)) if gse_ms else None
     mode_name = {0: 'fp32 CUDA cores', 1: 'tcgen05 3xTF32', 2: 'tcgen05 1xTF32', 3: 'tcgen05 3xFP16 (fp32-accurate split)', 4: 'tcgen05 3xFP16 split, CTA-pair TMA multicast of B'}[GF.GSE_MODE]
-    roofline = {'kernel': 'gse_embed (structure-embedding contraction)', 'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf,
+    roofline_gse = {'kernel': 'gse_embed (structure-embedding contraction)', 'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf,
                 'unit': 'TFLOP/s', 'frac': (achieved / peak_tf) if achieved else None, 'traffic': None,
                 'avg_ms_per_launch': avg_ms, 'launches_timed': len(gse_solo_ms), 'flops_per_launch': flops,
                 'avg_ms_per_launch_with_other_streams_active': avg_ms_concurrent,
                 'timing': 'CUDA events around the launch, one pair in flight (kernel alone on the GPU), same workload, after the timed regions',
                 'share_of_gpu_time': (sum(gse_ms) / (ms_res * S)) if gse_ms else None, 'mode': mode_name,
                 'peak_source': f'{peak_src} bf16 dense (MEASURED_PEAKS.json); TF32 dense peak is half of it'}
+
+    # dominant kernel by share of the step's GPU time: linear_tc_kernel (every nn.Linear and the KPConv contraction; ~80 launches
+    # per pair, shapes M=40 000..320, K=32..3840, N=32..1024).  ALGORITHMIC flops = 2*M*N*K of the fp32 product the reference
+    # computes (the kernel executes 3 TF32 MMAs per product term for fp32 accuracy); times = CUDA events around each launch.
+    g_flops = sum(2.0 * m * n * k for m, n, k, _ in gemm)
+    g_ms = sum(t for _, _, _, t in gemm)
+    g_bytes = sum(4.0 * (m * k + n * k + m * n) for m, n, k, _ in gemm)
+    big = sorted(gemm, key=lambda r: -r[3])[:3]
+    roofline = {'kernel': 'linear_tc_kernel (tcgen05 3xTF32 GEMM: all nn.Linear + KPConv contraction)', 'bound': 'tensor',
+                'achieved': (g_flops / (g_ms * 1e-3) / 1e12) if g_ms else None, 'peak': peak_tf, 'unit': 'TFLOP/s',
+                'frac': (g_flops / (g_ms * 1e-3) / 1e12 / peak_tf) if g_ms else None, 'traffic': None,
+                'launches_timed': n_gemm, 'launches_per_pair': n_gemm / max(n_solo, 1), 'ms_per_pair': g_ms / max(n_solo, 1),
+                'flops_per_pair': g_flops / max(n_solo, 1), 'algorithmic_bytes_per_pair': g_bytes / max(n_solo, 1),
+                'achieved_GBps': (g_bytes / (g_ms * 1e-3) / 1e9) if g_ms else None, 'hbm_peak_GBps': peak_hbm,
+                'slowest_launches_m_n_k_ms': [[m, n, k, round(t, 4)] for m, n, k, t in big],
+                'share_of_gpu_time': (g_ms / max(n_solo, 1)) / (ms_res / (K * S) * S) if g_ms else None,
+                'timing': 'CUDA events around every launch, one pair in flight (kernel alone on the GPU), same workload, after the timed regions',
+                'note': 'a family of ~80 small GEMMs per pair: most launches cover <= 27 CTAs and are latency-bound (K-loop of one CTA), '
+                        'see DESIGN.md section 5; share_of_gpu_time = its time per pair (kernel alone) / stream-time per pair (streams x wall)',
+                'peak_source': f'{peak_src} bf16 dense (MEASURED_PEAKS.json); the TF32 pipe peaks at half of it and 3 MMAs run per product'}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -302,7 +331,7 @@ def main():
                    'weights': 'random init (synthetic_state_dict seed 7351)'},
         'e2e': {'value': total_pairs / (ms_e2e * 1e-3), 'unit': 'pairs/s', 'ms_per_step': ms_e2e / K,
                 'h2d_bytes_per_step': int(h2d_bytes), 'd2h_bytes_per_step': 96 * S},
-        'gpu_launches': int(launches), 'cuda_mallocs_in_timed_regions': int(seg1 - seg0), 'roofline': roofline, 'cpu_baseline': cpu, 'clocks': sampler.summary(),
+        'gpu_launches': int(launches), 'cuda_mallocs_in_timed_regions': int(seg1 - seg0), 'roofline': roofline, 'roofline_gse_embed': roofline_gse, 'cpu_baseline': cpu, 'clocks': sampler.summary(),
         'quality': {'median_rre_deg': float(rows_t[:, 0].median()), 'median_rte': float(rows_t[:, 1].median()),
                     'mean_correspondences': float(rows_t[:, 2].mean()), 'pairs': int(rows_t.shape[0]),
                     'mean_PIR': float(rows_t[:, 4].nanmean()), 'mean_IR': float(rows_t[:, 5].nanmean()),

@@ -72,6 +72,8 @@ _sig('geob200_node_correspondences_workspace_bytes', SZ, I64, I64, I64)
 _sig('geob200_node_correspondences', c_int, P, P, P, P, P, P, P, P, I64, I64, I64, P, F, P, P, P, P, SZ, P)
 _sig('geob200_evaluate', c_int, P, P, I64, F, P, P, I64, P, P, I64, F, P, P, P, I64, c_int, F, F, F, P, P)
 
+_sig('geob200_linear_profile_enable', c_int, c_int)
+_sig('geob200_linear_profile_read', I64, I64, P, P)
 _sig('geob200_backbone_workspace_bytes', SZ, P, P)
 _sig('geob200_backbone_forward', c_int, P, P, P, P, P, P, P, P, P, P, P, P, SZ, P, SZ, P)
 _sig('geob200_transformer_workspace_bytes', SZ, I64, I64, I64, I64, I64)
@@ -147,7 +149,8 @@ def workspace(nbytes, device, tag='default'):
     key = (device.index if device.index is not None else torch.cuda.current_device(), stream_ptr(), tag)
     buf = _WS.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        # 30% headroom: pair sizes vary by a few percent and regrowing a large scratch means a cudaMalloc in the hot loop
+        buf = torch.empty(max(int(nbytes * 1.3), 1 << 20), dtype=torch.uint8, device=device)
         _WS[key] = buf
     return buf
 

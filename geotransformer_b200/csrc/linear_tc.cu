@@ -15,6 +15,9 @@
 //                              warp butterfly, written as per-tile partials in double)
 #include <cuda.h>
 
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 #include "geob200.h"
 
@@ -306,6 +309,12 @@ static int encode_map(CUtensorMap* map, const float* base, int64_t rows, int64_t
 
 }  // namespace ltc
 
+// ---- optional per-launch profile (bench.py roofline): CUDA events around every linear_tc launch + its shape ----------------
+struct ProfRec { cudaEvent_t a, b; long long m, n, k; };
+static std::vector<ProfRec> g_prof;
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+
 // returns 1 when the shape/alignment is not handled by the tensor-core path (caller falls back to the fp32 kernel)
 int linear_tc(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, const float* row_scale, float* y, int64_t ldy,
               int64_t m, int64_t n, int64_t k, int relu, cudaStream_t st, const GnFuse* gn) {
@@ -330,10 +339,52 @@ int linear_tc(const float* x, int64_t ldx, const float* w, int64_t ldw, const fl
         if (g.groups <= 0 || n % g.groups != 0 || (cpg < 32 ? (32 % cpg) != 0 : (cpg % 32) != 0 || (BN % cpg) != 0) || relu) return 1;
         g.slot_width = (int)(cpg < 32 ? cpg : 32);
     }
+    ProfRec rec{};
+    const bool prof = g_prof_on;
+    if (prof) {
+        cudaEventCreate(&rec.a);
+        cudaEventCreate(&rec.b);
+        rec.m = m; rec.n = n; rec.k = k;
+        cudaEventRecord(rec.a, st);
+    }
     ltc::linear_tc_kernel<<<grid, ltc::NTHREADS, ltc::SMEM, st>>>(mx, mw, bias, row_scale, y, (int)ldy, (int)m, (int)n, (int)k, BN, relu, g);
+    if (prof) {
+        cudaEventRecord(rec.b, st);
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        g_prof.push_back(rec);
+    }
     GEOB_CHECK_LAUNCH();
     count_launches(1);
     return 0;
 }
 
 }  // namespace geob200
+
+extern "C" {
+
+// Profiling aid for bench.py: while enabled every tensor-core GEMM launch is bracketed by CUDA events on its stream.
+int geob200_linear_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(geob200::g_prof_mu);
+    for (auto& r : geob200::g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    geob200::g_prof.clear();
+    geob200::g_prof_on = on != 0;
+    return 0;
+}
+
+// Synchronises the recorded launches and returns their number; shapes[3*i..] = (m, n, k), ms[i] = kernel time.
+int64_t geob200_linear_profile_read(int64_t capacity, int64_t* shapes, float* ms) {
+    std::lock_guard<std::mutex> lk(geob200::g_prof_mu);
+    int64_t n = 0;
+    for (auto& r : geob200::g_prof) {
+        if (n >= capacity) break;
+        if (cudaEventSynchronize(r.b) != cudaSuccess) break;
+        float t = 0.f;
+        cudaEventElapsedTime(&t, r.a, r.b);
+        shapes[3 * n] = r.m; shapes[3 * n + 1] = r.n; shapes[3 * n + 2] = r.k;
+        ms[n] = t;
+        ++n;
+    }
+    return n;
+}
+
+}  // extern "C"

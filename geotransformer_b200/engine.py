@@ -28,6 +28,7 @@ class RegistrationEngine:
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         self.num_streams = num_streams
         self.evaluator = evaluator
+        self.stage_times = None          # set to {} to collect per-stage CUDA-event times (profiling; adds ~7 events per pair)
         self.streams = [torch.cuda.Stream(self.device) for _ in range(num_streams)]
         self.pool = ThreadPoolExecutor(max_workers=num_streams)
         # per slot: [estimated_transform (16) | metrics (8)] on the device and pinned on the host
@@ -37,8 +38,16 @@ class RegistrationEngine:
     def _one(self, slot, pair, keep):
         stream = self.streams[slot]
         b = self.cfg.backbone
+        marks = None
+        if self.stage_times is not None:
+            marks = []
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            marks.append(('begin', e))
         data = registration_collate_fn_stack_mode([pair], b.num_stages, b.init_voxel_size, b.init_radius, self.limits,
                                                   device=self.device)
+        if marks is not None:
+            data['_stage_events'] = marks
         out = self.model(data)
         r_dev, r_host = self.r_dev[slot], self.r_host[slot]
         r_dev[:16].copy_(out['estimated_transform'].reshape(16))
@@ -48,6 +57,9 @@ class RegistrationEngine:
         done = torch.cuda.Event()
         done.record(stream)
         done.synchronize()                      # this thread only; the other streams keep running
+        if marks is not None:          # per-stage GPU time of this pair (stage label = the interval ending at that mark)
+            for (_, e0), (label, e1) in zip(marks[:-1], marks[1:]):
+                self.stage_times.setdefault('collate' if label == 'start' else label, []).append(e0.elapsed_time(e1))
         res = {'estimated_transform': r_host[:16].reshape(4, 4).clone(), 'num_corr': int(out['ref_corr_points'].shape[0]),
                'num_superpoints': (int(out['ref_points_c'].shape[0]), int(out['src_points_c'].shape[0]))}
         if self.evaluator is not None:

@@ -41,6 +41,13 @@ class GeoTransformer(nn.Module):
     @torch.no_grad()
     def forward(self, data_dict, taps=None):
         out = {}
+        marks = data_dict.get('_stage_events')            # profiling hook: list receiving (label, CUDA event) pairs
+        def mark(label):
+            if marks is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append((label, e))
+        mark('start')
         feats = data_dict['features']
         lens = data_dict['lengths']
         fl = self.fine_level
@@ -75,13 +82,16 @@ class GeoTransformer(nn.Module):
             gt_pending = GF.node_correspondences(ref_c, src_c, ref_all_pts, src_all_pts, transform, self.matching_radius,
                                                  ref_node_masks, src_node_masks, ref_knn_masks, src_knn_masks)
 
+        mark('partition+gt')
         native = getattr(self, '_native', None)          # NativeModel: backbone / transformer as one C call each
         feats_list = native.backbone_forward(feats, data_dict) if native is not None else self.backbone(feats, data_dict)
         feats_c, feats_f = feats_list[-1], feats_list[0]
+        mark('backbone')
         if taps is not None:
             taps['feats_c'], taps['feats_f'] = feats_c, feats_f
 
         ref_fc, src_fc = self.transformer(ref_c, src_c, feats_c[:nc], feats_c[nc:], native=native)
+        mark('transformer')
         ref_fc_n, src_fc_n = GF.l2_normalize(ref_fc), GF.l2_normalize(src_fc)
         ref_ff, src_ff = feats_f[:nf], feats_f[nf:]
         out.update(ref_feats_c=ref_fc_n, src_feats_c=src_fc_n, ref_feats_f=ref_ff, src_feats_f=src_ff)
@@ -102,9 +112,11 @@ class GeoTransformer(nn.Module):
             taps['matching_scores_raw'] = scores
         scores = self.optimal_transport(scores, rk_masks, sk_masks)
         out['matching_scores'] = scores
+        mark('matching+sinkhorn')
 
         rc, sc, cs, T = self.fine_matching(rk_pts, sk_pts, rk_masks, sk_masks, scores, node_scores)
         out.update(ref_corr_points=rc, src_corr_points=sc, corr_scores=cs, estimated_transform=T)
+        mark('lgr')
         if gt_pending is not None:
             out['gt_node_corr_indices'], out['gt_node_corr_overlaps'] = GF.finish_node_correspondences(*gt_pending)
         return out

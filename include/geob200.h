@@ -217,6 +217,11 @@ int geob200_evaluate(const int64_t* gt_node_corr_indices, const float* gt_node_c
                      int64_t n_src_points, int mode, float rmse_threshold, float rre_threshold, float rte_threshold,
                      float* metrics, void* stream);
 
+/* Profiling aid (bench.py roofline): while enabled, every tcgen05 GEMM launch (nn.Linear and the KPConv contraction) is
+ * bracketed by CUDA events on its stream; _read synchronises them and returns the count, shapes[3i..] = (m, n, k), ms[i]. */
+int geob200_linear_profile_enable(int on);
+int64_t geob200_linear_profile_read(int64_t capacity, int64_t* shapes, float* ms);
+
 /* ---- native stage drivers (native.cu) ------------------------------------------------------------------------
  * The whole KPConv-FPN backbone / geometric transformer as ONE call: same kernels in the same order as the per-op entry
  * points above (bitwise-identical results), driven from C++ so that the host cost per pair is a few hundred microseconds

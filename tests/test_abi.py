@@ -13,7 +13,7 @@ def _header_decls():
     hdr = open(os.path.join(ROOT, 'include', 'geob200.h')).read()
     hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
     hdr = re.sub(r'typedef struct \{.*?\} \w+;', '', hdr, flags=re.S)
-    return re.findall(r'\b(?:int|void|size_t|uint64_t|const char\*)\s+(geob200_\w+)\s*\(([^;]*?)\)\s*;', hdr, flags=re.S)
+    return re.findall(r'\b(?:int|void|size_t|uint64_t|int64_t|const char\*)\s+(geob200_\w+)\s*\(([^;]*?)\)\s*;', hdr, flags=re.S)
 
 
 def test_library_exports_every_declared_symbol():

@@ -36,6 +36,16 @@ for s in (1, 4, 6, 8):
     print(f'streams {s:2d}: {n / dt:7.1f} pairs/s  ({dt / n * 1e3:.2f} ms per pair)')
     eng.close()
 
+# per-stage GPU time of a pair, alone and with 4 pairs in flight
+for s in (1, 4):
+    eng = RegistrationEngine(model, cfg, limits, num_streams=s, evaluator=ev)
+    eng.register(pairs[:16])
+    eng.stage_times = {}
+    eng.register(pairs)
+    print(f'streams {s}: per-stage ms per pair:', {k: round(sum(v) / len(v), 3) for k, v in eng.stage_times.items()},
+          'total', round(sum(sum(v) / len(v) for v in eng.stage_times.values()), 3))
+    eng.close()
+
 # is the GPU the limit?  triple the Sinkhorn work (+1.1 ms of full-GPU kernels per pair) and compare
 it0 = model.optimal_transport.num_iterations
 for s, iters in ((4, it0), (4, 3 * it0), (6, it0), (6, 3 * it0)):
