@@ -32,6 +32,7 @@ _sig('geob200_grid_subsample', c_int, P, I64, P, I64, F, P, P, P, SZ, P)
 _sig('geob200_radius_search_workspace_bytes', SZ, I64, I64, I64)
 _sig('geob200_radius_search', c_int, P, I64, P, I64, P, P, I64, F, I64, P, P, P, P, SZ, P)
 
+_sig('geob200_neighbor_histogram', c_int, P, I64, I64, I64, I64, P, P)
 _sig('geob200_kpconv_workspace_bytes', SZ, I64)
 _sig('geob200_kpconv', c_int, P, P, P, P, I64, I64, I64, P, I64, P, P, I64, I64, F, P, P, SZ, P)
 _sig('geob200_kpconv_tc_workspace_bytes', SZ, I64, I64, I64)

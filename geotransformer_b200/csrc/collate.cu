@@ -626,6 +626,17 @@ __global__ void rs_redo_kernel(const float* __restrict__ q_pts, const CloudSeg* 
     }
 }
 
+// calibrate_neighbors_stack_mode (utils/data.py:190-217): histogram of the number of valid entries per neighbour-table row
+// (np.sum(neighbors < n_support, axis=1) -> np.bincount(...)[:hist_n]).  One thread per row, counts beyond hist_n dropped.
+__global__ void __launch_bounds__(256) neighbor_histogram_kernel(const long long* __restrict__ nbr, long long rows, int width,
+                                                                 long long n_support, int hist_n, int* __restrict__ hist) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    int c = 0;
+    for (int j = 0; j < width; ++j) c += nbr[r * width + j] < n_support ? 1 : 0;
+    if (c < hist_n) atomicAdd(&hist[c], 1);
+}
+
 }  // namespace geob200
 
 using namespace geob200;
@@ -786,6 +797,16 @@ int geob200_radius_search(const float* q_points, int64_t n_query, const float* s
     }
     GEOB_CHECK_LAUNCH();
     count_launches(4);
+    return 0;
+}
+
+int geob200_neighbor_histogram(const int64_t* neighbors, int64_t n_rows, int64_t width, int64_t n_support, int64_t hist_n,
+                               int32_t* hist, void* stream) {
+    GEOB_REQUIRE(n_rows > 0 && width > 0 && hist_n > 0, "neighbor_histogram: empty input");
+    neighbor_histogram_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const long long*)neighbors, (long long)n_rows, (int)width, (long long)n_support, (int)hist_n, hist);
+    GEOB_CHECK_LAUNCH();
+    count_launches(1);
     return 0;
 }
 

@@ -91,3 +91,28 @@ def registration_collate_fn_stack_mode(data_dicts, num_stages, voxel_size, searc
         collated['lengths'] = lengths
     collated['batch_size'] = batch_size
     return collated
+
+
+def calibrate_neighbors_stack_mode(dataset, collate_fn, num_stages, voxel_size, search_radius, keep_ratio=0.8, sample_threshold=2000):
+    """reference ``utils/data.py:190-217``: neighbour limits = the keep_ratio quantile of the neighbourhood sizes per stage.
+    The collate runs on the GPU at the histogram width and the row counts are histogrammed on the device
+    (`geob200_neighbor_histogram`); only the (num_stages, hist_n) table comes back, once per sample, for the early exit."""
+    from .. import _lib as L
+    hist_n = int(np.ceil(4 / 3 * np.pi * (search_radius / voxel_size + 1) ** 3))
+    max_neighbor_limits = [hist_n] * num_stages
+    hists = None
+    lib = L.lib()
+    for i in range(len(dataset)):
+        data_dict = collate_fn([dataset[i]], num_stages, voxel_size, search_radius, max_neighbor_limits, precompute_data=True)
+        if hists is None:
+            hists = torch.zeros((num_stages, hist_n), dtype=torch.int32, device=data_dict['neighbors'][0].device)
+        for s, neighbors in enumerate(data_dict['neighbors']):
+            # support = query cloud of the same stage: the sentinel is the number of rows (data.py:205)
+            L.check(lib.geob200_neighbor_histogram(neighbors.data_ptr(), neighbors.shape[0], neighbors.shape[1], neighbors.shape[0],
+                                                   hist_n, hists[s].data_ptr(), L.stream_ptr()), 'neighbor_histogram')
+        if int(hists.sum(dim=1).min().item()) > sample_threshold:
+            break
+    neighbor_hists = hists.cpu().numpy()
+    cum_sum = np.cumsum(neighbor_hists.T, axis=0)
+    neighbor_limits = np.sum(cum_sum < (keep_ratio * cum_sum[hist_n - 1, :]), axis=0)
+    return neighbor_limits

@@ -46,6 +46,11 @@ int geob200_radius_search(const float* q_points, int64_t n_query, const float* s
                           int64_t width, int64_t* out, int32_t* counts, int32_t* max_count, void* workspace,
                           size_t workspace_bytes, void* stream);
 
+/* calibrate_neighbors_stack_mode (utils/data.py:190-217): hist[c] += #rows of a neighbour table (n_rows, width) with
+ * exactly c entries < n_support, for c < hist_n (int32 device histogram, accumulated across calls). */
+int geob200_neighbor_histogram(const int64_t* neighbors, int64_t n_rows, int64_t width, int64_t n_support, int64_t hist_n,
+                               int32_t* hist, void* stream);
+
 /* ---- KPConv-FPN backbone --------------------------------------------------------------------------------- */
 
 /* KPConv.forward (reference geotransformer/modules/kpconv/kpconv.py:79-122), fused gather -> kernel-point

@@ -85,6 +85,23 @@ def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, 
             'upsampling': upsampling}
 
 
+def calibrate_neighbors(pairs, cfg, keep_ratio=0.8, sample_threshold=2000, impl=collate_oracle):
+    """utils/data.py:190-217 calibrate_neighbors_stack_mode over a list of raw pairs: the keep_ratio quantile of the
+    neighbourhood sizes per stage, histogrammed up to ceil(4/3 pi (r/voxel + 1)^3)."""
+    b = cfg.backbone
+    hist_n = int(np.ceil(4 / 3 * np.pi * (b.init_radius / b.init_voxel_size + 1) ** 3))
+    hists = np.zeros((b.num_stages, hist_n), dtype=np.int64)
+    for pair in pairs:
+        data = collate_pair(pair, cfg, [hist_n] * b.num_stages, impl=impl)
+        for s, nbr in enumerate(data['neighbors']):
+            counts = (nbr.numpy() < nbr.shape[0]).sum(axis=1)
+            hists[s] += np.bincount(counts, minlength=hist_n)[:hist_n]
+        if hists.sum(axis=1).min() > sample_threshold:
+            break
+    cum = np.cumsum(hists.T, axis=0)
+    return np.sum(cum < keep_ratio * cum[hist_n - 1, :], axis=0)
+
+
 def canonical_neighbors(q_points, s_points, table):
     """Re-orders every row of a neighbour table by (fp32 reference distance, index): removes the implementation-defined
     order inside exact-distance tie groups (radius_neighbors_cpu.cpp sorts with an unstable std::sort)."""

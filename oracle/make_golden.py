@@ -153,7 +153,27 @@ def run(workload):
     print(f'[{workload}] wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)')
 
 
+def run_calibration():
+    """neighbour-limit calibration (utils/data.py:190-217) of the real reference over three demo pairs"""
+    ref_harness.load_experiment('3dmatch')
+    from geotransformer.utils.data import calibrate_neighbors_stack_mode, registration_collate_fn_stack_mode
+    cfg = make_cfg('3dmatch')
+    b = cfg.backbone
+    keys = ('ref_points', 'src_points', 'ref_feats', 'src_feats', 'transform')
+    pairs = [{k: make_pair('demo2k', i)[k] for k in keys} for i in range(3)]
+    g = {}
+    for thr in (2000, 150):
+        want = calibrate_neighbors_stack_mode(pairs, registration_collate_fn_stack_mode, b.num_stages, b.init_voxel_size, b.init_radius,
+                                              sample_threshold=thr)
+        got = geo_oracle.calibrate_neighbors(pairs, cfg, sample_threshold=thr)
+        got_ref_ext = geo_oracle.calibrate_neighbors(pairs, cfg, sample_threshold=thr, impl=ref_ext)
+        assert np.array_equal(want, got) and np.array_equal(want, got_ref_ext), (want, got, got_ref_ext)
+        g[f'limits_threshold_{thr}'] = np.asarray(want)
+        print(f'[calibration] sample_threshold {thr}: limits {want.tolist()} (oracle equal)')
+    np.savez_compressed(os.path.join(GOLD, 'calibration.npz'), **g)
+
+
 if __name__ == '__main__':
     assert ref_harness.available(), 'needs /root/reference'
-    for w in (sys.argv[1:] or ['demo2k', 'modelnet717']):
-        run(w)
+    for w in (sys.argv[1:] or ['demo2k', 'modelnet717', 'calibration']):
+        run_calibration() if w == 'calibration' else run(w)

@@ -121,3 +121,17 @@ def test_cpu_tensor_drop_in_roundtrip():
     sp, sl = ext.grid_subsampling(pts, lens, 0.1)
     op, ol = co.grid_subsampling(pts, lens, 0.1)
     assert not sp.is_cuda and torch.equal(sp, op) and torch.equal(sl, ol)
+
+
+def test_calibrate_neighbors_matches_reference(golden, models):
+    """GPU collate at the histogram width + device histogram == the limits computed by the real reference (fixture)"""
+    from geotransformer_b200.utils.data import calibrate_neighbors_stack_mode, registration_collate_fn_stack_mode
+    cfg, _, _ = models('3dmatch')
+    b = cfg.backbone
+    keys = ('ref_points', 'src_points', 'ref_feats', 'src_feats', 'transform')
+    pairs = [{k: make_pair('demo2k', i)[k] for k in keys} for i in range(3)]
+    gold = golden('calibration')
+    for thr in (2000, 150):
+        got = calibrate_neighbors_stack_mode(pairs, registration_collate_fn_stack_mode, b.num_stages, b.init_voxel_size, b.init_radius,
+                                             sample_threshold=thr)
+        assert np.array_equal(np.asarray(got), gold[f'limits_threshold_{thr}']), (got, gold[f'limits_threshold_{thr}'])

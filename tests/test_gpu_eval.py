@@ -171,3 +171,29 @@ def test_engine_streams_and_metrics(models):
             tol = 2e-3 if name == 'RRE' else 1e-5
             assert abs(x['metrics'][name] - float(o[name])) <= tol * max(1.0, abs(float(o[name]))), (i, name)
     assert len({tuple(x['estimated_transform'].flatten().tolist()) for x in a}) == 5        # five different pairs
+
+
+def test_tester_loop_writes_reference_npz(models, tmp_path):
+    """SingleTester-style loop: one <scene>/<ref>_<src>.npz per pair with the arrays test.py:73-92 writes, metrics summary"""
+    from geotransformer_b200.tester import RegistrationTester, NPZ_OUTPUT_KEYS
+    cfg, sd, model = models('3dmatch')
+    model = model.cuda().eval()
+    dataset = []
+    for i in range(3):
+        p = make_pair('demo2k', i)
+        d = {k: p[k] for k in ('ref_points', 'src_points', 'ref_feats', 'src_feats', 'transform')}
+        d.update(scene_name='synthetic_scene', ref_frame=2 * i, src_frame=2 * i + 1, overlap=0.5)
+        dataset.append(d)
+    lines = []
+    tester = RegistrationTester(cfg, model, [38, 36, 36, 38], output_dir=str(tmp_path), num_streams=2, chunk=2)
+    summary, per_pair = tester.run(dataset, log=lines.append)
+    tester.close()
+    assert len(per_pair) == 3 and len(lines) == 3 and set(summary) == {'PIR', 'IR', 'RRE', 'RTE', 'RMSE', 'RR'}
+    for i, entry in enumerate(per_pair):
+        z = np.load(entry['file'])
+        assert entry['file'].endswith(f'synthetic_scene/{2 * i}_{2 * i + 1}.npz')
+        assert set(z.files) == set(NPZ_OUTPUT_KEYS) | {'transform', 'overlap'}
+        assert np.array_equal(z['estimated_transform'], entry['estimated_transform'].numpy())
+        assert np.array_equal(z['transform'], dataset[i]['transform'])
+        assert z['gt_node_corr_indices'].shape[1] == 2 and z['ref_corr_points'].shape[0] == entry['num_corr']
+    assert abs(summary['RRE'] - np.mean([p['metrics']['RRE'] for p in per_pair])) < 1e-6

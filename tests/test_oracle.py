@@ -82,6 +82,16 @@ def test_forward_restatement_matches_reference_fixture(golden, models):
         assert abs(float(metrics[name]) - v) < (1e-3 if name == 'RRE' else 1e-5), name
 
 
+def test_calibration_restatement_matches_reference_fixture(golden, models):
+    """calibrate_neighbors_stack_mode (utils/data.py:190-217): restatement vs the limits the real reference computed"""
+    cfg, _, _ = models('3dmatch')
+    keys = ('ref_points', 'src_points', 'ref_feats', 'src_feats', 'transform')
+    pairs = [{k: make_pair('demo2k', i)[k] for k in keys} for i in range(3)]
+    gold = golden('calibration')
+    for thr in (2000, 150):
+        assert np.array_equal(G.calibrate_neighbors(pairs, cfg, sample_threshold=thr), gold[f'limits_threshold_{thr}'])
+
+
 def test_sinkhorn_marginals_property():
     g = torch.Generator().manual_seed(1)
     s = torch.randn(3, 20, 20, generator=g)
