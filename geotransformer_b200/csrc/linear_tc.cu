@@ -7,10 +7,10 @@
 // One CTA per 128 x BN output tile (BN = min(N,128)), K in chunks of 32 floats (one 128-byte swizzle row):
 //   warp 0      TMA producer : cp.async.bulk.tensor.2d (UTMALDG) of the raw X tile (128 x 32) and W tile (BN x 32) through
 //                              SWIZZLE_128B tensor maps; out-of-bounds rows/columns are zero-filled by the TMA unit
-//   warps 1-4   splitters    : in-place hi = tf32_rn(x), lo = x - hi into a second buffer (generic proxy ->
+//   warps 1-8   splitters    : in-place hi = tf32_rn(x), lo = x - hi into a second buffer (generic proxy ->
 //                              fence.proxy.async), so the MMA sees exact tf32 operands
-//   warp 5      MMA issuer   : tcgen05.mma.cta_group::1.kind::tf32 M128 N{BN} K8, 3 per K-step; tcgen05.commit frees the stage
-//   warps 6-9   epilogue     : tcgen05.ld 32x32b, + bias, ReLU, direct row-segment stores (each thread owns one output row);
+//   warp 9      MMA issuer   : tcgen05.mma.cta_group::1.kind::tf32 M128 N{BN} K8, 3 per K-step; tcgen05.commit frees the stage
+//   warps 10-13 epilogue     : tcgen05.ld 32x32b, + bias, ReLU, direct row-segment stores (each thread owns one output row);
 //                              optionally the GroupNorm statistics of the output (per-tile column sums through a transposing
 //                              warp butterfly, written as per-tile partials in double)
 #include <cuda.h>
@@ -30,7 +30,10 @@ constexpr int TILE_A = BM * 128;       // 16 KB
 constexpr int TILE_B = 128 * 128;      // 16 KB (BN <= 128 rows)
 constexpr int STAGE = 2 * TILE_A + 2 * TILE_B;   // raw/hi + lo for both operands = 64 KB
 constexpr int NSTAGE = 3;
-constexpr int NTHREADS = 320;
+constexpr int NSPLIT_WARPS = 8;                       // warps 1..8
+constexpr int MMA_WARP = 1 + NSPLIT_WARPS;            // warp 9
+constexpr int EPI_WARP0 = MMA_WARP + 1;               // warps 10..13 (warp & 3 covers the four TMEM lane quarters)
+constexpr int NTHREADS = (EPI_WARP0 + 4) * 32;        // 448
 // 193.25 KB + the 1 KB the system reserves per CTA fits the 196 KB shared-memory carve-out; anything larger forces the 228 KB
 // configuration and costs ~8 us per launch in carve-out switches against the neighbouring kernels (measured)
 constexpr int SMEM = NSTAGE * STAGE + 1024 + 256;
@@ -86,7 +89,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const __grid_con
                                                                 const __grid_constant__ CUtensorMap map_w,
                                                                 const float* __restrict__ bias, const float* __restrict__ row_scale,
                                                                 float* __restrict__ Y, int ldy, int M, int N, int K, int BN, int relu,
-                                                                GnFuse gn) {
+                                                                GnFuse gn, float* __restrict__ splitk_out, int chunks_per_split) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ float bias_s[128];
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -100,15 +103,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const __grid_con
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int nk = (K + KC - 1) / KC;
+    // split-K: CTA z accumulates K-chunks [kc0, kc1) and stores its raw partial tile; splitk_reduce_kernel finishes the job
+    const int kc0 = blockIdx.z * chunks_per_split, kc1 = min(nk, kc0 + chunks_per_split);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&split_full[s], 4); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&split_full[s], NSPLIT_WARPS); mbar_init(&empty[s], 1); }
         mbar_init(acc_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
     }
-    if (warp == 5) {
+    if (warp == MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -121,7 +126,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const __grid_con
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
-            for (int kc = 0; kc < nk; ++kc) {
+            for (int kc = kc0; kc < kc1; ++kc) {
                 mbar_wait(&empty[s], ph ^ 1u);
                 unsigned char* st = smem + s * STAGE;
                 mbar_arrive_expect_tx(&raw_full[s], (uint32_t)(TILE_A + BN * 128));
@@ -130,38 +135,54 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const __grid_con
                 if (++s == NSTAGE) { s = 0; ph ^= 1u; }
             }
         }
-    } else if (warp <= 4) {
-        const int t = threadIdx.x - 32;              // 0..127
+    } else if (warp <= NSPLIT_WARPS) {
+        constexpr int NT = NSPLIT_WARPS * 32;
+        const int t = threadIdx.x - 32;              // 0..NT-1
         int s = 0;
         uint32_t ph = 0;
-        for (int kc = 0; kc < nk; ++kc) {
+        const int nvec_a = TILE_A / 16, nvec_b = BN * 128 / 16;
+        const int nvec = nvec_a + nvec_b;            // multiple of NT (BN is a multiple of 16)
+        for (int kc = kc0; kc < kc1; ++kc) {
             mbar_wait(&raw_full[s], ph);
             unsigned char* st = smem + s * STAGE;
-            // element-wise, so the swizzled positions are irrelevant: same offset in the hi and lo buffers
-            const int nvec_a = TILE_A / 16, nvec_b = BN * 128 / 16;
-            for (int v = t; v < nvec_a + nvec_b; v += 128) {
-                unsigned char* p = (v < nvec_a) ? (st + v * 16) : (st + 2 * TILE_A + (v - nvec_a) * 16);
-                unsigned char* pl = p + ((v < nvec_a) ? TILE_A : TILE_B);
-                float4 x = *reinterpret_cast<float4*>(p);
-                float4 hi, lo;
-                hi.x = tf32_rn(x.x); lo.x = x.x - hi.x;     // round-to-nearest split: |lo| <= 2^-12 |x|, unbiased
-                hi.y = tf32_rn(x.y); lo.y = x.y - hi.y;
-                hi.z = tf32_rn(x.z); lo.z = x.z - hi.z;
-                hi.w = tf32_rn(x.w); lo.w = x.w - hi.w;
-                *reinterpret_cast<float4*>(p) = hi;
-                *reinterpret_cast<float4*>(pl) = lo;
+            // element-wise, so the swizzled positions are irrelevant: same offset in the hi and lo buffers.
+            // Two 16-byte vectors per thread and iteration: their shared-memory round trips overlap.
+            for (int v0 = t; v0 < nvec; v0 += 2 * NT) {
+                const int v1 = v0 + NT;
+                unsigned char* p0 = (v0 < nvec_a) ? (st + v0 * 16) : (st + 2 * TILE_A + (v0 - nvec_a) * 16);
+                unsigned char* l0 = p0 + ((v0 < nvec_a) ? TILE_A : TILE_B);
+                const bool two = v1 < nvec;
+                unsigned char* p1 = !two ? p0 : (v1 < nvec_a) ? (st + v1 * 16) : (st + 2 * TILE_A + (v1 - nvec_a) * 16);
+                unsigned char* l1 = p1 + ((v1 < nvec_a) ? TILE_A : TILE_B);
+                const float4 x0 = *reinterpret_cast<float4*>(p0);
+                const float4 x1 = *reinterpret_cast<float4*>(p1);
+                float4 h0, q0, h1, q1;
+                h0.x = tf32_rn(x0.x); q0.x = x0.x - h0.x;     // round-to-nearest split: |lo| <= 2^-12 |x|, unbiased
+                h0.y = tf32_rn(x0.y); q0.y = x0.y - h0.y;
+                h0.z = tf32_rn(x0.z); q0.z = x0.z - h0.z;
+                h0.w = tf32_rn(x0.w); q0.w = x0.w - h0.w;
+                h1.x = tf32_rn(x1.x); q1.x = x1.x - h1.x;
+                h1.y = tf32_rn(x1.y); q1.y = x1.y - h1.y;
+                h1.z = tf32_rn(x1.z); q1.z = x1.z - h1.z;
+                h1.w = tf32_rn(x1.w); q1.w = x1.w - h1.w;
+                *reinterpret_cast<float4*>(p0) = h0;
+                *reinterpret_cast<float4*>(l0) = q0;
+                if (two) {
+                    *reinterpret_cast<float4*>(p1) = h1;
+                    *reinterpret_cast<float4*>(l1) = q1;
+                }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&split_full[s]);
             if (++s == NSTAGE) { s = 0; ph ^= 1u; }
         }
-    } else if (warp == 5) {
+    } else if (warp == MMA_WARP) {
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             int s = 0;
             uint32_t ph = 0;
-            for (int kc = 0; kc < nk; ++kc) {
+            for (int kc = kc0; kc < kc1; ++kc) {
                 mbar_wait(&split_full[s], ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t st = smem_u32(smem + s * STAGE);
@@ -173,7 +194,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const __grid_con
                     // main products and the (2^-11 smaller) correction products go to separate accumulators (columns
                     // [0,128) and [128,256)): the fp32 accumulation in the tensor core truncates, so keeping the number of
                     // additions into the main accumulator at K/8 instead of 3K/8 cuts the systematic error by 3x
-                    const uint32_t first = (kc == 0 && kk == 0) ? 0u : 1u;
+                    const uint32_t first = (kc == kc0 && kk == 0) ? 0u : 1u;
                     umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, first);
                     umma_tf32(tmem_base + 128, a_hi + adv, b_lo + adv, idesc, first);
                     umma_tf32(tmem_base + 128, a_lo + adv, b_hi + adv, idesc, 1u);
@@ -188,7 +209,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const __grid_con
         // the tile's bias row goes through shared memory once (loaded while the main loop runs): per-element global loads in
         // the epilogue are a chain of 32 dependent L2 round trips per chunk (~8 us per tile, measured)
         {
-            const int et = threadIdx.x - 6 * 32;
+            const int et = threadIdx.x - EPI_WARP0 * 32;
             bias_s[et] = (bias != nullptr && n0 + et < N) ? __ldg(bias + n0 + et) : 0.f;
             asm volatile("bar.sync 1, 128;" ::: "memory");
         }
@@ -218,8 +239,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const __grid_con
                   "=r"(w2[25]), "=r"(w2[26]), "=r"(w2[27]), "=r"(w2[28]), "=r"(w2[29]), "=r"(w2[30]), "=r"(w2[31])
                 : "r"(taddr + 128));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            const float rs = (row_scale != nullptr && m < M) ? row_scale[m] : 1.0f;   // KPConv: 1 / neighbour count
             const int nvalid = min(32, N - (n0 + cc));
+            if (splitk_out != nullptr) {              // raw partial sums of this K-slice (N is a multiple of 16: float4-aligned)
+                if (m < M) {
+                    float* pr = splitk_out + ((long long)blockIdx.z * M + m) * N + n0 + cc;
+#pragma unroll
+                    for (int c = 0; c < 32; c += 4)
+                        if (c < nvalid)
+                            *reinterpret_cast<float4*>(pr + c) =
+                                make_float4(__uint_as_float(v[c]) + __uint_as_float(w2[c]), __uint_as_float(v[c + 1]) + __uint_as_float(w2[c + 1]),
+                                            __uint_as_float(v[c + 2]) + __uint_as_float(w2[c + 2]), __uint_as_float(v[c + 3]) + __uint_as_float(w2[c + 3]));
+                }
+                continue;
+            }
+            const float rs = (row_scale != nullptr && m < M) ? row_scale[m] : 1.0f;   // KPConv: 1 / neighbour count
             float o[32];
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
@@ -256,10 +289,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const __grid_con
                 if ((lane & (gn.slot_width - 1)) == 0) gn_sm[q * 128 + (cc + lane) / gn.slot_width] = make_float2(a, b2);
             }
         }
-        if (gn.groups > 0) {
+        if (gn.groups > 0 && splitk_out == nullptr) {
             // 4 epilogue warps -> per-tile partial in a fixed order; gn_finalize_kernel (kpconv.cu) folds the tiles afterwards
             // (no fence / ticket here: the CTA must not wait for its output stores to drain)
-            const int et = threadIdx.x - 6 * 32;
+            const int et = threadIdx.x - EPI_WARP0 * 32;
             const int slots_tile = BN / gn.slot_width, slots_total = N / gn.slot_width;
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (et < slots_tile) {
@@ -272,10 +305,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const __grid_con
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 5) {
+    if (warp == MMA_WARP) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
     }
+}
+
+// y[m][n] = (sum_z P[z][m][n]) * row_scale[m] + bias[n] (+ ReLU): the splits are added in a fixed order
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ P, int splits, long long MN, int N,
+                                                            const float* __restrict__ bias, const float* __restrict__ row_scale,
+                                                            float* __restrict__ Y, int ldy, int relu) {
+    const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i4 >= MN) return;
+    float4 a = *reinterpret_cast<const float4*>(P + i4);
+    for (int z = 1; z < splits; ++z) {
+        const float4 b = *reinterpret_cast<const float4*>(P + (long long)z * MN + i4);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    const long long m = i4 / N;
+    const int n = (int)(i4 % N);
+    const float rs = row_scale != nullptr ? row_scale[m] : 1.0f;
+    float o[4] = {a.x * rs, a.y * rs, a.z * rs, a.w * rs};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        if (bias != nullptr) o[u] += bias[n + u];
+        if (relu) o[u] = fmaxf(o[u], 0.f);
+    }
+    float* y = Y + m * ldy + n;
+    if ((reinterpret_cast<uintptr_t>(y) & 15) == 0) *reinterpret_cast<float4*>(y) = make_float4(o[0], o[1], o[2], o[3]);
+    else { y[0] = o[0]; y[1] = o[1]; y[2] = o[2]; y[3] = o[3]; }
 }
 
 // cuTensorMapEncodeTiled is fetched through the runtime (cudaGetDriverEntryPoint) so that libgeob200.so does not link
@@ -314,6 +372,31 @@ struct ProfRec { cudaEvent_t a, b; long long m, n, k; };
 static std::vector<ProfRec> g_prof;
 static std::mutex g_prof_mu;
 static bool g_prof_on = false;
+static bool g_splitk_on = true;
+
+// ---- split-K scratch: one grow-only buffer per stream (like a BLAS workspace; freed with the process) ---------------------
+struct SplitWs { void* ptr; size_t bytes; };
+static std::vector<std::pair<cudaStream_t, SplitWs>> g_split_ws;
+static std::mutex g_split_mu;
+static float* splitk_scratch(cudaStream_t st, size_t bytes) {
+    std::lock_guard<std::mutex> lk(g_split_mu);
+    for (auto& e : g_split_ws)
+        if (e.first == st) {
+            if (e.second.bytes >= bytes) return (float*)e.second.ptr;
+            // stream-ordered free: earlier kernels on this stream may still read the old buffer
+            cudaFreeAsync(e.second.ptr, st);
+            e.second = {nullptr, 0};
+            if (cudaMallocAsync(&e.second.ptr, bytes * 2, st) != cudaSuccess) return nullptr;
+            e.second.bytes = bytes * 2;
+            return (float*)e.second.ptr;
+        }
+    SplitWs w{nullptr, 0};
+    const size_t cap = bytes * 2 > (16u << 20) ? bytes * 2 : (16u << 20);
+    if (cudaMallocAsync(&w.ptr, cap, st) != cudaSuccess) return nullptr;
+    w.bytes = cap;
+    g_split_ws.push_back({st, w});
+    return (float*)w.ptr;
+}
 
 // returns 1 when the shape/alignment is not handled by the tensor-core path (caller falls back to the fp32 kernel)
 int linear_tc(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, const float* row_scale, float* y, int64_t ldy,
@@ -339,6 +422,28 @@ int linear_tc(const float* x, int64_t ldx, const float* w, int64_t ldw, const fl
         if (g.groups <= 0 || n % g.groups != 0 || (cpg < 32 ? (32 % cpg) != 0 : (cpg % 32) != 0 || (BN % cpg) != 0) || relu) return 1;
         g.slot_width = (int)(cpg < 32 ? cpg : 32);
     }
+    // split-K: a deep K loop on a handful of tiles leaves most SMs idle and is pure latency (1.4 us per 32-wide chunk): give
+    // every K-slice of >= 8 chunks its own CTA when the grid would cover less than half of the GPU
+    const int nk = (int)((k + ltc::KC - 1) / ltc::KC);
+    const int tiles = (int)(grid.x * grid.y);
+    int splits = 1;
+    if (g_splitk_on && tiles * 2 <= num_sms() && nk >= 16) {
+        splits = nk / 8;
+        if (splits > num_sms() / tiles) splits = num_sms() / tiles;
+        if (splits > 16) splits = 16;
+        if (splits < 2) splits = 1;
+    }
+    // the epilogue statistics need the complete sums: with split-K the caller runs the stand-alone GroupNorm statistics instead
+    if (gn != nullptr && splits > 1) return 1;
+    int cps = nk;
+    float* part = nullptr;
+    if (splits > 1) {
+        cps = (nk + splits - 1) / splits;
+        splits = (nk + cps - 1) / cps;
+        part = splitk_scratch(st, (size_t)splits * (size_t)m * (size_t)n * sizeof(float));
+        if (part == nullptr) { splits = 1; cps = nk; }
+    }
+    grid.z = (unsigned)splits;
     ProfRec rec{};
     const bool prof = g_prof_on;
     if (prof) {
@@ -347,7 +452,13 @@ int linear_tc(const float* x, int64_t ldx, const float* w, int64_t ldw, const fl
         rec.m = m; rec.n = n; rec.k = k;
         cudaEventRecord(rec.a, st);
     }
-    ltc::linear_tc_kernel<<<grid, ltc::NTHREADS, ltc::SMEM, st>>>(mx, mw, bias, row_scale, y, (int)ldy, (int)m, (int)n, (int)k, BN, relu, g);
+    ltc::linear_tc_kernel<<<grid, ltc::NTHREADS, ltc::SMEM, st>>>(mx, mw, bias, row_scale, y, (int)ldy, (int)m, (int)n, (int)k, BN, relu, g,
+                                                                  part, cps);
+    if (part != nullptr) {
+        const long long mn = (long long)m * n;
+        ltc::splitk_reduce_kernel<<<(unsigned)((mn / 4 + 255) / 256), 256, 0, st>>>(part, splits, mn, (int)n, bias, row_scale, y, (int)ldy, relu);
+        count_launches(1);
+    }
     if (prof) {
         cudaEventRecord(rec.b, st);
         std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -361,6 +472,11 @@ int linear_tc(const float* x, int64_t ldx, const float* w, int64_t ldw, const fl
 }  // namespace geob200
 
 extern "C" {
+
+int geob200_set_split_k(int on) {
+    geob200::g_splitk_on = on != 0;
+    return 0;
+}
 
 // Profiling aid for bench.py: while enabled every tensor-core GEMM launch is bracketed by CUDA events on its stream.
 int geob200_linear_profile_enable(int on) {

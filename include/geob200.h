@@ -225,6 +225,8 @@ int geob200_evaluate(const int64_t* gt_node_corr_indices, const float* gt_node_c
 /* Profiling aid (bench.py roofline): while enabled, every tcgen05 GEMM launch (nn.Linear and the KPConv contraction) is
  * bracketed by CUDA events on its stream; _read synchronises them and returns the count, shapes[3i..] = (m, n, k), ms[i]. */
 int geob200_linear_profile_enable(int on);
+/* split-K for deep-K GEMMs on few tiles (default on); off = every tile runs its whole K loop in one CTA */
+int geob200_set_split_k(int on);
 int64_t geob200_linear_profile_read(int64_t capacity, int64_t* shapes, float* ms);
 
 /* ---- native stage drivers (native.cu) ------------------------------------------------------------------------

@@ -106,6 +106,33 @@ def test_linear_tensor_core_3xtf32_matches_fp32(m, k, n):
     close(got_tc_relu, F.relu(F.linear(x.double(), w.double())).float(), tol_tc, 'linear 3xTF32 relu')
 
 
+@pytest.mark.parametrize('m,k,n', [(640, 3840, 256), (130, 1920, 128), (3400, 1920, 128), (640, 1024, 256), (64, 512, 32)])
+def test_linear_split_k(m, k, n):
+    """deep-K GEMMs on few tiles run one CTA per K-slice + a fixed-order reduction: same result as the single-CTA K loop (to
+    accumulation-order noise), deterministic, bias / ReLU / strided output applied by the reduction"""
+    from geotransformer_b200 import _lib
+    g = torch.Generator().manual_seed(m + k)
+    x, w, b = torch.randn(m, k, generator=g), torch.randn(n, k, generator=g) / math.sqrt(k), torch.randn(n, generator=g)
+    want = F.linear(x.double(), w.double(), b.double()).float()
+    lib = _lib.lib()
+    cx, cw, cb = x.cuda(), w.cuda(), b.cuda()
+    try:
+        lib.geob200_set_split_k(0)
+        one = GF.linear(cx, cw, cb)
+        lib.geob200_set_split_k(1)
+        split = GF.linear(cx, cw, cb)
+        split2 = GF.linear(cx, cw, cb)
+        out = torch.full((m, 2 * n), 3.0, device='cuda')
+        GF.linear(cx, cw, cb, relu=True, out=out[:, n:])
+    finally:
+        lib.geob200_set_split_k(1)
+    close(one, want, 2.5e-5, 'single-CTA K loop')
+    close(split, want, 2.5e-5, 'split-K')
+    assert torch.equal(split, split2)
+    close(out[:, n:], F.relu(want), 2.5e-5, 'split-K relu, strided out')
+    assert bool((out[:, :n] == 3.0).all())
+
+
 def test_linear_column_slice_input():
     g = torch.Generator().manual_seed(1)
     x, w = torch.randn(50, 256, generator=g), torch.randn(64, 64, generator=g)
