@@ -163,7 +163,19 @@ def main():
     dev = torch.device('cuda', local)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group('nccl', device_id=dev)
+        # NCCL may print its version banner on stdout (NCCL_DEBUG=VERSION): keep stdout for the ONE JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     from geotransformer_b200 import functional as GF, _lib
     from geotransformer_b200.config import make_cfg
@@ -210,6 +222,8 @@ def main():
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
+        if os.environ.get('GEOB_BENCH_DEBUG'):
+            print(f'[rank {rank}] {n} steps x {S} pairs: {ms:.1f} ms', file=sys.stderr, flush=True)
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
