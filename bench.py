@@ -203,7 +203,7 @@ def main():
     h2d_bytes = sum(v.numel() * v.element_size() for v in pinned[0].values()) * S
     from geotransformer_b200.loss import Evaluator
     evaluator = Evaluator(cfg)          # PIR/IR/RRE/RTE/RMSE/RR on the device, inside the timed region (one launch per pair)
-    engine = RegistrationEngine(model, cfg, limits, num_streams=S, device=dev, evaluator=evaluator)
+    engine = RegistrationEngine(model, cfg, limits, num_streams=S, device=dev, evaluator=evaluator, pin_cpu=True)
 
     def barrier():
         if world > 1:
@@ -341,6 +341,7 @@ def main():
         'config': {'workload': args.workload, 'pairs_per_step_per_gpu': S, 'streams': S, 'points_per_cloud': int(pairs[0]['ref_points'].shape[0]),
                    'superpoints_per_cloud': int(np.mean(n_c)) if n_c else None, 'sinkhorn_iterations': cfg.model.num_sinkhorn_iterations,
                    'parallelism': f'pairs sharded over {world} GPU(s), one all_gather of metric rows',
+                   'host_threads_pinned_to_gpu_numa_node': bool(engine.pinned_cpu),
                    'l2': 'a different pair every step; per-pair working set (~0.5 GB incl. 2x75 MB embeddings) exceeds the 126 MB L2',
                    'weights': 'random init (synthetic_state_dict seed 7351)'},
         'e2e': {'value': total_pairs / (ms_e2e * 1e-3), 'unit': 'pairs/s', 'ms_per_step': ms_e2e / K,

@@ -17,9 +17,31 @@ from . import _lib
 from .utils.data import registration_collate_fn_stack_mode
 
 
+def pin_host_threads_to_gpu(device):
+    """Restrict the calling thread (and the threads it creates afterwards) to the CPUs NVML reports as local to `device`
+    (same NUMA node / PCIe root).  On a two-socket host a launch thread running on the remote socket costs tens of percent of
+    throughput.  Best effort: returns False when NVML or the affinity call is unavailable."""
+    try:
+        import os
+        import pynvml
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(device).uuid)
+        handle = pynvml.nvmlDeviceGetHandleByUUID(('GPU-' + uuid) if not uuid.startswith('GPU-') else uuid)
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return False
+        os.sched_setaffinity(0, cpus)
+        return True
+    except Exception:
+        return False
+
+
 class RegistrationEngine:
-    def __init__(self, model, cfg, neighbor_limits, num_streams=4, device=None, native=True, evaluator=None):
-        """evaluator: optional geotransformer_b200.loss.Evaluator; its metrics (PIR, IR, RRE, RTE, RMSE, RR) are then computed
+    def __init__(self, model, cfg, neighbor_limits, num_streams=4, device=None, native=True, evaluator=None, pin_cpu=False):
+        """pin_cpu: bind the calling thread and the worker threads to the CPUs local to the GPU (pin_host_threads_to_gpu).
+        evaluator: optional geotransformer_b200.loss.Evaluator; its metrics (PIR, IR, RRE, RTE, RMSE, RR) are then computed
         on the device for every pair and travel back with the transform in the same D2H copy."""
         self.model, self.cfg, self.limits = model, cfg, neighbor_limits
         if native and not hasattr(model, '_native'):
@@ -27,6 +49,7 @@ class RegistrationEngine:
             enable_native(model)          # C++ stage drivers: same results, ~10x less host time per pair
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         self.num_streams = num_streams
+        self.pinned_cpu = pin_host_threads_to_gpu(self.device) if pin_cpu else False
         self.evaluator = evaluator
         self.stage_times = None          # set to {} to collect per-stage CUDA-event times (profiling; adds ~7 events per pair)
         self.streams = [torch.cuda.Stream(self.device) for _ in range(num_streams)]
