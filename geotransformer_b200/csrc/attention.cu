@@ -183,57 +183,69 @@ __global__ void __launch_bounds__(128) att_scores_kernel(const float* __restrict
     constexpr int D = C / H;
     constexpr int NV = ATS_G * H;                 // values reduced together: (key u, head h) -> v[u * H + h]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n = blockIdx.x;
-    const int m_begin = blockIdx.y * keys_per_cta;
-    const int m_end = min(M, m_begin + keys_per_cta);
     const bool has_e = (E != nullptr);
+    // persistent: work items = (query, chunk of keys_per_cta keys) in row-major order, a contiguous range per CTA (the grid is
+    // sized to the resident capacity, so there is no partial last wave; consecutive items mostly share the query registers)
+    const int chunks = (M + keys_per_cta - 1) / keys_per_cta;
+    const long long items = (long long)N * chunks;
+    const long long it0 = items * blockIdx.x / gridDim.x, it1 = items * (blockIdx.x + 1) / gridDim.x;
     float4 qv[J];
     float4 qpv[H][J];
     int hq[J];
 #pragma unroll
-    for (int j = 0; j < J; ++j) {
-        const int c = j * 128 + 4 * lane;
-        qv[j] = *reinterpret_cast<const float4*>(q + (long long)n * ldq + c);
-        hq[j] = c / D;
-#pragma unroll
-        for (int h = 0; h < H; ++h)
-            qpv[h][j] = has_e ? *reinterpret_cast<const float4*>(qp + ((long long)n * H + h) * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    const float* e_row = has_e ? E + (long long)n * M * C : nullptr;
-    for (int m0 = m_begin + warp * ATS_G; m0 < m_end; m0 += 4 * ATS_G) {
-        float4 kk[ATS_G][J], ee[ATS_G][J];
-#pragma unroll
-        for (int u = 0; u < ATS_G; ++u) {
-            const int m = min(m0 + u, M - 1);
+    for (int j = 0; j < J; ++j) hq[j] = (j * 128 + 4 * lane) / D;
+    int n_loaded = -1;
+    for (long long it = it0; it < it1; ++it) {
+        const int n = (int)(it / chunks);
+        const int m_begin = (int)(it % chunks) * keys_per_cta;
+        const int m_end = min(M, m_begin + keys_per_cta);
+        if (n != n_loaded) {
 #pragma unroll
             for (int j = 0; j < J; ++j) {
-                kk[u][j] = __ldg(reinterpret_cast<const float4*>(k + (long long)m * ldk + j * 128 + 4 * lane));
-                if (has_e) ee[u][j] = __ldcs(reinterpret_cast<const float4*>(e_row + (long long)m * C + j * 128 + 4 * lane));
+                const int c = j * 128 + 4 * lane;
+                qv[j] = *reinterpret_cast<const float4*>(q + (long long)n * ldq + c);
+#pragma unroll
+                for (int h = 0; h < H; ++h)
+                    qpv[h][j] = has_e ? *reinterpret_cast<const float4*>(qp + ((long long)n * H + h) * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+            n_loaded = n;
         }
-        float v[NV];
+        const float* e_row = has_e ? E + (long long)n * M * C : nullptr;
+        for (int m0 = m_begin + warp * ATS_G; m0 < m_end; m0 += 4 * ATS_G) {
+            float4 kk[ATS_G][J], ee[ATS_G][J];
 #pragma unroll
-        for (int u = 0; u < ATS_G; ++u) {
-#pragma unroll
-            for (int h = 0; h < H; ++h) {
-                float a = 0.f;
+            for (int u = 0; u < ATS_G; ++u) {
+                const int m = min(m0 + u, M - 1);
 #pragma unroll
                 for (int j = 0; j < J; ++j) {
-                    const float p = dot4(kk[u][j], qv[j], 0.f);
-                    a += (hq[j] == h) ? p : 0.f;
-                    if (has_e) a = dot4(ee[u][j], qpv[h][j], a);
+                    kk[u][j] = __ldg(reinterpret_cast<const float4*>(k + (long long)m * ldk + j * 128 + 4 * lane));
+                    if (has_e) ee[u][j] = __ldcs(reinterpret_cast<const float4*>(e_row + (long long)m * C + j * 128 + 4 * lane));
                 }
-                v[u * H + h] = a;
             }
-        }
-        warp_butterfly(v, lane);      // transposing reduction: lane l ends up with value index l >> (5 - log2 NV)
-        // NV = 2^b values: value index = the top b lane bits; one lane per value writes
-        constexpr int SH = (NV == 32) ? 0 : (NV == 16) ? 1 : (NV == 8) ? 2 : 3;
-        const int idx = lane >> SH;
-        const int u = idx / H, h = idx % H;
-        if ((lane & ((1 << SH) - 1)) == 0 && m0 + u < m_end) {
-            const float bias = has_e ? qb[(long long)n * H + h] : 0.f;
-            S[((long long)n * H + h) * M + m0 + u] = (v[0] + bias) / div;
+            float v[NV];
+#pragma unroll
+            for (int u = 0; u < ATS_G; ++u) {
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+                    float a = 0.f;
+#pragma unroll
+                    for (int j = 0; j < J; ++j) {
+                        const float p = dot4(kk[u][j], qv[j], 0.f);
+                        a += (hq[j] == h) ? p : 0.f;
+                        if (has_e) a = dot4(ee[u][j], qpv[h][j], a);
+                    }
+                    v[u * H + h] = a;
+                }
+            }
+            warp_butterfly(v, lane);      // transposing reduction: lane l ends up with value index l >> (5 - log2 NV)
+            // NV = 2^b values: value index = the top b lane bits; one lane per value writes
+            constexpr int SH = (NV == 32) ? 0 : (NV == 16) ? 1 : (NV == 8) ? 2 : 3;
+            const int idx = lane >> SH;
+            const int u = idx / H, h = idx % H;
+            if ((lane & ((1 << SH) - 1)) == 0 && m0 + u < m_end) {
+                const float bias = has_e ? qb[(long long)n * H + h] : 0.f;
+                S[((long long)n * H + h) * M + m0 + u] = (v[0] + bias) / div;
+            }
         }
     }
 }
@@ -318,13 +330,16 @@ __global__ void __launch_bounds__(256) att_softmax_pv_kernel(const float* __rest
 template <int H, int J>
 static int launch_streaming(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, const float* qp, const float* qb,
                             const float* E, int N, int M, float div, float* out, int ldo, float* S, cudaStream_t st) {
-    // enough CTAs to fill the GPU several times over, but at least 64 keys per CTA so that q / qp loads stay amortised
-    int chunks = (4 * num_sms() + N - 1) / N;
-    chunks = max(1, min(chunks, M / 64));
-    int kpc = (M + chunks - 1) / chunks;
-    kpc = (kpc + 4 * ATS_G - 1) / (4 * ATS_G) * (4 * ATS_G);
-    chunks = (M + kpc - 1) / kpc;
-    att_scores_kernel<H, J><<<dim3((unsigned)N, (unsigned)chunks), 128, 0, st>>>(q, ldq, k, ldk, qp, qb, E, N, M, kpc, div, S);
+    // work items of 32 keys (2 butterfly groups per warp); one CTA per resident slot (occupancy queried once per instantiation)
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, att_scores_kernel<H, J>, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    }
+    const int kpc = 8 * ATS_G;
+    const long long items = (long long)N * ((M + kpc - 1) / kpc);
+    long long grid = (long long)per_sm * num_sms();
+    if (grid > items) grid = items;
+    att_scores_kernel<H, J><<<(unsigned)grid, 128, 0, st>>>(q, ldq, k, ldk, qp, qb, E, N, M, kpc, div, S);
     const size_t smem = sizeof(float) * (ATT_R * H * (size_t)((M + 3) / 4 * 4) + 4 * ATT_R * 128 * J);     // scores + the 4 partial outputs
     static size_t smem_set = 0;
     if (smem > 48 * 1024 && smem > smem_set) {

@@ -98,6 +98,9 @@ __global__ void __launch_bounds__(256) row_positive_kernel(const float* __restri
 // rows are fetched eight at a time.  Also emits inv_count[m] = 1 / max(#neighbours with a positive feature sum, 1)
 // (kpconv.py:113-116).  Stage 2 is the 3xTF32 tcgen05 GEMM wf (M x 15 Cin) . W (15 Cin x Cout) with the per-row scale and the
 // bias applied in its epilogue (linear_tc.cu).
+// CPL = channels per lane: 2 when Cin is a multiple of 64 (every broadcast read of an influence row then feeds 30 FMAs instead
+// of 15; with 15 the kernel is bound by the shared-memory pipe, 4 LDS.128 per 15 FMAs)
+template <int CPL>
 __global__ void __launch_bounds__(256) kpconv_gather_kernel(const float* __restrict__ feats, const unsigned char* __restrict__ pos,
                                                             const float* __restrict__ q_pts, const float* __restrict__ s_pts,
                                                             const long long* __restrict__ nbr, int H, const float* __restrict__ kp,
@@ -113,10 +116,12 @@ __global__ void __launch_bounds__(256) kpconv_gather_kernel(const float* __restr
     if (m >= M) return;
     const float qx = q_pts[3ll * m], qy = q_pts[3ll * m + 1], qz = q_pts[3ll * m + 2];
     int npos = 0;
-    for (int c0 = 0; c0 < Cin; c0 += 32) {
-        float acc[KP];
+    for (int c0 = 0; c0 < Cin; c0 += 32 * CPL) {
+        float acc[CPL][KP];
 #pragma unroll
-        for (int k = 0; k < KP; ++k) acc[k] = 0.f;
+        for (int p = 0; p < CPL; ++p)
+#pragma unroll
+            for (int k = 0; k < KP; ++k) acc[p][k] = 0.f;
         for (int h0 = 0; h0 < H; h0 += 32) {
             const int h = h0 + lane;
             const long long idx = (h < H) ? nbr[(long long)m * H + h] : (long long)Ns;
@@ -138,9 +143,12 @@ __global__ void __launch_bounds__(256) kpconv_gather_kernel(const float* __restr
             __syncwarp();
             const int hn = min(32, H - h0);
             for (int hb = 0; hb < hn; hb += 8) {
-                float f[8];
+                float f[8][CPL];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) f[u] = __ldg(feats + (long long)sidx[warp][(hb + u) & 31] * Cin + c0 + lane);
+                for (int u = 0; u < 8; ++u)
+#pragma unroll
+                    for (int p = 0; p < CPL; ++p)
+                        f[u][p] = __ldg(feats + (long long)sidx[warp][(hb + u) & 31] * Cin + c0 + 32 * p + lane);
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     if (hb + u < hn) {
@@ -148,18 +156,35 @@ __global__ void __launch_bounds__(256) kpconv_gather_kernel(const float* __restr
                         const float4 a0 = iv[0], a1 = iv[1], a2 = iv[2], a3 = iv[3];
                         const float wv[16] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w, a3.x, a3.y, a3.z, a3.w};
 #pragma unroll
-                        for (int k = 0; k < KP; ++k) acc[k] = fmaf(wv[k], f[u], acc[k]);
+                        for (int p = 0; p < CPL; ++p)
+#pragma unroll
+                            for (int k = 0; k < KP; ++k) acc[p][k] = fmaf(wv[k], f[u][p], acc[p][k]);
                     }
                 }
             }
         }
-        float* wrow = wf + (long long)m * (KP * Cin) + c0 + lane;
 #pragma unroll
-        for (int k = 0; k < KP; ++k) wrow[(long long)k * Cin] = acc[k];
+        for (int p = 0; p < CPL; ++p) {
+            float* wrow = wf + (long long)m * (KP * Cin) + c0 + 32 * p + lane;
+#pragma unroll
+            for (int k = 0; k < KP; ++k) wrow[(long long)k * Cin] = acc[p][k];
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) npos += __shfl_xor_sync(0xffffffffu, npos, o);
     if (lane == 0) inv_count[m] = 1.0f / (float)max(npos, 1);
+}
+
+static void launch_kpconv_gather(const float* s_feats, const unsigned char* pos, const float* q_points, const float* s_points,
+                                 const long long* neighbors, int n_neighbors, const float* kernel_points, float sigma, int n_support,
+                                 int n_query, int c_in, float* wf, float* inv_count, cudaStream_t st) {
+    const unsigned grid = (unsigned)((n_query + 7) / 8);
+    if (c_in % 64 == 0)
+        kpconv_gather_kernel<2><<<grid, 256, 0, st>>>(s_feats, pos, q_points, s_points, neighbors, n_neighbors, kernel_points, sigma,
+                                                     n_support, n_query, c_in, wf, inv_count);
+    else
+        kpconv_gather_kernel<1><<<grid, 256, 0, st>>>(s_feats, pos, q_points, s_points, neighbors, n_neighbors, kernel_points, sigma,
+                                                     n_support, n_query, c_in, wf, inv_count);
 }
 
 // General KPConv, Cin % 32 == 0 and Cout % 32 == 0 (mid channels 32..512 of the bottleneck blocks).
@@ -630,9 +655,8 @@ int geob200_kpconv_tc(const float* s_feats, const float* q_points, const float* 
     float* inv_count = ar.take<float>(n_query);
     float* wf = ar.take<float>((size_t)n_query * KP * c_in);
     row_positive_kernel<<<(unsigned)((n_support + 7) / 8), 256, 0, st>>>(s_feats, (int)n_support, (int)c_in, pos);
-    kpconv_gather_kernel<<<(unsigned)((n_query + 7) / 8), 256, 0, st>>>(s_feats, pos, q_points, s_points, (const long long*)neighbors,
-                                                                       (int)n_neighbors, kernel_points, sigma, (int)n_support,
-                                                                       (int)n_query, (int)c_in, wf, inv_count);
+    launch_kpconv_gather(s_feats, pos, q_points, s_points, (const long long*)neighbors, (int)n_neighbors, kernel_points, sigma,
+                         (int)n_support, (int)n_query, (int)c_in, wf, inv_count, st);
     GEOB_CHECK_LAUNCH();
     count_launches(2);
     const int rc = linear_tc(wf, KP * c_in, weights_t, KP * c_in, bias, inv_count, out, c_out, n_query, c_out, KP * c_in, 0, st);
@@ -856,9 +880,8 @@ int geob200_kpconv_group_norm(const float* s_feats, const float* q_points, const
     float* inv_count = ar.take<float>(n_query);
     float* wf = ar.take<float>((size_t)n_query * KP * c_in);
     row_positive_kernel<<<(unsigned)((n_support + 7) / 8), 256, 0, st>>>(s_feats, (int)n_support, (int)c_in, pos);
-    kpconv_gather_kernel<<<(unsigned)((n_query + 7) / 8), 256, 0, st>>>(s_feats, pos, q_points, s_points, (const long long*)neighbors,
-                                                                       (int)n_neighbors, kernel_points, sigma, (int)n_support,
-                                                                       (int)n_query, (int)c_in, wf, inv_count);
+    launch_kpconv_gather(s_feats, pos, q_points, s_points, (const long long*)neighbors, (int)n_neighbors, kernel_points, sigma,
+                         (int)n_support, (int)n_query, (int)c_in, wf, inv_count, st);
     GEOB_CHECK_LAUNCH();
     count_launches(2);
     const GnWs w = gn_carve(gn_workspace, gn_workspace_bytes, groups);
