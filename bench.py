@@ -124,7 +124,8 @@ def cpu_reference_pairs_per_s(workload, n_pairs, threads):
         data = G.collate_pair(pair, cfg, limits, impl=impl)
         t1 = time.perf_counter()
         with torch.no_grad():
-            G.forward(sd, cfg, data)
+            out = G.forward(sd, cfg, data)
+            G.evaluate(cfg, out, pair['transform'])
         t2 = time.perf_counter()
         t_collate += t1 - t0
         t_fwd += t2 - t1
@@ -142,16 +143,17 @@ def main():
         if rank != 0:
             return
         threads = cpu_threads()
-        # bounded sample per step: 1 pair of the workload (several seconds to minutes of CPU work)
-        steps = max(1, min(args.steps, 2))
-        warm = min(args.warmup, 0)
+        # bounded sample per step: 1 pair of the workload (~3 s of CPU work on 16 threads); at most 20 timed + 2 warm-up pairs
+        steps = max(1, min(args.steps, 20))
+        warm = max(0, min(args.warmup, 2))
         for _ in range(warm):
             cpu_reference_pairs_per_s(args.workload, 1, threads)
         v, secs, desc = cpu_reference_pairs_per_s(args.workload, steps, threads)
         line = {'metric': METRIC, 'value': v, 'unit': 'pairs/s', 'n_gpus': args.gpus, 'steps': steps, 'warmup': warm,
                 'ms_per_step': 1000.0 * secs / steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                 'dtype': 'f32', 'data': 'synthetic', 'impl': 'reference',
-                'config': {'workload': args.workload, 'pairs_per_step': 1, 'note': 'CPU path, rank 0 only'},
+                'config': {'workload': args.workload, 'pairs_per_step': 1,
+                           'note': f'CPU path, rank 0 only; --steps {args.steps} --warmup {args.warmup} bounded to {steps} / {warm} pairs'},
                 'cpu_baseline': {'value': v, 'unit': 'pairs/s', 'cores': threads, 'kind': 'reference', 'sample': desc},
                 'e2e': {'value': v, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
                 'gpu_launches': 0}
