@@ -22,6 +22,7 @@ namespace geob200 {
 constexpr int ATT_R = 2;
 constexpr int ATT_KPT = 2;
 constexpr int ATT_MAXH = 8;
+constexpr int ATT_KQ = 8;          // key ranges of the streaming P.V kernel (64 * ATT_KQ threads)
 
 template <int H>
 __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk,
@@ -174,32 +175,63 @@ __device__ __forceinline__ float dot4(const float4 a, const float4 b, float acc)
     return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc))));
 }
 
+constexpr int ATS_DEPTH = 3;      // E row groups in flight per warp (cp.async ring in shared memory)
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Persistent CTAs (one per resident slot); a CTA owns a contiguous range of (query, 4-key group) work units, its 4 warps take
+// them round-robin.  Each warp streams the E rows of its next ATS_DEPTH-1 groups into its private shared-memory ring with
+// cp.async (every lane later reads back exactly the 16-byte pieces it copied, so no barrier is needed): ~8 KB of E in flight
+// per warp without spending registers on it.
 template <int H, int J>
 __global__ void __launch_bounds__(128) att_scores_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk,
                                                          const float* __restrict__ qp, const float* __restrict__ qb,
-                                                         const float* __restrict__ E, int N, int M, int keys_per_cta, float div,
-                                                         float* __restrict__ S) {
+                                                         const float* __restrict__ E, int N, int M, float div, float* __restrict__ S) {
     constexpr int C = 128 * J;
     constexpr int D = C / H;
     constexpr int NV = ATS_G * H;                 // values reduced together: (key u, head h) -> v[u * H + h]
+    extern __shared__ float4 ring_all[];          // [4 warps][ATS_DEPTH][ATS_G][J][32 lanes]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4* ring = ring_all + (size_t)warp * ATS_DEPTH * ATS_G * J * 32;
     const bool has_e = (E != nullptr);
-    // persistent: work items = (query, chunk of keys_per_cta keys) in row-major order, a contiguous range per CTA (the grid is
-    // sized to the resident capacity, so there is no partial last wave; consecutive items mostly share the query registers)
-    const int chunks = (M + keys_per_cta - 1) / keys_per_cta;
-    const long long items = (long long)N * chunks;
-    const long long it0 = items * blockIdx.x / gridDim.x, it1 = items * (blockIdx.x + 1) / gridDim.x;
+    const int gpq = (M + ATS_G - 1) / ATS_G;      // groups per query
+    const long long groups = (long long)N * gpq;
+    const long long g_begin = groups * blockIdx.x / gridDim.x, g_end = groups * (blockIdx.x + 1) / gridDim.x;
     float4 qv[J];
     float4 qpv[H][J];
     int hq[J];
 #pragma unroll
     for (int j = 0; j < J; ++j) hq[j] = (j * 128 + 4 * lane) / D;
+
+    auto prefetch = [&](long long g, int slot) {           // E rows of group g -> ring slot (no-op group when g is out of range)
+        if (has_e && g < g_end) {
+            const int n = (int)(g / gpq), m0 = (int)(g % gpq) * ATS_G;
+            const float* e_row = E + (long long)n * M * C;
+#pragma unroll
+            for (int u = 0; u < ATS_G; ++u) {
+                const int m = min(m0 + u, M - 1);
+#pragma unroll
+                for (int j = 0; j < J; ++j)
+                    cp_async16(&ring[((slot * ATS_G + u) * J + j) * 32 + lane], e_row + (long long)m * C + j * 128 + 4 * lane);
+            }
+        }
+        cp_async_commit();
+    };
+
+    const long long first = g_begin + warp;
+#pragma unroll
+    for (int d = 0; d < ATS_DEPTH - 1; ++d) prefetch(first + 4ll * d, d);
     int n_loaded = -1;
-    for (long long it = it0; it < it1; ++it) {
-        const int n = (int)(it / chunks);
-        const int m_begin = (int)(it % chunks) * keys_per_cta;
-        const int m_end = min(M, m_begin + keys_per_cta);
-        if (n != n_loaded) {
+    int slot = 0;
+    for (long long g = first; g < g_end; g += 4) {
+        prefetch(g + 4ll * (ATS_DEPTH - 1), (slot + ATS_DEPTH - 1) % ATS_DEPTH);
+        const int n = (int)(g / gpq), m0 = (int)(g % gpq) * ATS_G;
+        if (n != n_loaded) {                                  // warp-uniform
 #pragma unroll
             for (int j = 0; j < J; ++j) {
                 const int c = j * 128 + 4 * lane;
@@ -210,56 +242,53 @@ __global__ void __launch_bounds__(128) att_scores_kernel(const float* __restrict
             }
             n_loaded = n;
         }
-        const float* e_row = has_e ? E + (long long)n * M * C : nullptr;
-        for (int m0 = m_begin + warp * ATS_G; m0 < m_end; m0 += 4 * ATS_G) {
-            float4 kk[ATS_G][J], ee[ATS_G][J];
+        float4 kk[ATS_G][J];
 #pragma unroll
-            for (int u = 0; u < ATS_G; ++u) {
-                const int m = min(m0 + u, M - 1);
+        for (int u = 0; u < ATS_G; ++u) {
+            const int m = min(m0 + u, M - 1);
+#pragma unroll
+            for (int j = 0; j < J; ++j) kk[u][j] = __ldg(reinterpret_cast<const float4*>(k + (long long)m * ldk + j * 128 + 4 * lane));
+        }
+        cp_async_wait<ATS_DEPTH - 1>();                       // this group's E rows have landed (own copies only: no barrier)
+        float v[NV];
+#pragma unroll
+        for (int u = 0; u < ATS_G; ++u) {
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                float a = 0.f;
 #pragma unroll
                 for (int j = 0; j < J; ++j) {
-                    kk[u][j] = __ldg(reinterpret_cast<const float4*>(k + (long long)m * ldk + j * 128 + 4 * lane));
-                    if (has_e) ee[u][j] = __ldcs(reinterpret_cast<const float4*>(e_row + (long long)m * C + j * 128 + 4 * lane));
+                    const float p = dot4(kk[u][j], qv[j], 0.f);
+                    a += (hq[j] == h) ? p : 0.f;
+                    if (has_e) a = dot4(ring[((slot * ATS_G + u) * J + j) * 32 + lane], qpv[h][j], a);
                 }
-            }
-            float v[NV];
-#pragma unroll
-            for (int u = 0; u < ATS_G; ++u) {
-#pragma unroll
-                for (int h = 0; h < H; ++h) {
-                    float a = 0.f;
-#pragma unroll
-                    for (int j = 0; j < J; ++j) {
-                        const float p = dot4(kk[u][j], qv[j], 0.f);
-                        a += (hq[j] == h) ? p : 0.f;
-                        if (has_e) a = dot4(ee[u][j], qpv[h][j], a);
-                    }
-                    v[u * H + h] = a;
-                }
-            }
-            warp_butterfly(v, lane);      // transposing reduction: lane l ends up with value index l >> (5 - log2 NV)
-            // NV = 2^b values: value index = the top b lane bits; one lane per value writes
-            constexpr int SH = (NV == 32) ? 0 : (NV == 16) ? 1 : (NV == 8) ? 2 : 3;
-            const int idx = lane >> SH;
-            const int u = idx / H, h = idx % H;
-            if ((lane & ((1 << SH) - 1)) == 0 && m0 + u < m_end) {
-                const float bias = has_e ? qb[(long long)n * H + h] : 0.f;
-                S[((long long)n * H + h) * M + m0 + u] = (v[0] + bias) / div;
+                v[u * H + h] = a;
             }
         }
+        warp_butterfly(v, lane);      // transposing reduction: lane l ends up with value index l >> (5 - log2 NV)
+        // NV = 2^b values: value index = the top b lane bits; one lane per value writes
+        constexpr int SH = (NV == 32) ? 0 : (NV == 16) ? 1 : (NV == 8) ? 2 : 3;
+        const int idx = lane >> SH;
+        const int u = idx / H, h = idx % H;
+        if ((lane & ((1 << SH) - 1)) == 0 && m0 + u < M) {
+            const float bias = has_e ? qb[(long long)n * H + h] : 0.f;
+            S[((long long)n * H + h) * M + m0 + u] = (v[0] + bias) / div;
+        }
+        slot = (slot + 1) % ATS_DEPTH;
     }
+    cp_async_wait<0>();
 }
 
 // softmax over the keys and P.V for R = 2 queries per CTA (value rows fetched once for both); thread <-> channel
 template <int H>
-__global__ void __launch_bounds__(256) att_softmax_pv_kernel(const float* __restrict__ S, const float* __restrict__ v, int ldv, int N,
+__global__ void __launch_bounds__(512) att_softmax_pv_kernel(const float* __restrict__ S, const float* __restrict__ v, int ldv, int N,
                                                              int M, int C, float* __restrict__ out, int ldo) {
     extern __shared__ float sm[];
     float* sc = sm;                               // [R][H][M]
     const int n0 = blockIdx.x * ATT_R;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int d = C / H;
-    for (int rh = warp; rh < ATT_R * H; rh += 8) {
+    for (int rh = warp; rh < ATT_R * H; rh += (int)(blockDim.x >> 5)) {
         const int r = rh / H;
         float* s = sc + rh * M;
         if (n0 + r >= N) {
@@ -280,7 +309,7 @@ __global__ void __launch_bounds__(256) att_softmax_pv_kernel(const float* __rest
         for (int m = lane; m < M; m += 32) s[m] = s[m] / sum;
     }
     __syncthreads();
-    // P.V: thread = (4 channels, quarter of the keys); 16-byte value loads, 4 of them in flight; quarters folded through smem
+    // P.V: thread = (4 channels, one of ATT_KQ key ranges); 16-byte value loads, 4 of them in flight; ranges folded through smem
     float4* red = reinterpret_cast<float4*>(sc + ((ATT_R * H * M + 3) & ~3));      // [4][R][C/4]
     const int C4 = C >> 2;
     const int kq = threadIdx.x / 64, c4 = threadIdx.x % 64;
@@ -288,7 +317,7 @@ __global__ void __launch_bounds__(256) att_softmax_pv_kernel(const float* __rest
         const int h = (4 * c4) / d;
         const float* p0 = sc + (0 * H + h) * M;
         const float* p1 = sc + (1 * H + h) * M;
-        const int per = (M + 3) / 4, mb = kq * per, me = min(M, mb + per);
+        const int per = (M + ATT_KQ - 1) / ATT_KQ, mb = kq * per, me = min(M, mb + per);
         float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
         int m = mb;
         for (; m + 3 < me; m += 4) {
@@ -317,36 +346,41 @@ __global__ void __launch_bounds__(256) att_softmax_pv_kernel(const float* __rest
     for (int t = threadIdx.x; t < ATT_R * C4; t += blockDim.x) {
         const int r = t / C4, cc = t % C4;
         if (n0 + r >= N) continue;
-        const float4 q0 = red[(0 * ATT_R + r) * C4 + cc], q1 = red[(1 * ATT_R + r) * C4 + cc];
-        const float4 q2 = red[(2 * ATT_R + r) * C4 + cc], q3 = red[(3 * ATT_R + r) * C4 + cc];
+        float4 acc = red[(0 * ATT_R + r) * C4 + cc];
+#pragma unroll
+        for (int g = 1; g < ATT_KQ; ++g) {                      // fixed order
+            const float4 x = red[(g * ATT_R + r) * C4 + cc];
+            acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+        }
         float* o = out + (long long)(n0 + r) * ldo + 4 * cc;
-        o[0] = (q0.x + q1.x) + (q2.x + q3.x);
-        o[1] = (q0.y + q1.y) + (q2.y + q3.y);
-        o[2] = (q0.z + q1.z) + (q2.z + q3.z);
-        o[3] = (q0.w + q1.w) + (q2.w + q3.w);
+        o[0] = acc.x; o[1] = acc.y; o[2] = acc.z; o[3] = acc.w;
     }
 }
 
 template <int H, int J>
 static int launch_streaming(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, const float* qp, const float* qb,
                             const float* E, int N, int M, float div, float* out, int ldo, float* S, cudaStream_t st) {
-    // work items of 32 keys (2 butterfly groups per warp); one CTA per resident slot (occupancy queried once per instantiation)
+    // one CTA per resident slot (occupancy queried once per instantiation); each owns a contiguous range of 4-key groups
+    constexpr int ring_bytes = 4 * ATS_DEPTH * ATS_G * J * 32 * (int)sizeof(float4);
     static int per_sm = 0;
     if (per_sm == 0) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, att_scores_kernel<H, J>, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+        if (ring_bytes > 48 * 1024 &&
+            cudaFuncSetAttribute(att_scores_kernel<H, J>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes) != cudaSuccess)
+            return -1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, att_scores_kernel<H, J>, 128, ring_bytes) != cudaSuccess || per_sm < 1)
+            per_sm = 1;
     }
-    const int kpc = 8 * ATS_G;
-    const long long items = (long long)N * ((M + kpc - 1) / kpc);
+    const long long groups = (long long)N * ((M + ATS_G - 1) / ATS_G);
     long long grid = (long long)per_sm * num_sms();
-    if (grid > items) grid = items;
-    att_scores_kernel<H, J><<<(unsigned)grid, 128, 0, st>>>(q, ldq, k, ldk, qp, qb, E, N, M, kpc, div, S);
-    const size_t smem = sizeof(float) * (ATT_R * H * (size_t)((M + 3) / 4 * 4) + 4 * ATT_R * 128 * J);     // scores + the 4 partial outputs
+    if (grid * 4 > groups) grid = (groups + 3) / 4;
+    att_scores_kernel<H, J><<<(unsigned)grid, 128, ring_bytes, st>>>(q, ldq, k, ldk, qp, qb, E, N, M, div, S);
+    const size_t smem = sizeof(float) * (ATT_R * H * (size_t)((M + 3) / 4 * 4) + ATT_KQ * ATT_R * 128 * J);     // scores + the partial outputs
     static size_t smem_set = 0;
     if (smem > 48 * 1024 && smem > smem_set) {
         if (cudaFuncSetAttribute(att_softmax_pv_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
         smem_set = smem;
     }
-    att_softmax_pv_kernel<H><<<(unsigned)((N + ATT_R - 1) / ATT_R), 256, smem, st>>>(S, v, ldv, N, M, 128 * J, out, ldo);
+    att_softmax_pv_kernel<H><<<(unsigned)((N + ATT_R - 1) / ATT_R), 64 * ATT_KQ, smem, st>>>(S, v, ldv, N, M, 128 * J, out, ldo);
     return 0;
 }
 
@@ -417,7 +451,7 @@ int geob200_attention(const float* q, int64_t ldq, const float* k, int64_t ldk, 
     GEOB_REQUIRE(ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0, "attention: row strides must be multiples of 4 floats");
     GEOB_REQUIRE(heads == 1 || heads == 2 || heads == 4 || heads == 8, "attention: heads must be 1, 2, 4 or 8");
     const float div = sqrtf((float)(channels / heads));   // d_model_per_head ** 0.5
-    const size_t smem_pv = sizeof(float) * (ATT_R * heads * (size_t)((n_key + 3) / 4 * 4) + 4 * ATT_R * channels);
+    const size_t smem_pv = sizeof(float) * (ATT_R * heads * (size_t)((n_key + 3) / 4 * 4) + ATT_KQ * ATT_R * channels);
     if ((channels == 128 || channels == 256) && smem_pv <= 200 * 1024 && workspace != nullptr) {
         // streaming path: lanes <-> channels, (query, key-chunk) grid, scores through the workspace
         GEOB_REQUIRE(workspace_bytes >= geob200_attention_workspace_bytes(n_query, n_key, heads), "attention: workspace too small");
