@@ -223,26 +223,13 @@ __global__ void __launch_bounds__(128) att_scores_kernel(const float* __restrict
         cp_async_commit();
     };
 
-    auto load_k = [&](long long g, float4 (&dst)[ATS_G][J]) {   // key rows of group g (L2 resident) into registers
-        const int m0 = (int)(g % gpq) * ATS_G;
-#pragma unroll
-        for (int u = 0; u < ATS_G; ++u) {
-            const int m = min(m0 + u, M - 1);
-#pragma unroll
-            for (int j = 0; j < J; ++j) dst[u][j] = __ldg(reinterpret_cast<const float4*>(k + (long long)m * ldk + j * 128 + 4 * lane));
-        }
-    };
-
     const long long first = g_begin + warp;
 #pragma unroll
     for (int d = 0; d < ATS_DEPTH - 1; ++d) prefetch(first + 4ll * d, d);
     int n_loaded = -1;
     int slot = 0;
-    float4 kk[ATS_G][J], kk_next[ATS_G][J];
-    if (first < g_end) load_k(first, kk);
     for (long long g = first; g < g_end; g += 4) {
         prefetch(g + 4ll * (ATS_DEPTH - 1), (slot + ATS_DEPTH - 1) % ATS_DEPTH);
-        if (g + 4 < g_end) load_k(g + 4, kk_next);           // next group's key rows: their L2 latency hides behind this group's math
         const int n = (int)(g / gpq), m0 = (int)(g % gpq) * ATS_G;
         if (n != n_loaded) {                                  // warp-uniform
 #pragma unroll
@@ -254,6 +241,13 @@ __global__ void __launch_bounds__(128) att_scores_kernel(const float* __restrict
                     qpv[h][j] = has_e ? *reinterpret_cast<const float4*>(qp + ((long long)n * H + h) * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
             n_loaded = n;
+        }
+        float4 kk[ATS_G][J];
+#pragma unroll
+        for (int u = 0; u < ATS_G; ++u) {
+            const int m = min(m0 + u, M - 1);
+#pragma unroll
+            for (int j = 0; j < J; ++j) kk[u][j] = __ldg(reinterpret_cast<const float4*>(k + (long long)m * ldk + j * 128 + 4 * lane));
         }
         cp_async_wait<ATS_DEPTH - 1>();                       // this group's E rows have landed (own copies only: no barrier)
         float v[NV];
@@ -281,10 +275,6 @@ __global__ void __launch_bounds__(128) att_scores_kernel(const float* __restrict
             S[((long long)n * H + h) * M + m0 + u] = (v[0] + bias) / div;
         }
         slot = (slot + 1) % ATS_DEPTH;
-#pragma unroll
-        for (int u = 0; u < ATS_G; ++u)
-#pragma unroll
-            for (int j = 0; j < J; ++j) kk[u][j] = kk_next[u][j];
     }
     cp_async_wait<0>();
 }
