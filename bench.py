@@ -183,7 +183,6 @@ def main():
     from geotransformer_b200.config import make_cfg
     from geotransformer_b200.model import create_model
     from geotransformer_b200.synth import WORKLOADS
-    from geotransformer_b200.utils.data import registration_collate_fn_stack_mode
     from geotransformer_b200.weights import synthetic_state_dict
 
     if args.gse_mode is not None:

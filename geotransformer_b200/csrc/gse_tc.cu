@@ -732,7 +732,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) gse_emb
             int acc = 0;
             uint32_t acc_ph[2] = {0, 0};
             for (long long itile = 0; itile < n_iters; ++itile) {
-            const long long tile = itile * gridDim.x + blockIdx.x;   // tile >= n_tiles: idle slot, pipeline still runs
+                // slots with itile * gridDim.x + blockIdx.x >= n_tiles are idle, the pipeline still runs
                 mbar_wait(&tempty[acc], acc_ph[acc] ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * C);

@@ -10,7 +10,6 @@ bench.py measures as `e2e` (the SingleTester-compa
 import threading
 from concurrent.futures import ThreadPoolExecutor
 
-import numpy as np
 import torch
 
 from . import _lib

@@ -11,7 +11,6 @@ rejected explicitly (the reference reads ``points[0]``, ``extra/cloud/cloud.cpp:
 To install it in place of the reference module: ``sys.modules['geotransformer.ext'] = geotransformer_b200.ext``
 (see INTEGRATION.md).
 """
-import ctypes
 
 import torch
 

@@ -7,7 +7,7 @@ forked workers, so here the raw pair is moved to the device and collated in the 
 import numpy as np
 import torch
 
-from ..modules.ops import grid_subsample, radius_search, radius_search_deferred
+from ..modules.ops import grid_subsample, radius_search_deferred
 
 
 def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, neighbor_limits):

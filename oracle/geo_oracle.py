@@ -25,7 +25,6 @@ Reference map (all paths under /root/reference):
                            geotransformer/modules/ops/transformation.py:7-60
   model assembly           experiments/*/model.py:69-212
 """
-import math
 
 import numpy as np
 import torch
