@@ -91,8 +91,9 @@ def load_peaks():
 def make_inputs(workload, n_pairs, rank, world):
     from geotransformer_b200.synth import make_pair
     pairs = []
-    for i in range(n_pairs):
-        p = make_pair(workload, rank + i * world)
+    from geotransformer_b200.distributed import pair_ids
+    for pid in pair_ids(n_pairs, rank, world):
+        p = make_pair(workload, pid)
         pairs.append({k: p[k] for k in ('ref_points', 'src_points', 'ref_feats', 'src_feats', 'transform')})
     return pairs
 
@@ -180,6 +181,7 @@ def main():
             os.close(saved_stdout)
 
     from geotransformer_b200 import functional as GF, _lib
+    from geotransformer_b200.distributed import gather_metric_rows, max_over_ranks
     from geotransformer_b200.config import make_cfg
     from geotransformer_b200.model import create_model
     from geotransformer_b200.synth import WORKLOADS
@@ -225,11 +227,7 @@ def main():
         ms = e0.elapsed_time(e1)
         if os.environ.get('GEOB_BENCH_DEBUG'):
             print(f'[rank {rank}] {n} steps x {S} pairs: {ms:.1f} ms', file=sys.stderr, flush=True)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+        return max_over_ranks(ms, dev, world)
 
     timed(resident, 0, W)
     timed(pinned, 0, W)
@@ -274,10 +272,7 @@ def main():
         rows.append([m['RRE'], m['RTE'], float(out['num_corr']), float(rank + (W * S + j) * world), m['PIR'], m['IR'], m['RMSE'],
                      m['RR']])
     rows_t = torch.tensor(rows, dtype=torch.float32, device=dev)
-    if world > 1:
-        gathered = [torch.empty_like(rows_t) for _ in range(world)]
-        dist.all_gather(gathered, rows_t)
-        rows_t = torch.cat(gathered, dim=0)
+    rows_t = gather_metric_rows(rows_t, world)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

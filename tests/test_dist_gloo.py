@@ -20,20 +20,17 @@ def _worker(rank, world, port, n_pairs, q):
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
+    from geotransformer_b200.distributed import gather_metric_rows, max_over_ranks, pair_ids     # what bench.py calls
     from geotransformer_b200.synth import make_pair
     rows = []
-    for i in range(n_pairs // world):
-        pid = rank + i * world                       # same assignment as bench.make_inputs
+    for pid in pair_ids(n_pairs // world, rank, world):
         pair = make_pair('modelnet717', pid)
-        rows.append([float(pair['ref_points'].sum()), float(pair['transform'][0, 3]), 0.0, float(pid)])
+        rows.append([float(pair['ref_points'].sum()), float(pair['transform'][0, 3]), 0.0, float(pid), 0.0, 0.0, 0.0, 1.0])
     rows = torch.tensor(rows, dtype=torch.float32)
-    gathered = [torch.empty_like(rows) for _ in range(world)]
-    dist.all_gather(gathered, rows)
-    allrows = torch.cat(gathered)
-    t = torch.tensor([float(rank + 1)])
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)          # the max-over-ranks timing reduction
+    allrows = gather_metric_rows(rows, world)
+    tmax = max_over_ranks(float(rank + 1), torch.device('cpu'), world)    # the max-over-ranks timing reduction
     if rank == 0:
-        q.put((allrows.numpy(), float(t.item())))
+        q.put((allrows.numpy(), tmax))
     dist.barrier()
     dist.destroy_process_group()
 
