@@ -187,7 +187,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // Persistent CTAs (one per resident slot); a CTA owns a contiguous range of (query, 4-key group) work units, its 4 warps take
 // them round-robin.  Each warp streams the E rows of its next ATS_DEPTH-1 groups into its private shared-memory ring with
 // cp.async (every lane later reads back exactly the 16-byte pieces it copied, so no barrier is needed): ~8 KB of E in flight
-// per warp without spending registers on it.  The key rows (L2 resident) travel the same way, so the loop has no exposed load.
+// per warp without spending registers on it.
 template <int H, int J>
 __global__ void __launch_bounds__(128) att_scores_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk,
                                                          const float* __restrict__ qp, const float* __restrict__ qb,
@@ -195,10 +195,9 @@ __global__ void __launch_bounds__(128) att_scores_kernel(const float* __restrict
     constexpr int C = 128 * J;
     constexpr int D = C / H;
     constexpr int NV = ATS_G * H;                 // values reduced together: (key u, head h) -> v[u * H + h]
-    extern __shared__ float4 ring_all[];          // [4 warps][ATS_DEPTH][E rows | key rows][ATS_G][J][32 lanes]
+    extern __shared__ float4 ring_all[];          // [4 warps][ATS_DEPTH][ATS_G][J][32 lanes]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr int SLOT = 2 * ATS_G * J * 32;      // float4 per ring slot: the group's E rows, then its key rows
-    float4* ring = ring_all + (size_t)warp * ATS_DEPTH * SLOT;
+    float4* ring = ring_all + (size_t)warp * ATS_DEPTH * ATS_G * J * 32;
     const bool has_e = (E != nullptr);
     const int gpq = (M + ATS_G - 1) / ATS_G;      // groups per query
     const long long groups = (long long)N * gpq;
@@ -209,18 +208,16 @@ __global__ void __launch_bounds__(128) att_scores_kernel(const float* __restrict
 #pragma unroll
     for (int j = 0; j < J; ++j) hq[j] = (j * 128 + 4 * lane) / D;
 
-    auto prefetch = [&](long long g, int slot) {           // E and key rows of group g -> ring slot (empty group when out of range)
-        if (g < g_end) {
+    auto prefetch = [&](long long g, int slot) {           // E rows of group g -> ring slot (no-op group when g is out of range)
+        if (has_e && g < g_end) {
             const int n = (int)(g / gpq), m0 = (int)(g % gpq) * ATS_G;
-            const float* e_row = has_e ? E + (long long)n * M * C : nullptr;
+            const float* e_row = E + (long long)n * M * C;
 #pragma unroll
             for (int u = 0; u < ATS_G; ++u) {
                 const int m = min(m0 + u, M - 1);
 #pragma unroll
-                for (int j = 0; j < J; ++j) {
-                    if (has_e) cp_async16(&ring[slot * SLOT + (u * J + j) * 32 + lane], e_row + (long long)m * C + j * 128 + 4 * lane);
-                    cp_async16(&ring[slot * SLOT + ((ATS_G + u) * J + j) * 32 + lane], k + (long long)m * ldk + j * 128 + 4 * lane);
-                }
+                for (int j = 0; j < J; ++j)
+                    cp_async16(&ring[((slot * ATS_G + u) * J + j) * 32 + lane], e_row + (long long)m * C + j * 128 + 4 * lane);
             }
         }
         cp_async_commit();
@@ -245,7 +242,14 @@ __global__ void __launch_bounds__(128) att_scores_kernel(const float* __restrict
             }
             n_loaded = n;
         }
-        cp_async_wait<ATS_DEPTH - 1>();                       // this group's rows have landed (own copies only: no barrier)
+        float4 kk[ATS_G][J];
+#pragma unroll
+        for (int u = 0; u < ATS_G; ++u) {
+            const int m = min(m0 + u, M - 1);
+#pragma unroll
+            for (int j = 0; j < J; ++j) kk[u][j] = __ldg(reinterpret_cast<const float4*>(k + (long long)m * ldk + j * 128 + 4 * lane));
+        }
+        cp_async_wait<ATS_DEPTH - 1>();                       // this group's E rows have landed (own copies only: no barrier)
         float v[NV];
 #pragma unroll
         for (int u = 0; u < ATS_G; ++u) {
@@ -254,9 +258,9 @@ __global__ void __launch_bounds__(128) att_scores_kernel(const float* __restrict
                 float a = 0.f;
 #pragma unroll
                 for (int j = 0; j < J; ++j) {
-                    const float p = dot4(ring[slot * SLOT + ((ATS_G + u) * J + j) * 32 + lane], qv[j], 0.f);
+                    const float p = dot4(kk[u][j], qv[j], 0.f);
                     a += (hq[j] == h) ? p : 0.f;
-                    if (has_e) a = dot4(ring[slot * SLOT + (u * J + j) * 32 + lane], qpv[h][j], a);
+                    if (has_e) a = dot4(ring[((slot * ATS_G + u) * J + j) * 32 + lane], qpv[h][j], a);
                 }
                 v[u * H + h] = a;
             }
@@ -357,7 +361,7 @@ template <int H, int J>
 static int launch_streaming(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, const float* qp, const float* qb,
                             const float* E, int N, int M, float div, float* out, int ldo, float* S, cudaStream_t st) {
     // one CTA per resident slot (occupancy queried once per instantiation); each owns a contiguous range of 4-key groups
-    constexpr int ring_bytes = 4 * ATS_DEPTH * 2 * ATS_G * J * 32 * (int)sizeof(float4);
+    constexpr int ring_bytes = 4 * ATS_DEPTH * ATS_G * J * 32 * (int)sizeof(float4);
     static int per_sm = 0;
     if (per_sm == 0) {
         if (ring_bytes > 48 * 1024 &&
