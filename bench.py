@@ -39,6 +39,7 @@ def parse():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='3dmatch20k')
     ap.add_argument('--gse-mode', type=int, default=None)
+    ap.add_argument('--linear-persistent', type=int, default=None, help='1/0: persistent tile loop of the tcgen05 GEMM')
     ap.add_argument('--streams', type=int, default=4, help='pairs in flight per GPU (one CUDA stream + host thread each)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     return ap.parse_args()
@@ -189,6 +190,8 @@ def main():
 
     if args.gse_mode is not None:
         GF.GSE_MODE = args.gse_mode
+    if args.linear_persistent is not None:
+        _lib.lib().geob200_set_linear_persistent(int(args.linear_persistent))
     cfg = make_cfg(WORKLOADS[args.workload][0])
     limits = cfg.neighbor_limits or [27, 75, 147, 157, 119][:cfg.backbone.num_stages]
     model = create_model(cfg)

@@ -75,6 +75,7 @@ _sig('geob200_evaluate', c_int, P, P, I64, F, P, P, I64, P, P, I64, F, P, P, P, 
 
 _sig('geob200_linear_profile_enable', c_int, c_int)
 _sig('geob200_set_split_k', c_int, c_int)
+_sig('geob200_set_linear_persistent', c_int, c_int)
 _sig('geob200_linear_profile_read', I64, I64, P, P)
 _sig('geob200_backbone_workspace_bytes', SZ, P, P)
 _sig('geob200_backbone_forward', c_int, P, P, P, P, P, P, P, P, P, P, P, P, SZ, P, SZ, P)

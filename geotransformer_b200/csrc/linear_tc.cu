@@ -311,6 +311,237 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const __grid_con
     }
 }
 
+// ---- persistent variant (multi-wave GEMMs) ----------------------------------------------------------------------------------
+// One CTA per SM walks the output tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...  The operand ring keeps running across
+// tile boundaries and there are TWO accumulator sets in TMEM (2 x (main 128 + corrections 128) = 512 columns): while the four
+// epilogue warps drain, normalise and store tile i, the producer / splitters / MMA issuer are already deep in the K loop of
+// tile i + 1, so the per-tile fixed cost (first TMA round trip, TMEM drain, stores) is hidden instead of paid per CTA.
+constexpr int SMEM_PERSIST = SMEM + 4 * 128 * 8 + 512;      // + GroupNorm column sums [4][128] float2 + the bias row
+
+__global__ void __launch_bounds__(NTHREADS, 1) linear_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x,
+                                                                           const __grid_constant__ CUtensorMap map_w,
+                                                                           const float* __restrict__ bias,
+                                                                           const float* __restrict__ row_scale, float* __restrict__ Y,
+                                                                           int ldy, int M, int N, int K, int BN, int relu, GnFuse gn,
+                                                                           int col_tiles, int num_tiles) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = (uint64_t*)(smem + NSTAGE * STAGE);
+    uint64_t* raw_full = bars;                  // TMA landed
+    uint64_t* split_full = bars + NSTAGE;       // hi/lo ready
+    uint64_t* empty = bars + 2 * NSTAGE;        // MMAs done with the stage
+    uint64_t* acc_full = bars + 3 * NSTAGE;     // [2] accumulator set complete
+    uint64_t* acc_empty = acc_full + 2;         // [2] accumulator set drained by the epilogue
+    uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
+    float2* gn_sm = (float2*)(smem + NSTAGE * STAGE + 256);
+    float* bias_s = (float*)(smem + NSTAGE * STAGE + 256 + 4 * 128 * 8);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nk = (K + KC - 1) / KC;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&split_full[s], NSPLIT_WARPS); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    }
+    if (warp == MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const int m0 = (t / col_tiles) * BM, n0 = (t % col_tiles) * BN;
+                for (int kc = 0; kc < nk; ++kc) {
+                    mbar_wait(&empty[s], ph ^ 1u);
+                    unsigned char* st = smem + s * STAGE;
+                    mbar_arrive_expect_tx(&raw_full[s], (uint32_t)(TILE_A + BN * 128));
+                    tma_load_2d(st, &map_x, kc * KC, m0, &raw_full[s]);
+                    tma_load_2d(st + 2 * TILE_A, &map_w, kc * KC, n0, &raw_full[s]);
+                    if (++s == NSTAGE) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp <= NSPLIT_WARPS) {
+        constexpr int NT = NSPLIT_WARPS * 32;
+        const int tt = threadIdx.x - 32;
+        int s = 0;
+        uint32_t ph = 0;
+        const int nvec_a = TILE_A / 16, nvec_b = BN * 128 / 16;
+        const int nvec = nvec_a + nvec_b;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            for (int kc = 0; kc < nk; ++kc) {
+                mbar_wait(&raw_full[s], ph);
+                unsigned char* st = smem + s * STAGE;
+                for (int v0 = tt; v0 < nvec; v0 += 2 * NT) {
+                    const int v1 = v0 + NT;
+                    unsigned char* p0 = (v0 < nvec_a) ? (st + v0 * 16) : (st + 2 * TILE_A + (v0 - nvec_a) * 16);
+                    unsigned char* l0 = p0 + ((v0 < nvec_a) ? TILE_A : TILE_B);
+                    const bool two = v1 < nvec;
+                    unsigned char* p1 = !two ? p0 : (v1 < nvec_a) ? (st + v1 * 16) : (st + 2 * TILE_A + (v1 - nvec_a) * 16);
+                    unsigned char* l1 = p1 + ((v1 < nvec_a) ? TILE_A : TILE_B);
+                    const float4 x0 = *reinterpret_cast<float4*>(p0);
+                    const float4 x1 = *reinterpret_cast<float4*>(p1);
+                    float4 h0, q0, h1, q1;
+                    h0.x = tf32_rn(x0.x); q0.x = x0.x - h0.x;
+                    h0.y = tf32_rn(x0.y); q0.y = x0.y - h0.y;
+                    h0.z = tf32_rn(x0.z); q0.z = x0.z - h0.z;
+                    h0.w = tf32_rn(x0.w); q0.w = x0.w - h0.w;
+                    h1.x = tf32_rn(x1.x); q1.x = x1.x - h1.x;
+                    h1.y = tf32_rn(x1.y); q1.y = x1.y - h1.y;
+                    h1.z = tf32_rn(x1.z); q1.z = x1.z - h1.z;
+                    h1.w = tf32_rn(x1.w); q1.w = x1.w - h1.w;
+                    *reinterpret_cast<float4*>(p0) = h0;
+                    *reinterpret_cast<float4*>(l0) = q0;
+                    if (two) {
+                        *reinterpret_cast<float4*>(p1) = h1;
+                        *reinterpret_cast<float4*>(l1) = q1;
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&split_full[s]);
+                if (++s == NSTAGE) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp == MMA_WARP) {
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            int s = 0;
+            uint32_t ph = 0;
+            int it = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+                const int set = it & 1;
+                mbar_wait(&acc_empty[set], (((uint32_t)it >> 1) & 1u) ^ 1u);      // the epilogue has drained the previous use of this set
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t acc = tmem_base + (uint32_t)(set * 256);
+                for (int kc = 0; kc < nk; ++kc) {
+                    mbar_wait(&split_full[s], ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t st = smem_u32(smem + s * STAGE);
+                    const uint64_t a_hi = make_desc(st), a_lo = make_desc(st + TILE_A);
+                    const uint64_t b_hi = make_desc(st + 2 * TILE_A), b_lo = make_desc(st + 2 * TILE_A + TILE_B);
+#pragma unroll
+                    for (int kk = 0; kk < KC / 8; ++kk) {
+                        const uint64_t adv = (uint64_t)(kk * 2);
+                        const uint32_t first = (kc == 0 && kk == 0) ? 0u : 1u;
+                        umma_tf32(acc, a_hi + adv, b_hi + adv, idesc, first);
+                        umma_tf32(acc + 128, a_hi + adv, b_lo + adv, idesc, first);
+                        umma_tf32(acc + 128, a_lo + adv, b_hi + adv, idesc, 1u);
+                    }
+                    umma_commit(&empty[s]);
+                    if (++s == NSTAGE) { s = 0; ph ^= 1u; }
+                }
+                umma_commit(&acc_full[set]);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int et = threadIdx.x - EPI_WARP0 * 32;
+        int it = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+            const int set = it & 1;
+            const int ty = t / col_tiles;
+            const int m0 = ty * BM, n0 = (t % col_tiles) * BN;
+            asm volatile("bar.sync 1, 128;" ::: "memory");                          // previous tile's readers of bias_s / gn_sm are done
+            bias_s[et] = (bias != nullptr && n0 + et < N) ? __ldg(bias + n0 + et) : 0.f;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(&acc_full[set], ((uint32_t)it >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int m = m0 + q * 32 + lane;
+            const float rs = (row_scale != nullptr && m < M) ? row_scale[m] : 1.0f;
+            for (int cc = 0; cc < BN; cc += 32) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + (uint32_t)(set * 256) + ((uint32_t)(q * 32) << 16) + (uint32_t)cc;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                      "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+                      "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+                      "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr));
+                uint32_t w2[32];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(w2[0]), "=r"(w2[1]), "=r"(w2[2]), "=r"(w2[3]), "=r"(w2[4]), "=r"(w2[5]), "=r"(w2[6]), "=r"(w2[7]), "=r"(w2[8]),
+                      "=r"(w2[9]), "=r"(w2[10]), "=r"(w2[11]), "=r"(w2[12]), "=r"(w2[13]), "=r"(w2[14]), "=r"(w2[15]), "=r"(w2[16]),
+                      "=r"(w2[17]), "=r"(w2[18]), "=r"(w2[19]), "=r"(w2[20]), "=r"(w2[21]), "=r"(w2[22]), "=r"(w2[23]), "=r"(w2[24]),
+                      "=r"(w2[25]), "=r"(w2[26]), "=r"(w2[27]), "=r"(w2[28]), "=r"(w2[29]), "=r"(w2[30]), "=r"(w2[31])
+                    : "r"(taddr + 128));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (cc + 32 >= BN) {        // last chunk read: hand the accumulator set back before the stores and statistics
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[set]);
+                }
+                const int nvalid = min(32, N - (n0 + cc));
+                float o[32];
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    float x = (__uint_as_float(v[c]) + __uint_as_float(w2[c])) * rs + bias_s[cc + c];
+                    if (relu) x = fmaxf(x, 0.f);
+                    o[c] = x;
+                }
+                if (m < M) {
+                    float* yr = Y + (long long)m * ldy + n0 + cc;
+                    if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(yr) & 15) == 0)) {
+#pragma unroll
+                        for (int c = 0; c < 32; c += 4) *reinterpret_cast<float4*>(yr + c) = make_float4(o[c], o[c + 1], o[c + 2], o[c + 3]);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c)
+                            if (c < nvalid) yr[c] = o[c];
+                    }
+                }
+                if (gn.groups > 0) {
+                    float s1[32], s2[32];
+                    const bool rv = m < M;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const float x = (rv && c < nvalid) ? o[c] : 0.f;
+                        s1[c] = x;
+                        s2[c] = x * x;
+                    }
+                    float a = warp_butterfly(s1, lane), b2 = warp_butterfly(s2, lane);
+                    for (int off = 1; off < gn.slot_width; off <<= 1) {
+                        a += __shfl_xor_sync(0xffffffffu, a, off);
+                        b2 += __shfl_xor_sync(0xffffffffu, b2, off);
+                    }
+                    if ((lane & (gn.slot_width - 1)) == 0) gn_sm[q * 128 + (cc + lane) / gn.slot_width] = make_float2(a, b2);
+                }
+            }
+            if (gn.groups > 0) {
+                const int slots_tile = BN / gn.slot_width, slots_total = N / gn.slot_width;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (et < slots_tile) {
+                    const float2 p0 = gn_sm[et], p1 = gn_sm[128 + et], p2 = gn_sm[256 + et], p3 = gn_sm[384 + et];
+                    double* dst = gn.partial + ((long long)ty * slots_total + n0 / gn.slot_width + et) * 2;
+                    dst[0] = ((double)p0.x + (double)p1.x) + ((double)p2.x + (double)p3.x);
+                    dst[1] = ((double)p0.y + (double)p1.y) + ((double)p2.y + (double)p3.y);
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == MMA_WARP) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
 // y[m][n] = (sum_z P[z][m][n]) * row_scale[m] + bias[n] (+ ReLU): the splits are added in a fixed order
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ P, int splits, long long MN, int N,
                                                             const float* __restrict__ bias, const float* __restrict__ row_scale,
@@ -373,6 +604,7 @@ static std::vector<ProfRec> g_prof;
 static std::mutex g_prof_mu;
 static bool g_prof_on = false;
 static bool g_splitk_on = true;
+static bool g_persistent_on = false;   // opt-in until validated on hardware: geob200_set_linear_persistent(1)
 
 // ---- split-K scratch: one grow-only buffer per stream (like a BLAS workspace; freed with the process) ---------------------
 struct SplitWs { void* ptr; size_t bytes; };
@@ -452,8 +684,19 @@ int linear_tc(const float* x, int64_t ldx, const float* w, int64_t ldw, const fl
         rec.m = m; rec.n = n; rec.k = k;
         cudaEventRecord(rec.a, st);
     }
-    ltc::linear_tc_kernel<<<grid, ltc::NTHREADS, ltc::SMEM, st>>>(mx, mw, bias, row_scale, y, (int)ldy, (int)m, (int)n, (int)k, BN, relu, g,
-                                                                  part, cps);
+    const bool persistent = g_persistent_on && splits == 1 && tiles > num_sms();
+    if (persistent) {
+        static bool pset = false;
+        if (!pset) {
+            GEOB_CHECK_CUDA(cudaFuncSetAttribute(ltc::linear_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ltc::SMEM_PERSIST));
+            pset = true;
+        }
+        ltc::linear_tc_persistent_kernel<<<num_sms(), ltc::NTHREADS, ltc::SMEM_PERSIST, st>>>(mx, mw, bias, row_scale, y, (int)ldy, (int)m, (int)n,
+                                                                                            (int)k, BN, relu, g, (int)grid.x, tiles);
+    } else {
+        ltc::linear_tc_kernel<<<grid, ltc::NTHREADS, ltc::SMEM, st>>>(mx, mw, bias, row_scale, y, (int)ldy, (int)m, (int)n, (int)k, BN, relu, g,
+                                                                      part, cps);
+    }
     if (part != nullptr) {
         const long long mn = (long long)m * n;
         ltc::splitk_reduce_kernel<<<(unsigned)((mn / 4 + 255) / 256), 256, 0, st>>>(part, splits, mn, (int)n, bias, row_scale, y, (int)ldy, relu);
@@ -472,6 +715,11 @@ int linear_tc(const float* x, int64_t ldx, const float* w, int64_t ldw, const fl
 }  // namespace geob200
 
 extern "C" {
+
+int geob200_set_linear_persistent(int on) {
+    geob200::g_persistent_on = on != 0;
+    return 0;
+}
 
 int geob200_set_split_k(int on) {
     geob200::g_splitk_on = on != 0;

@@ -133,6 +133,38 @@ def test_linear_split_k(m, k, n):
     assert bool((out[:, :n] == 3.0).all())
 
 
+@pytest.mark.parametrize('m,k,n,groups', [(40000, 64, 128, 32), (40000, 480, 32, 32), (20011, 32, 128, 32), (24000, 64, 256, 32),
+                                          (19000, 96, 128, 0)])
+def test_linear_persistent_tile_loop(m, k, n, groups):
+    """multi-wave GEMMs through the persistent kernel (two TMEM accumulator sets, operand ring running across tiles): bitwise
+    the same output and GroupNorm statistics as one CTA per tile"""
+    from geotransformer_b200 import _lib
+    g = torch.Generator().manual_seed(m + k)
+    x, w, b = torch.randn(m, k, generator=g), torch.randn(n, k, generator=g) / math.sqrt(k), torch.randn(n, generator=g)
+    gw, gb = torch.rand(n, generator=g) + 0.5, torch.randn(n, generator=g)
+    cx, cw, cb, cgw, cgb = x.cuda(), w.cuda(), b.cuda(), gw.cuda(), gb.cuda()
+    lib = _lib.lib()
+
+    def run():
+        if groups:
+            return GF.linear_group_norm(cx, cw, cb, cgw, cgb, groups, negative_slope=0.1)
+        return GF.linear(cx, cw, cb, relu=True)
+    try:
+        lib.geob200_set_linear_persistent(0)
+        one = run()
+        lib.geob200_set_linear_persistent(1)
+        per = run()
+        per2 = run()
+    finally:
+        lib.geob200_set_linear_persistent(0)
+    y = F.linear(x.double(), w.double(), b.double())
+    want = F.leaky_relu(F.group_norm(y.t().unsqueeze(0), groups, gw.double(), gb.double(), 1e-5).squeeze(0).t(), 0.1).float() if groups \
+        else F.relu(y).float()
+    close(one, want, 3e-5, 'one CTA per tile')
+    assert torch.equal(per, one), float((per - one).abs().max())
+    assert torch.equal(per, per2)
+
+
 def test_linear_column_slice_input():
     g = torch.Generator().manual_seed(1)
     x, w = torch.randn(50, 256, generator=g), torch.randn(64, 64, generator=g)

@@ -12,6 +12,10 @@ from geotransformer_b200 import functional as GF
 SHAPES = [(40000, 64, 32), (40000, 480, 32), (40000, 32, 128), (40000, 64, 128), (12000, 960, 64), (12000, 64, 256), (3400, 1920, 128),
           (3400, 128, 512), (640, 3840, 256), (640, 256, 1024), (640, 1024, 256), (640, 256, 768), (320, 256, 256), (640, 256, 512)]
 print('root', ROOT)
+if os.environ.get('GEOB200_LINEAR_PERSISTENT'):
+    from geotransformer_b200 import _lib
+    _lib.lib().geob200_set_linear_persistent(1)
+    print('persistent tile loop ON')
 for m, k, n in SHAPES:
     x = torch.randn(m, k, device='cuda')
     w = torch.randn(n, k, device='cuda')
