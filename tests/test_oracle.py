@@ -82,6 +82,27 @@ def test_forward_restatement_matches_reference_fixture(golden, models):
         assert abs(float(metrics[name]) - v) < (1e-3 if name == 'RRE' else 1e-5), name
 
 
+def test_evaluator_variants_match_reference_fixture(golden, models):
+    """the three Evaluator variants (3DMatch / KITTI / ModelNet, loss.py:95-159) of the restatement on the demo pair vs the
+    numbers the real reference Evaluators produced on the same outputs"""
+    from geotransformer_b200.config import make_cfg
+    cfg, sd, _ = models('3dmatch')
+    gold = golden('demo2k')
+    pair = make_pair('demo2k', 0)
+    data = G.collate_pair(pair, cfg, gold['neighbor_limits'].tolist())
+    for key in ('neighbors', 'subsampling', 'upsampling'):
+        for i in range(len(data[key])):
+            data[key][i] = torch.from_numpy(gold[f'{key}_{i}'].astype(np.int64))      # the reference's exact-tie order
+    with torch.no_grad():
+        out = G.forward(sd, cfg, data)
+    assert np.array_equal(out['gt_node_corr_indices'].numpy(), gold['gt_node_corr_indices'])
+    for variant, suffix in (('3dmatch', ''), ('kitti', '_kitti'), ('modelnet', '_modelnet')):
+        metrics = G.evaluate(make_cfg(variant), out, data['transform'])
+        assert sorted(metrics) == gold['metric_names' + suffix].tolist()
+        for name, v in zip(gold['metric_names' + suffix].tolist(), gold['metric_values' + suffix]):
+            assert abs(float(metrics[name]) - v) < (1e-3 if name == 'RRE' else 1e-5), (variant, name)
+
+
 def test_calibration_restatement_matches_reference_fixture(golden, models):
     """calibrate_neighbors_stack_mode (utils/data.py:190-217): restatement vs the limits the real reference computed"""
     cfg, _, _ = models('3dmatch')
