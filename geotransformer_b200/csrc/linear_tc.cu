@@ -15,6 +15,7 @@
 //                              warp butterfly, written as per-tile partials in double)
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -684,7 +685,8 @@ int linear_tc(const float* x, int64_t ldx, const float* w, int64_t ldw, const fl
         rec.m = m; rec.n = n; rec.k = k;
         cudaEventRecord(rec.a, st);
     }
-    const bool persistent = g_persistent_on && splits == 1 && tiles > num_sms();
+    static const bool env_persistent = [] { const char* e = getenv("GEOB200_LINEAR_PERSISTENT"); return e != nullptr && e[0] == '1'; }();
+    const bool persistent = (g_persistent_on || env_persistent) && splits == 1 && tiles > num_sms();
     if (persistent) {
         static bool pset = false;
         if (!pset) {
