@@ -605,7 +605,7 @@ static std::vector<ProfRec> g_prof;
 static std::mutex g_prof_mu;
 static bool g_prof_on = false;
 static bool g_splitk_on = true;
-static bool g_persistent_on = false;   // opt-in until validated on hardware: geob200_set_linear_persistent(1)
+static bool g_persistent_on = true;    // persistent tile loop for GEMMs of more than one wave of tiles (geob200_set_linear_persistent)
 
 // ---- split-K scratch: one grow-only buffer per stream (like a BLAS workspace; freed with the process) ---------------------
 struct SplitWs { void* ptr; size_t bytes; };

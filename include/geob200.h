@@ -227,7 +227,7 @@ int geob200_evaluate(const int64_t* gt_node_corr_indices, const float* gt_node_c
 int geob200_linear_profile_enable(int on);
 /* split-K for deep-K GEMMs on few tiles (default on); off = every tile runs its whole K loop in one CTA */
 int geob200_set_split_k(int on);
-/* persistent tile loop with two TMEM accumulator sets for GEMMs of more than one wave of tiles */
+/* persistent tile loop with two TMEM accumulator sets for GEMMs of more than one wave of tiles (default on) */
 int geob200_set_linear_persistent(int on);
 int64_t geob200_linear_profile_read(int64_t capacity, int64_t* shapes, float* ms);
 

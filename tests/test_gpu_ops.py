@@ -156,7 +156,7 @@ def test_linear_persistent_tile_loop(m, k, n, groups):
         per = run()
         per2 = run()
     finally:
-        lib.geob200_set_linear_persistent(0)
+        lib.geob200_set_linear_persistent(1)          # the default
     y = F.linear(x.double(), w.double(), b.double())
     want = F.leaky_relu(F.group_norm(y.t().unsqueeze(0), groups, gw.double(), gb.double(), 1e-5).squeeze(0).t(), 0.1).float() if groups \
         else F.relu(y).float()
