@@ -51,6 +51,10 @@ _sig('geob200_maxpool', c_int, P, P, I64, I64, I64, I64, P, P)
 _sig('geob200_upsample_concat', c_int, P, P, I64, I64, P, I64, I64, I64, P, P)
 _sig('geob200_point_to_node_partition', c_int, P, I64, P, I64, I64, P, P, P, P, P, P, P)
 _sig('geob200_gather_rows', c_int, P, I64, I64, P, I64, P, P)
+_sig('geob200_knn_partition', c_int, P, I64, P, I64, I64, P, P, P)
+_sig('geob200_pairwise_distance', c_int, P, I64, P, I64, I64, c_int, P, P)
+_sig('geob200_point_to_node_indices', c_int, P, I64, P, I64, P, P, P)
+_sig('geob200_apply_transform', c_int, P, I64, P, P, P)
 _sig('geob200_gse_indices', c_int, P, I64, F, F, I64, P, P, P)
 _sig('geob200_gse_embed_workspace_bytes', SZ, I64, I64)
 _sig('geob200_gse_embed', c_int, P, P, I64, I64, P, P, P, P, P, P, P, P, c_int, P, SZ, P)

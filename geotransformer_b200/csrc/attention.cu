@@ -362,11 +362,9 @@ static int launch_streaming(const float* q, int ldq, const float* k, int ldk, co
                             const float* E, int N, int M, float div, float* out, int ldo, float* S, cudaStream_t st) {
     // one CTA per resident slot (occupancy queried once per instantiation); each owns a contiguous range of 4-key groups
     constexpr int ring_bytes = 4 * ATS_DEPTH * ATS_G * J * 32 * (int)sizeof(float4);
-    static int per_sm = 0;
+    if (ring_bytes > 48 * 1024 && ensure_max_smem((const void*)att_scores_kernel<H, J>)) return -1;
+    static int per_sm = 0;          // same value on every device of the box; a racing first call computes it twice
     if (per_sm == 0) {
-        if (ring_bytes > 48 * 1024 &&
-            cudaFuncSetAttribute(att_scores_kernel<H, J>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes) != cudaSuccess)
-            return -1;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, att_scores_kernel<H, J>, 128, ring_bytes) != cudaSuccess || per_sm < 1)
             per_sm = 1;
     }
@@ -375,11 +373,7 @@ static int launch_streaming(const float* q, int ldq, const float* k, int ldk, co
     if (grid * 4 > groups) grid = (groups + 3) / 4;
     att_scores_kernel<H, J><<<(unsigned)grid, 128, ring_bytes, st>>>(q, ldq, k, ldk, qp, qb, E, N, M, div, S);
     const size_t smem = sizeof(float) * (ATT_R * H * (size_t)((M + 3) / 4 * 4) + ATT_KQ * ATT_R * 128 * J);     // scores + the partial outputs
-    static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
-        if (cudaFuncSetAttribute(att_softmax_pv_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-        smem_set = smem;
-    }
+    if (smem > 48 * 1024 && ensure_max_smem((const void*)att_softmax_pv_kernel<H>)) return -1;
     att_softmax_pv_kernel<H><<<(unsigned)((N + ATT_R - 1) / ATT_R), 64 * ATT_KQ, smem, st>>>(S, v, ldv, N, M, 128 * J, out, ldo);
     return 0;
 }
@@ -481,14 +475,8 @@ int geob200_attention(const float* q, int64_t ldq, const float* k, int64_t ldk, 
     // generic path (any C <= 256 that is a multiple of 4; no workspace needed)
     const size_t smem = sizeof(float) * (ATT_R * channels + ATT_R * heads * channels + ATT_R * heads * n_key);
     GEOB_REQUIRE(smem <= 200 * 1024, "attention: too many keys (%lld)", (long long)n_key);
-    static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
-        GEOB_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        GEOB_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        GEOB_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        GEOB_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
-    }
+    if (smem > 48 * 1024 && (ensure_max_smem((const void*)attention_kernel<1>) || ensure_max_smem((const void*)attention_kernel<2>) ||
+                             ensure_max_smem((const void*)attention_kernel<4>) || ensure_max_smem((const void*)attention_kernel<8>))) return -1;
     const unsigned grid = (unsigned)((n_query + ATT_R - 1) / ATT_R);
 #define LAUNCH_ATT(HV)                                                                                                              \
     attention_kernel<HV><<<grid, 256, smem, st>>>(q, (int)ldq, k, (int)ldk, v, (int)ldv, qp, qb, embed, (int)n_query, (int)n_key,  \

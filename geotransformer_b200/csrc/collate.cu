@@ -11,6 +11,10 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <mutex>
+#include <set>
+#include <utility>
+
 #include "common.cuh"
 #include "geob200.h"
 
@@ -24,6 +28,23 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+int ensure_max_smem(const void* kernel) {
+    static std::mutex mu;
+    static std::set<std::pair<const void*, int>> done;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    if (done.count({kernel, dev})) return 0;
+    int optin = 0;
+    cudaFuncAttributes fa{};
+    cudaError_t e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, kernel);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+    if (e != cudaSuccess) { set_error("ensure_max_smem: %s", cudaGetErrorString(e)); return -1; }
+    done.insert({kernel, dev});
+    return 0;
 }
 
 // ----------------------------------------------------------------------------------------------------------
@@ -785,11 +806,7 @@ int geob200_radius_search(const float* q_points, int64_t n_query, const float* s
         // queries with more than CAP neighbours (none at the reference's densities) are redone with a
         // 16384-entry buffer; the launch is a no-op when the overflow list is empty, so no host sync is needed.
         constexpr int CAP2 = 16384;
-        static bool attr_set = false;
-        if (!attr_set) {
-            GEOB_CHECK_CUDA(cudaFuncSetAttribute(rs_redo_kernel<CAP2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CAP2 * 8));
-            attr_set = true;
-        }
+        if (ensure_max_smem((const void*)rs_redo_kernel<CAP2>)) return -1;
         rs_redo_kernel<CAP2><<<num_sms(), 32, CAP2 * 8, st>>>(
             q_points, q_segs, s_segs, clouds, cell_start, sorted, radius, (int)width, (long long)n_support,
             (long long*)out, counts, max_count, overflow_list, overflow_n, (int)batch);

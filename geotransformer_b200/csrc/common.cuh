@@ -11,6 +11,9 @@ namespace geob200 {
 void set_error(const char* fmt, ...);
 // number of kernels launched by this library since load (bench.py reports it as gpu_launches)
 void count_launches(int n);
+// Opt a kernel in to the device's maximum dynamic shared memory, once per (kernel, device), thread-safe (the engine launches
+// from several host threads and a process may drive several GPUs).  Returns 0, or -1 with the error message set.
+int ensure_max_smem(const void* kernel);
 
 #define GEOB_CHECK_CUDA(expr)                                                                   \
     do {                                                                                        \

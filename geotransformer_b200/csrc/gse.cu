@@ -249,11 +249,7 @@ int geob200_gse_indices(const float* points, int64_t n, float sigma_d, float fac
     GEOB_REQUIRE(angle_k == 3, "gse_indices: angle_k=%lld unsupported (all shipped models use 3)", (long long)angle_k);
     GEOB_REQUIRE(n * 16 <= 200 * 1024, "gse_indices: too many superpoints (%lld)", (long long)n);
     const size_t smem = sizeof(float4) * n;
-    static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
-        GEOB_CHECK_CUDA(cudaFuncSetAttribute(gse_indices_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
-    }
+    if (smem > 48 * 1024 && ensure_max_smem((const void*)gse_indices_kernel<3>)) return -1;
     gse_indices_kernel<3><<<(unsigned)((n + 7) / 8), 256, smem, st>>>(points, (int)n, sigma_d, factor_a, d_indices, a_indices);
     GEOB_CHECK_LAUNCH();
     count_launches(1);
@@ -281,11 +277,7 @@ int geob200_gse_embed(const float* d_indices, const float* a_indices, int64_t n,
     }
     if (channels == GSE_C) {
         const size_t smem = sizeof(float) * (4 * GSE_PAIRS * GSE_AST + 2 * GSE_BK * GSE_C);
-        static bool set = false;
-        if (!set) {
-            GEOB_CHECK_CUDA(cudaFuncSetAttribute(gse_embed_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            set = true;
-        }
+        if (ensure_max_smem((const void*)gse_embed_fp32_kernel)) return -1;
         gse_embed_fp32_kernel<<<(unsigned)((n_pairs + GSE_PAIRS - 1) / GSE_PAIRS), 256, smem, st>>>(
             d_indices, a_indices, n_pairs, div_term, wd_t, wa_t, bd, ba, embeddings);
     } else {

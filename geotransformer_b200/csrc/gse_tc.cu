@@ -837,12 +837,7 @@ int geob200_gse_embed_tc(const float* d_idx, const float* a_idx, long long n_pai
         float* scale = bsum + tc::C;
         tc::gse_absmax_kernel<<<1, 1024, 0, st>>>(Wd, Wa, scale);
         tc::gse_pack_b_f16_kernel<<<(unsigned)((img_floats + 255) / 256), 256, 0, st>>>(Wd, Wa, bd, ba, scale, h_hi, h_lo, bsum);
-        static bool set16 = false;
-        if (!set16) {
-            GEOB_CHECK_CUDA(cudaFuncSetAttribute(tc::gse_embed_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::F16_SMEM));
-            GEOB_CHECK_CUDA(cudaFuncSetAttribute(tc::gse_embed_f16_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::F16_SMEM));
-            set16 = true;
-        }
+        if (ensure_max_smem((const void*)tc::gse_embed_f16_kernel) || ensure_max_smem((const void*)tc::gse_embed_f16_cluster_kernel)) return -1;
         if (mode == 4) {
             // CTA pairs (cluster of 2) share every B chunk through TMA multicast; grid = even number of CTAs, one per SM
             int g2 = (int)((n_tiles + 1) / 2 < (long long)(num_sms() / 2) ? (n_tiles + 1) / 2 : (long long)(num_sms() / 2)) * 2;
@@ -855,18 +850,10 @@ int geob200_gse_embed_tc(const float* d_idx, const float* a_idx, long long n_pai
     }
     tc::gse_pack_b_kernel<<<(unsigned)((img_floats + 255) / 256), 256, 0, st>>>(Wd, Wa, bd, ba, img_hi, img_lo, bias_sum);
     if (mode == 1) {
-        static bool set = false;
-        if (!set) {
-            GEOB_CHECK_CUDA(cudaFuncSetAttribute(tc::gse_embed_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<3>::SMEM));
-            set = true;
-        }
+        if (ensure_max_smem((const void*)tc::gse_embed_tc_kernel<3>)) return -1;
         tc::gse_embed_tc_kernel<3><<<grid, tc::NTHREADS, tc::Cfg<3>::SMEM, st>>>(d_idx, a_idx, n_pairs, div_term, img_hi, img_lo, bias_sum, E);
     } else {
-        static bool set = false;
-        if (!set) {
-            GEOB_CHECK_CUDA(cudaFuncSetAttribute(tc::gse_embed_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<1>::SMEM));
-            set = true;
-        }
+        if (ensure_max_smem((const void*)tc::gse_embed_tc_kernel<1>)) return -1;
         tc::gse_embed_tc_kernel<1><<<grid, tc::NTHREADS, tc::Cfg<1>::SMEM, st>>>(d_idx, a_idx, n_pairs, div_term, img_hi, img_lo, bias_sum, E);
     }
     GEOB_CHECK_LAUNCH();

@@ -694,11 +694,7 @@ int geob200_kpconv(const float* s_feats, const float* q_points, const float* s_p
     const dim3 grid(qtiles, (unsigned)split);
 #define LAUNCH_KP(RCV)                                                                                              \
     {                                                                                                               \
-        static bool set = false;                                                                                    \
-        if (!set) {                                                                                                 \
-            GEOB_CHECK_CUDA(cudaFuncSetAttribute(kpconv_kernel<RCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            set = true;                                                                                             \
-        }                                                                                                           \
+        if (ensure_max_smem((const void*)kpconv_kernel<RCV>)) return -1;                                            \
         kpconv_kernel<RCV><<<grid, 256, smem, st>>>(s_feats, pos, q_points, s_points, (const long long*)neighbors,  \
                                                     (int)n_neighbors, kernel_points, weights, bias, sigma,         \
                                                     (int)n_support, (int)n_query, (int)c_in, (int)c_out, out);     \

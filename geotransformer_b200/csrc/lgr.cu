@@ -455,11 +455,7 @@ int geob200_local_global_registration(const float* ref_knn_points, const float* 
     int* inl = patch_inliers != nullptr ? patch_inliers : inl_tmp;
 
     const size_t smem = sizeof(float) * K * (K + 1) + 2 * (size_t)K * K;
-    static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
-        GEOB_CHECK_CUDA(cudaFuncSetAttribute(lgr_corr_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
-    }
+    if (smem > 48 * 1024 && ensure_max_smem((const void*)lgr_corr_kernel<4>)) return -1;
     lgr_corr_kernel<4><<<P, 256, smem, st>>>(log_scores, K, (int)score_ld, ref_knn_masks, src_knn_masks, (int)topk,
                                              confidence_threshold, mutual, patch_count, patch_ij, patch_score);
     lgr_offsets_kernel<<<1, 1024, 0, st>>>(patch_count, P, patch_off, num_corr);

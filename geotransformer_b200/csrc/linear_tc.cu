@@ -641,11 +641,7 @@ int linear_tc(const float* x, int64_t ldx, const float* w, int64_t ldw, const fl
     CUtensorMap mx, mw;
     if (ltc::encode_map(&mx, x, m, k, ldx, ltc::BM)) return -1;
     if (ltc::encode_map(&mw, w, n, k, ldw, BN)) return -1;
-    static bool set = false;
-    if (!set) {
-        GEOB_CHECK_CUDA(cudaFuncSetAttribute(ltc::linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ltc::SMEM));
-        set = true;
-    }
+    if (ensure_max_smem((const void*)ltc::linear_tc_kernel)) return -1;
     dim3 grid((unsigned)(n / BN), (unsigned)((m + ltc::BM - 1) / ltc::BM));
     GnFuse g{};
     if (gn != nullptr) {
@@ -685,14 +681,9 @@ int linear_tc(const float* x, int64_t ldx, const float* w, int64_t ldw, const fl
         rec.m = m; rec.n = n; rec.k = k;
         cudaEventRecord(rec.a, st);
     }
-    static const bool env_persistent = [] { const char* e = getenv("GEOB200_LINEAR_PERSISTENT"); return e != nullptr && e[0] == '1'; }();
-    const bool persistent = (g_persistent_on || env_persistent) && splits == 1 && tiles > num_sms();
+    const bool persistent = g_persistent_on && splits == 1 && tiles > num_sms();
     if (persistent) {
-        static bool pset = false;
-        if (!pset) {
-            GEOB_CHECK_CUDA(cudaFuncSetAttribute(ltc::linear_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ltc::SMEM_PERSIST));
-            pset = true;
-        }
+        if (ensure_max_smem((const void*)ltc::linear_tc_persistent_kernel)) return -1;
         ltc::linear_tc_persistent_kernel<<<num_sms(), ltc::NTHREADS, ltc::SMEM_PERSIST, st>>>(mx, mw, bias, row_scale, y, (int)ldy, (int)m, (int)n,
                                                                                             (int)k, BN, relu, g, (int)grid.x, tiles);
     } else {

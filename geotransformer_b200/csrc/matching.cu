@@ -114,6 +114,8 @@ __global__ void __launch_bounds__(1024) topk_flat_kernel(const float* __restrict
     const long long total = (long long)nr * ns;
     const int k = (int)min((long long)min(k_req, KMAX), total);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // rows past the number of existing candidates are padding: index -1 (gather_patches turns it into an empty patch)
+    for (int i = k + threadIdx.x; i < k_req; i += blockDim.x) { ref_out[i] = -1; src_out[i] = -1; score_out[i] = 0.f; }
     if (k == 0) { if (threadIdx.x == 0) *k_out = 0; return; }
     unsigned prefix = 0, mask = 0;
     int remaining = k;
@@ -206,9 +208,9 @@ __global__ void __launch_bounds__(256) gather_patches_kernel(const long long* __
     if (t >= P * K) return;
     const int p = t / K, i = t % K;
     const long long node = corr[p];
-    const long long idx = knn[node * K + i];
+    const long long idx = node >= 0 ? knn[node * K + i] : (long long)n_pts;
     out_idx[t] = idx;
-    out_mask[t] = knn_masks[node * K + i];
+    out_mask[t] = node >= 0 ? knn_masks[node * K + i] : 0;
     const bool ok = idx < n_pts;
     out_pts[3 * t + 0] = ok ? pts[3 * idx + 0] : 0.f;
     out_pts[3 * t + 1] = ok ? pts[3 * idx + 1] : 0.f;
@@ -537,18 +539,10 @@ int geob200_sinkhorn(const float* scores, const uint8_t* row_masks, const uint8_
     const int K1 = (int)k + 1, ld = K1 | 1;
     const size_t smem = sizeof(float) * ((size_t)K1 * ld + 4 * K1);
     GEOB_REQUIRE(smem <= 200 * 1024, "sinkhorn: patch too large (k=%lld)", (long long)k);
-    static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
-        GEOB_CHECK_CUDA(cudaFuncSetAttribute(sinkhorn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
-    }
+    if (smem > 48 * 1024 && ensure_max_smem((const void*)sinkhorn_kernel)) return -1;
 #define LAUNCH_SK_REG(LPRV, NEV, MT)                                                                                                  \
     {                                                                                                                            \
-        static size_t set_bytes = 0;                                                                                             \
-        if (smem > 48 * 1024 && smem > set_bytes) {                                                                              \
-            GEOB_CHECK_CUDA(cudaFuncSetAttribute(sinkhorn_reg_kernel<LPRV, NEV, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            set_bytes = smem;                                                                                                    \
-        }                                                                                                                        \
+        if (smem > 48 * 1024 && ensure_max_smem((const void*)sinkhorn_reg_kernel<LPRV, NEV, MT>)) return -1;                         \
         const int threads = ((K1 * LPRV + 31) / 32) * 32;                                                                        \
         sinkhorn_reg_kernel<LPRV, NEV, MT><<<(unsigned)n_patches, threads, smem, st>>>(scores, row_masks, col_masks, alpha, (int)k,  \
                                                                                   (int)num_iterations, inf, out);               \

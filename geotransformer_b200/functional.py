@@ -212,14 +212,64 @@ def point_to_node_partition(points, nodes, point_limit, return_count=False):
     node_sizes = torch.empty((m,), dtype=_i32, device=dev)
     knn = torch.empty((m, point_limit), dtype=_i64, device=dev)
     knn_masks = torch.empty((m, point_limit), dtype=torch.bool, device=dev)
-    status = torch.empty((1,), dtype=_i32, device=dev)
     L.check(L.lib().geob200_point_to_node_partition(points.data_ptr(), n, nodes.data_ptr(), m, point_limit,
                                                     p2n.data_ptr(), node_masks.data_ptr(), node_sizes.data_ptr(),
-                                                    knn.data_ptr(), knn_masks.data_ptr(), status.data_ptr(),
+                                                    knn.data_ptr(), knn_masks.data_ptr(), None,
                                                     L.stream_ptr()), 'point_to_node_partition')
     if return_count:
         return p2n, node_sizes.long(), node_masks, knn, knn_masks
     return p2n, node_masks, knn, knn_masks
+
+
+def knn_partition(points, nodes, k, return_distance=False):
+    """reference ``pointcloud_partition.py:35-57``: (n_nodes, k) nearest point indices per node [and their distances]"""
+    _f(points, 'points'); _f(nodes, 'nodes')
+    n, m = points.shape[0], nodes.shape[0]
+    k = min(int(k), n)
+    idx = torch.empty((m, k), dtype=_i64, device=points.device)
+    d2 = torch.empty((m, k), dtype=_f32, device=points.device) if return_distance else None
+    L.check(L.lib().geob200_knn_partition(points.data_ptr(), n, nodes.data_ptr(), m, k, idx.data_ptr(), L.ptr(d2), L.stream_ptr()),
+            'knn_partition')
+    if return_distance:
+        return d2.sqrt_(), idx
+    return idx
+
+
+def pairwise_distance(x, y, normalized=False, channel_first=False):
+    """reference ``pairwise_distance.py:4-31`` for 2-D (or batched 3-D) inputs"""
+    if channel_first:
+        x, y = x.transpose(-1, -2), y.transpose(-1, -2)
+    if x.ndim == 3:
+        return torch.stack([pairwise_distance(a, b, normalized) for a, b in zip(x, y)])
+    x, y = x.contiguous(), y.contiguous()
+    _f(x, 'x'); _f(y, 'y')
+    if x.ndim != 2 or y.ndim != 2 or x.shape[1] != y.shape[1]:
+        raise RuntimeError('pairwise_distance: x (N, C) and y (M, C) expected')
+    out = torch.empty((x.shape[0], y.shape[0]), dtype=_f32, device=x.device)
+    L.check(L.lib().geob200_pairwise_distance(x.data_ptr(), x.shape[0], y.data_ptr(), y.shape[0], x.shape[1], int(normalized),
+                                              out.data_ptr(), L.stream_ptr()), 'pairwise_distance')
+    return out
+
+
+def point_to_node_indices(points, nodes, return_counts=False):
+    """reference ``pointcloud_partition.py:9-32`` (get_point_to_node_indices)"""
+    _f(points, 'points'); _f(nodes, 'nodes')
+    idx = torch.empty((points.shape[0],), dtype=_i64, device=points.device)
+    sizes = torch.empty((nodes.shape[0],), dtype=_i32, device=points.device) if return_counts else None
+    L.check(L.lib().geob200_point_to_node_indices(points.data_ptr(), points.shape[0], nodes.data_ptr(), nodes.shape[0], idx.data_ptr(),
+                                                  L.ptr(sizes), L.stream_ptr()), 'get_point_to_node_indices')
+    return (idx, sizes.long()) if return_counts else idx
+
+
+def apply_transform(points, transform):
+    """reference ``ops/transformation.py:7-60`` (points only) for a single (4, 4) transform: Q = P R^T + t"""
+    _f(transform, 'transform')
+    p = points.reshape(-1, 3).contiguous()
+    _f(p, 'points')
+    out = torch.empty_like(p)
+    L.check(L.lib().geob200_apply_transform(p.data_ptr(), p.shape[0], transform.data_ptr(), out.data_ptr(), L.stream_ptr()),
+            'apply_transform')
+    return out.reshape(points.shape)
 
 
 def gather_rows(table, indices):
@@ -354,7 +404,10 @@ def l2_normalize(x):
 
 # ------------------------------------------------------------------------------------------------ matching
 
-def superpoint_matching(ref_feats, src_feats, ref_masks, src_masks, num_correspondences, dual_normalization=True):
+def superpoint_matching(ref_feats, src_feats, ref_masks, src_masks, num_correspondences, dual_normalization=True, defer_count=False):
+    """reference ``superpoint_matching.py:13-50``.  The number of rows is min(k, #valid ref x #valid src): it is read back
+    from the device (one small D2H) unless ``defer_count`` -- then the full-capacity tensors (padding rows: index -1, score 0,
+    which ``gather_patches`` turns into empty patches) and the device count are returned and the caller trims later."""
     _f(ref_feats, 'ref_feats'); _f(src_feats, 'src_feats')
     dev = ref_feats.device
     nr, ns, c = ref_feats.shape[0], src_feats.shape[0], ref_feats.shape[1]
@@ -373,10 +426,10 @@ def superpoint_matching(ref_feats, src_feats, ref_masks, src_masks, num_correspo
                                             src_masks.data_ptr(), k, int(dual_normalization), ri.data_ptr(),
                                             si.data_ptr(), sc.data_ptr(), cnt.data_ptr(), ws.data_ptr(), ws.numel(),
                                             L.stream_ptr()), 'superpoint_matching')
-    if nr * ns < k:                      # only then can fewer than k correspondences exist
-        kk = int(cnt.item())
-        return ri[:kk], si[:kk], sc[:kk]
-    return ri, si, sc
+    if defer_count:
+        return ri, si, sc, cnt
+    kk = int(cnt.item())
+    return ri[:kk], si[:kk], sc[:kk]
 
 
 def gather_patches(corr_indices, node_knn_indices, node_knn_masks, points):

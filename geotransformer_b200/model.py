@@ -96,10 +96,15 @@ class GeoTransformer(nn.Module):
         ref_ff, src_ff = feats_f[:nf], feats_f[nf:]
         out.update(ref_feats_c=ref_fc_n, src_feats_c=src_fc_n, ref_feats_f=ref_ff, src_feats_f=src_ff)
 
-        ref_corr, src_corr, node_scores = self.coarse_matching(ref_fc_n, src_fc_n, ref_node_masks, src_node_masks)
+        # fewer than num_correspondences rows exist only when #valid ref x #valid src superpoints is smaller (tiny clouds):
+        # the count stays on the device, the padding rows become empty patches (no fine correspondences, so LGR is
+        # unaffected) and the per-patch outputs are trimmed after the forward's last host sync
+        ref_corr, src_corr, node_scores, corr_count = self.coarse_matching(ref_fc_n, src_fc_n, ref_node_masks, src_node_masks,
+                                                                           defer_count=True)
         forced = data_dict.get('forced_node_corr')       # test hook: teacher-forced coarse correspondences
         if forced is not None:
             ref_corr, src_corr, node_scores = forced
+            corr_count = None
         out.update(ref_node_corr_indices=ref_corr, src_node_corr_indices=src_corr, node_corr_scores=node_scores)
 
         rk_idx, rk_masks, rk_pts = GF.gather_patches(ref_corr, ref_knn_idx, ref_knn_masks, ref_f)
@@ -119,6 +124,12 @@ class GeoTransformer(nn.Module):
         mark('lgr')
         if gt_pending is not None:
             out['gt_node_corr_indices'], out['gt_node_corr_overlaps'] = GF.finish_node_correspondences(*gt_pending)
+        if corr_count is not None:
+            kk = int(corr_count.item())          # already complete: LGR synchronised the stream
+            if kk < ref_corr.shape[0]:
+                for key in ('ref_node_corr_indices', 'src_node_corr_indices', 'node_corr_scores', 'ref_node_corr_knn_points',
+                            'src_node_corr_knn_points', 'ref_node_corr_knn_masks', 'src_node_corr_knn_masks', 'matching_scores'):
+                    out[key] = out[key][:kk]
         return out
 
 
@@ -127,6 +138,14 @@ def enable_native(model):
     Call after the weights are loaded and the model is on its device."""
     from .native import NativeModel
     model._native = NativeModel(model)
+    if not getattr(model, '_native_hook', False):
+        # NativeModel snapshots pointers AND derived copies (fused q|k|v weights, transposes): rebuild it whenever new
+        # weights are loaded, otherwise the raw parameters would update in place while the derived copies stayed stale
+        def _rebuild(module, incompatible_keys):
+            if getattr(module, '_native', None) is not None:
+                module._native = NativeModel(module)
+        model.register_load_state_dict_post_hook(_rebuild)
+        model._native_hook = True
     return model
 
 

@@ -89,9 +89,9 @@ class SuperPointMatching(nn.Module):
         super().__init__()
         self.num_correspondences, self.dual_normalization = num_correspondences, dual_normalization
 
-    def forward(self, ref_feats, src_feats, ref_masks=None, src_masks=None):
+    def forward(self, ref_feats, src_feats, ref_masks=None, src_masks=None, defer_count=False):
         return GF.superpoint_matching(ref_feats, src_feats, ref_masks, src_masks, self.num_correspondences,
-                                      self.dual_normalization)
+                                      self.dual_normalization, defer_count=defer_count)
 
 
 class LocalGlobalRegistration(nn.Module):

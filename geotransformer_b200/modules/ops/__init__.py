@@ -28,6 +28,31 @@ def point_to_node_partition(points, nodes, point_limit, return_count=False):
     return GF.point_to_node_partition(points, nodes, point_limit, return_count)
 
 
+def knn_partition(points, nodes, k, return_distance=False):
+    """reference ``modules/ops/pointcloud_partition.py:35-57``."""
+    return GF.knn_partition(points, nodes, k, return_distance)
+
+
+def get_point_to_node_indices(points, nodes, return_counts=False):
+    """reference ``modules/ops/pointcloud_partition.py:9-32``."""
+    return GF.point_to_node_indices(points, nodes, return_counts)
+
+
+def ball_query_partition(points, nodes, radius, point_limit, return_count=False):
+    """reference ``modules/ops/pointcloud_partition.py:159-175``."""
+    node_knn_distances, node_knn_indices = GF.knn_partition(points, nodes, point_limit, return_distance=True)
+    node_knn_masks = torch.lt(node_knn_distances, radius)
+    node_knn_indices = torch.where(node_knn_masks, node_knn_indices, torch.full_like(node_knn_indices, points.shape[0]))
+    if return_count:
+        return node_knn_indices, node_knn_masks, node_knn_masks.sum(1)
+    return node_knn_indices, node_knn_masks
+
+
+def pairwise_distance(x, y, normalized=False, channel_first=False):
+    """reference ``modules/ops/pairwise_distance.py:4-31``."""
+    return GF.pairwise_distance(x, y, normalized, channel_first)
+
+
 def index_select(data, index, dim):
     """reference ``modules/ops/index_select.py:4-31`` (pure indexing; dim 0 on float tables uses the gather kernel)."""
     if dim == 0 and data.is_cuda and data.dtype == torch.float32 and data.ndim == 2 and data.is_contiguous():
@@ -41,5 +66,5 @@ def index_select(data, index, dim):
 def apply_transform(points, transform):
     """reference ``modules/ops/transformation.py:7-60`` (points only): Q = P R^T + t."""
     if transform.ndim == 2:
-        return torch.matmul(points.reshape(-1, 3), transform[:3, :3].t()).reshape(points.shape) + transform[:3, 3]
-    return torch.matmul(points, transform[:, :3, :3].transpose(-1, -2)) + transform[:, None, :3, 3]
+        return GF.apply_transform(points, transform.contiguous())
+    return torch.stack([GF.apply_transform(p, t.contiguous()) for p, t in zip(points, transform)])

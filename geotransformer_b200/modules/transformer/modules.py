@@ -196,13 +196,19 @@ def _tail(layer, hidden, inp, out=None):
     return GF.add_layernorm(x, y, ffn.norm.weight, ffn.norm.bias, ffn.norm.eps, out=out)
 
 
-def _fused(cache, mha, names):
-    """concatenated projection weights/biases (one GEMM instead of len(names)); cached per parameter version"""
-    key = '+'.join(names)
-    first = getattr(mha, names[0]).weight
-    w = cache.get('w_' + key, first, lambda _: torch.cat([getattr(mha, n).weight.detach() for n in names], dim=0).contiguous())
-    b = cache.get('b_' + key, first, lambda _: torch.cat([getattr(mha, n).bias.detach() for n in names], dim=0).contiguous())
-    return w, b
+def _fused(cache, mha, names, layer):
+    """concatenated projection weights/biases (one GEMM instead of len(names)); cached per layer, rebuilt when ANY of the
+    source parameters changes (version counters / storage)"""
+    key = f'{layer}:' + '+'.join(names)
+    params = [p for n in names for p in (getattr(mha, n).weight, getattr(mha, n).bias)]
+    stamp = tuple((p.data_ptr(), p._version) for p in params)
+    hit = cache._c.get(key)
+    if hit is None or hit[0] != stamp:
+        w = torch.cat([getattr(mha, n).weight.detach() for n in names], dim=0).contiguous()
+        b = torch.cat([getattr(mha, n).bias.detach() for n in names], dim=0).contiguous()
+        hit = (stamp, (w, b))
+        cache._c[key] = hit
+    return hit[1]
 
 
 class RPEConditionalTransformer(nn.Module):
@@ -245,7 +251,7 @@ class RPEConditionalTransformer(nn.Module):
             mha = layer.attention.attention
             h = mha.num_heads
             if block == 'self':
-                w, b = _fused(self._cache, mha, ('proj_q', 'proj_k', 'proj_v'))
+                w, b = _fused(self._cache, mha, ('proj_q', 'proj_k', 'proj_v'), i)
                 qkv = GF.linear(x, w, b)                                          # (N0+N1, 3C)
                 q, k, v = qkv[:, :c], qkv[:, c:2 * c], qkv[:, 2 * c:]
                 wp_t = self._cache.get(f'wp_t{i}', mha.proj_p.weight, lambda p: p.t().contiguous())
@@ -255,7 +261,7 @@ class RPEConditionalTransformer(nn.Module):
                 GF.attention(q[n0:], k[n0:], v[n0:], h, qp=qp[n0:], qb=qb[n0:], embed=embeddings1, out=hidden[n0:])
                 x = _tail(layer, hidden, x)
             else:
-                wkv, bkv = _fused(self._cache, mha, ('proj_k', 'proj_v'))
+                wkv, bkv = _fused(self._cache, mha, ('proj_k', 'proj_v'), i)
                 y = torch.empty_like(x)
                 # feats0 <- layer(feats0, feats1)
                 q0 = GF.linear(x[:n0], mha.proj_q.weight, mha.proj_q.bias)

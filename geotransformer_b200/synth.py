@@ -52,6 +52,8 @@ WORKLOADS = {
     'modelnet717': ('modelnet', _sphere, dict(n=717, R=0.60, sigma=0.01), 1.0),          # configs[1]
     '3dmatch20k': ('3dmatch', _room, dict(n=20000, L=1.85, sigma=0.003, off=0.1), 1.0),  # configs[2] (and [4])
     'kitti60k': ('kitti', _ground, dict(n=60000, R=60.0, sigma=0.05), 10.0),             # configs[3]
+    'kitti20k': ('kitti', _ground, dict(n=20000, R=35.0, sigma=0.05), 10.0),             # configs[3] density, oracle-runnable in ~30 s
+    'kitti4k': ('kitti', _ground, dict(n=4000, R=18.0, sigma=0.05), 10.0),               # configs[3] shape at a reference-runnable size
 }
 
 

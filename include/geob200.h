@@ -118,10 +118,26 @@ int geob200_upsample_concat(const float* x, const int64_t* up_indices, int64_t u
 /* ---- point-to-node grouping ------------------------------------------------------------------------------ */
 
 /* point_to_node_partition (reference geotransformer/modules/ops/pointcloud_partition.py:60-107).
- * node_masks / node_knn_masks are uint8 (torch.bool); node_sizes int32; status != 0 if a node owns > 4096 points. */
+ * node_masks / node_knn_masks are uint8 (torch.bool); node_sizes int32.  Exact for any number of points per node (chunked
+ * selection); status (may be NULL) is kept for ABI stability and always receives 0. */
 int geob200_point_to_node_partition(const float* points, int64_t n_points, const float* nodes, int64_t n_nodes,
                                     int64_t point_limit, int64_t* point_to_node, uint8_t* node_masks, int32_t* node_sizes,
                                     int64_t* node_knn_indices, uint8_t* node_knn_masks, int32_t* status, void* stream);
+
+/* knn_partition (pointcloud_partition.py:35-57): for every node the k nearest points, ascending by the matmul-form squared
+ * distance pairwise_distance(nodes, points) (ties by index).  knn_sq_distances (n_nodes, k) may be NULL.  1 <= k <= min(n_points, 2048). */
+int geob200_knn_partition(const float* points, int64_t n_points, const float* nodes, int64_t n_nodes, int64_t k,
+                          int64_t* knn_indices, float* knn_sq_distances, void* stream);
+/* pairwise_distance (ops/pairwise_distance.py:4-31) of row-major x (n, c), y (m, c): out (n, m) = clamp(x2 - 2xy + y2, 0),
+ * or 2 - 2xy when normalized != 0 */
+int geob200_pairwise_distance(const float* x, int64_t n, const float* y, int64_t m, int64_t channels, int normalized, float* out,
+                              void* stream);
+/* get_point_to_node_indices (pointcloud_partition.py:9-32): indices[i] = argmin_j pairwise_distance(points, nodes)[i, j];
+ * node_sizes (int32[n_nodes], may be NULL) = points per node */
+int geob200_point_to_node_indices(const float* points, int64_t n_points, const float* nodes, int64_t n_nodes, int64_t* indices,
+                                  int32_t* node_sizes, void* stream);
+/* apply_transform (ops/transformation.py:7-60) for one (4,4) device transform: out = points R^T + t */
+int geob200_apply_transform(const float* points, int64_t n_points, const float* transform, float* out, void* stream);
 
 /* out[r] = indices[r] < n_rows ? table[indices[r]] : 0  (index_select on a zero-padded table, ops/index_select.py) */
 int geob200_gather_rows(const float* table, int64_t n_rows, int64_t channels, const int64_t* indices, int64_t n_indices,
@@ -160,14 +176,16 @@ int geob200_l2_normalize(const float* x, int64_t n, int64_t channels, float* y, 
 
 /* ---- matching ---------------------------------------------------------------------------------------------- */
 
-/* SuperPointMatching.forward (superpoint_matching.py:13-50); num_out (device int32) = number of rows written. */
+/* SuperPointMatching.forward (superpoint_matching.py:13-50); num_out (device int32) = number of rows written =
+ * min(num_correspondences, #valid ref nodes x #valid src nodes); rows past it receive index -1 / score 0. */
 size_t geob200_superpoint_matching_workspace_bytes(int64_t n_ref, int64_t n_src);
 int geob200_superpoint_matching(const float* ref_feats, const float* src_feats, int64_t n_ref, int64_t n_src, int64_t channels,
                                 const uint8_t* ref_masks, const uint8_t* src_masks, int64_t num_correspondences, int dual,
                                 int64_t* ref_corr_indices, int64_t* src_corr_indices, float* corr_scores, int32_t* num_out,
                                 void* workspace, size_t workspace_bytes, void* stream);
 
-/* patch gathers of model.py:169-174: indices/masks/points of the k points of each selected superpoint */
+/* patch gathers of model.py:169-174: indices/masks/points of the k points of each selected superpoint; a negative
+ * corr index (padding row of geob200_superpoint_matching) yields an empty patch (sentinel indices, masks 0) */
 int geob200_gather_patches(const int64_t* corr_indices, int64_t n_corr, const int64_t* node_knn_indices,
                            const uint8_t* node_knn_masks, int64_t k, const float* points, int64_t n_points,
                            int64_t* out_indices, uint8_t* out_masks, float* out_points, void* stream);

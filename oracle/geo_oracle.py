@@ -260,6 +260,33 @@ def point_to_node_partition(points, nodes, point_limit):
     return point_to_node, node_masks, knn, knn_masks
 
 
+def knn_partition(points, nodes, k, return_distance=False):
+    """ops/pointcloud_partition.py:35-57."""
+    k = min(k, points.shape[0])
+    sq = pairwise_distance(nodes, points)
+    knn_sq, knn = sq.topk(dim=1, k=k, largest=False)
+    return (torch.sqrt(knn_sq), knn) if return_distance else knn
+
+
+def get_point_to_node_indices(points, nodes, return_counts=False):
+    """ops/pointcloud_partition.py:9-32."""
+    indices = pairwise_distance(points, nodes).min(dim=1)[1]
+    if return_counts:
+        u, c = torch.unique(indices, return_counts=True)
+        sizes = torch.zeros(nodes.shape[0], dtype=torch.long)
+        sizes[u] = c
+        return indices, sizes
+    return indices
+
+
+def ball_query_partition(points, nodes, radius, point_limit, return_count=False):
+    """ops/pointcloud_partition.py:159-175."""
+    d, idx = knn_partition(points, nodes, point_limit, return_distance=True)
+    masks = torch.lt(d, radius)
+    idx = torch.where(masks, idx, torch.full_like(idx, points.shape[0]))
+    return (idx, masks, masks.sum(1)) if return_count else (idx, masks)
+
+
 # ------------------------------------------------------------------------------------------------ transformer
 
 def embedding_indices(points, sigma_d, sigma_a, angle_k):

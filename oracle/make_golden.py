@@ -22,16 +22,10 @@ from geotransformer_b200.config import make_cfg                     # noqa: E402
 from geotransformer_b200.model import create_model                  # noqa: E402
 from geotransformer_b200.synth import make_pair                     # noqa: E402
 from geotransformer_b200.weights import synthetic_state_dict        # noqa: E402
-from oracle import geo_oracle, ref_ext, ref_harness                 # noqa: E402
+from oracle import fixture, geo_oracle, ref_ext, ref_harness        # noqa: E402
 
 GOLD = os.path.join(ROOT, 'tests', 'golden')
-LIMITS = {'demo2k': [38, 36, 36, 38], 'modelnet717': [13, 21, 27]}
-
-
-def sample_rows(t, n=64):
-    t = t.detach()
-    idx = np.unique(np.linspace(0, t.shape[0] - 1, num=min(n, t.shape[0])).astype(np.int64))
-    return idx, t[idx].numpy()
+LIMITS = {'demo2k': [38, 36, 36, 38], 'modelnet717': [13, 21, 27], 'kitti4k': [27, 75, 147, 157, 119]}
 
 
 def run(workload):
@@ -88,6 +82,21 @@ def run(workload):
         report[k] = (tuple(a.shape) == tuple(b.shape)) and float((a - b).abs().max()) if a.shape == b.shape else 'SHAPE'
     for k in ('ref_node_corr_indices', 'src_node_corr_indices'):
         report[k] = bool(torch.equal(o[k], ref_out[k]))
+    if not (report['ref_node_corr_indices'] and report['src_node_corr_indices']):
+        # adjacent coarse scores can sit within an ulp of each other (SURVEY.md 'hard parts': min relative gap 2e-6 with
+        # random weights) while the restatement's features differ from the reference's by 1e-7: accept a permutation
+        # between scores that agree to 1e-5 relative and compare the per-patch tensors under it
+        pos = {pr: i for i, pr in enumerate(zip(o['ref_node_corr_indices'].tolist(), o['src_node_corr_indices'].tolist()))}
+        want = list(zip(ref_out['ref_node_corr_indices'].tolist(), ref_out['src_node_corr_indices'].tolist()))
+        assert len(pos) == len(want) and set(pos) == set(want), 'coarse correspondence SETS differ'
+        perm = torch.tensor([pos[pr] for pr in want])
+        sc = o['node_corr_scores']
+        assert torch.allclose(sc[perm], sc, rtol=1e-5, atol=0), 'coarse correspondences permuted between DIFFERENT scores'
+        moved = int((perm != torch.arange(len(want))).sum())
+        print(f'[{workload}] {moved} coarse correspondences swapped between scores equal to 1e-5 relative')
+        a, b = o['matching_scores'][perm], ref_out['matching_scores']
+        report['matching_scores'] = float((a - b).abs().max())
+        report['ref_node_corr_indices'] = report['src_node_corr_indices'] = True
     # ground-truth superpoint correspondences and the Evaluator (loss.py:95-159)
     report['gt_node_corr_indices'] = bool(torch.equal(o['gt_node_corr_indices'], ref_out['gt_node_corr_indices']))
     report['gt_node_corr_overlaps'] = float((o['gt_node_corr_overlaps'] - ref_out['gt_node_corr_overlaps']).abs().max())
@@ -118,35 +127,12 @@ def run(workload):
     assert not bad, f'oracle restatement deviates from the reference: {bad}'
 
     # ---- fixtures
-    g = {}
-    for i, (p, l) in enumerate(zip(data['points'], data['lengths'])):
-        if i > 0:
-            g[f'points_{i}'] = p.numpy()
-        g[f'lengths_{i}'] = l.numpy()
-    for key in ('neighbors', 'subsampling', 'upsampling'):
-        for i, t in enumerate(data[key]):
-            g[f'{key}_{i}'] = t.numpy().astype(np.int32)
-    for k in ('feats_c', 'feats_f', 'ref_embeddings'):
-        t = taps[k]
-        idx, rows = sample_rows(t.reshape(t.shape[0], -1) if k != 'ref_embeddings' else t.reshape(-1, t.shape[-1]), 96)
-        g[k + '_rows'], g[k + '_sample'] = idx, rows
-        g[k + '_sum'] = np.array([t.double().sum().item(), t.double().abs().sum().item()])
-    for k in ('ref_feats_c', 'src_feats_c', 'estimated_transform', 'corr_scores', 'ref_corr_points', 'src_corr_points',
-              'ref_node_corr_indices', 'src_node_corr_indices'):
-        g[k] = ref_out[k].detach().numpy()
-    g['gt_node_corr_indices'] = ref_out['gt_node_corr_indices'].numpy()
-    g['gt_node_corr_overlaps'] = ref_out['gt_node_corr_overlaps'].numpy()
+    g = fixture.pack(data, taps, ref_out, o['node_corr_scores'], limits)
     g['metric_names'] = np.array(sorted(ref_metrics))
     g['metric_values'] = np.array([ref_metrics[k] for k in sorted(ref_metrics)], dtype=np.float64)
     for other, rm in other_metrics.items():
         g['metric_names_' + other] = np.array(sorted(rm))
         g['metric_values_' + other] = np.array([rm[k] for k in sorted(rm)], dtype=np.float64)
-    g['node_corr_scores'] = o['node_corr_scores'].numpy()
-    idx, rows = sample_rows(ref_out['matching_scores'].reshape(ref_out['matching_scores'].shape[0], -1), 16)
-    g['matching_scores_rows'], g['matching_scores_sample'] = idx, rows
-    for k in ('ref_node_knn_indices', 'src_node_knn_indices'):
-        g[k] = taps[k].numpy().astype(np.int32)
-    g['neighbor_limits'] = np.array(limits)
     os.makedirs(GOLD, exist_ok=True)
     path = os.path.join(GOLD, workload + '.npz')
     np.savez_compressed(path, **g)
@@ -175,5 +161,5 @@ def run_calibration():
 
 if __name__ == '__main__':
     assert ref_harness.available(), 'needs /root/reference'
-    for w in (sys.argv[1:] or ['demo2k', 'modelnet717', 'calibration']):
+    for w in (sys.argv[1:] or ['demo2k', 'modelnet717', 'kitti4k', 'calibration']):
         run_calibration() if w == 'calibration' else run(w)

@@ -11,7 +11,7 @@ from oracle import geo_oracle as G
 
 pytestmark = pytest.mark.gpu
 
-CASES = [('demo2k', '3dmatch'), ('modelnet717', 'modelnet')]
+CASES = [('demo2k', '3dmatch'), ('modelnet717', 'modelnet'), ('kitti4k', 'kitti')]
 
 
 def _collate(pair, cfg, limits):
@@ -24,12 +24,10 @@ def _rows(t, idx):
     return t.reshape(-1, t.shape[-1])[torch.from_numpy(idx).to(t.device)].cpu().numpy()
 
 
-@pytest.mark.parametrize('workload,cfg_name', CASES)
-def test_collate_matches_reference(workload, cfg_name, golden, models):
-    cfg, sd, model = models(cfg_name)
-    gold = golden(workload)
-    pair = make_pair(workload, 0)
-    limits = gold['neighbor_limits'].tolist()
+def check_collate(workload, cfg, pair, gold):
+    """GPU collate vs the gold dict (reference fixture or live oracle): lengths, level points (values AND order) and all
+    3S-2 neighbour tables, bit-exact up to the order inside exact-distance tie groups"""
+    limits = np.asarray(gold['neighbor_limits']).tolist()
     data = _collate(pair, cfg, limits)
     S = cfg.backbone.num_stages
     for i in range(S):
@@ -41,21 +39,31 @@ def test_collate_matches_reference(workload, cfg_name, golden, models):
         for i, t in enumerate(data[key]):
             want = torch.from_numpy(gold[f'{key}_{i}'].astype(np.int64))
             got = t.cpu()
-            assert got.shape == want.shape, f'{key}[{i}] shape'
+            assert got.shape == want.shape, f'{key}[{i}] shape {tuple(got.shape)} vs {tuple(want.shape)}'
             if not torch.equal(got, want):     # only the order inside exact-distance tie groups may differ
                 q, s = data['points'][i + qi].cpu(), data['points'][i + si].cpu()
                 assert torch.equal(G.canonical_neighbors(q, s, got), G.canonical_neighbors(q, s, want)), f'{key}[{i}]'
                 n_tie += int((got != want).any(dim=1).sum())
     print(f'{workload}: {n_tie} rows differ from the reference only by exact-tie order')
+    return data
 
 
 @pytest.mark.parametrize('workload,cfg_name', CASES)
-def test_forward_matches_reference(workload, cfg_name, golden, models):
+def test_collate_matches_reference(workload, cfg_name, golden, models):
     cfg, sd, model = models(cfg_name)
+    check_collate(workload, cfg, make_pair(workload, 0), golden(workload))
+
+
+def check_forward(workload, cfg, model, pair, gold, native=False):
+    """stage-wise parity of the CUDA forward against the gold dict (teacher forcing where the reference itself is
+    ill-conditioned); native=True runs the C++ stage drivers (what bench.py measures)"""
     model = model.cuda().eval()
-    gold = golden(workload)
-    pair = make_pair(workload, 0)
-    limits = gold['neighbor_limits'].tolist()
+    if native:
+        from geotransformer_b200.model import enable_native
+        enable_native(model)
+    elif hasattr(model, '_native'):
+        del model._native
+    limits = np.asarray(gold['neighbor_limits']).tolist()
     data = _collate(pair, cfg, limits)
     # teacher-force the reference's neighbour tables (identical up to exact-tie order, previous test)
     for key in ('neighbors', 'subsampling', 'upsampling'):
@@ -67,6 +75,13 @@ def test_forward_matches_reference(workload, cfg_name, golden, models):
         got = _rows(taps[k], gold[k + '_rows'])
         err = np.abs(got - gold[k + '_sample']).max() / max(np.abs(gold[k + '_sample']).max(), 1.0)
         assert err < tol, f'{k}: rel err {err:.2e}'
+    # structure embedding of the reference cloud (sampled (i, j) rows): E rms ~0.6, budget 2e-5 (3-term split on tcgen05)
+    nc = data['lengths_host'][-1][0]
+    emb = model.transformer.embedding(data['points'][-1][:nc].contiguous())
+    got = _rows(emb, gold['ref_embeddings_rows'])
+    err = np.abs(got - gold['ref_embeddings_sample']).max()
+    assert err < 5e-5, f'structure embedding: abs err {err:.2e}'
+    del emb
     fl = cfg.model.fine_level
     for side, sl in (('ref', slice(0, data['lengths_host'][fl][0])), ('src', slice(data['lengths_host'][fl][0], None))):
         got = taps[f'{side}_node_knn_indices'].cpu()
@@ -171,6 +186,53 @@ def test_forward_matches_reference(workload, cfg_name, golden, models):
             f'best hypothesis {best} ({inl[best]}) vs oracle {o_best} ({inl[o_best]}), dT {dT[o_pos]:.2e} / {dT[b_pos]:.2e}'
         print(f'{workload}: hypotheses {best} / {o_best} (inliers {int(inl[best])} / {int(inl[o_best])}, near tie {near_tie}); '
               f'final transform not compared')
+    return out
+
+
+@pytest.mark.parametrize('workload,cfg_name', CASES)
+def test_forward_matches_reference(workload, cfg_name, golden, models):
+    cfg, sd, model = models(cfg_name)
+    check_forward(workload, cfg, model, make_pair(workload, 0), golden(workload))
+
+
+# ---- BASELINE.json configs 3 and 4 at full size: the pinned restatement (oracle/geo_oracle.py == the real reference with 0.0
+# difference on the committed fixtures, KITTI branch included: tests/golden/kitti4k.npz) is run LIVE on the box's host cores
+# and packed into the fixture layout, so the headline workload goes through exactly the same stage-wise checks.
+FULL = [('3dmatch20k', '3dmatch'), ('kitti20k', 'kitti')]
+_LIVE = {}
+
+
+def _live_gold(workload, cfg, sd):
+    if workload not in _LIVE:
+        from oracle import fixture
+        torch.set_num_threads(min(16, torch.get_num_threads()))
+        pair = make_pair(workload, 0)
+        limits = cfg.neighbor_limits or [27, 75, 147, 157, 119][:cfg.backbone.num_stages]
+        odata = G.collate_pair(pair, cfg, limits)
+        taps = {}
+        with torch.no_grad():
+            o = G.forward(sd, cfg, odata, taps=taps)
+        _LIVE[workload] = (pair, fixture.pack(odata, taps, o, o['node_corr_scores'], limits))
+    return _LIVE[workload]
+
+
+@pytest.mark.parametrize('workload,cfg_name', FULL)
+def test_full_size_collate_matches_oracle(workload, cfg_name, models):
+    cfg, sd, model = models(cfg_name)
+    pair, gold = _live_gold(workload, cfg, sd)
+    check_collate(workload, cfg, pair, gold)
+
+
+@pytest.mark.parametrize('workload,cfg_name', FULL)
+@pytest.mark.parametrize('native', [False, True])
+def test_full_size_forward_matches_oracle(workload, cfg_name, native, models):
+    cfg, sd, model = models(cfg_name)
+    pair, gold = _live_gold(workload, cfg, sd)
+    out = check_forward(workload, cfg, model, pair, gold, native=native)
+    # ground-truth superpoint pairs (model.py:112-126) against the oracle's: identical up to overlaps within float noise of 0
+    got = set(map(tuple, out['gt_node_corr_indices'].cpu().tolist()))
+    want = set(map(tuple, gold['gt_node_corr_indices'].tolist()))
+    assert len(got ^ want) <= max(2, len(want) // 500), f'{len(got ^ want)} of {len(want)} gt superpoint pairs differ'
 
 
 def test_full_size_properties_3dmatch20k(models):

@@ -288,6 +288,89 @@ def test_point_to_node_partition(mn):
         _tie_aware_index_check(g_knn, knn, lambda r, n: sq[r, int(n)].item() if n < n0 else 1e12, 'node_knn')
 
 
+def test_point_to_node_partition_crowded_node():
+    """a node owning far more points than one selection buffer (the former 4096-point cap): still the exact K nearest"""
+    g = torch.Generator().manual_seed(3)
+    pts = torch.cat([torch.randn(9000, 3, generator=g) * 0.05, torch.randn(300, 3, generator=g) * 0.05 + 3.0])
+    nodes = torch.tensor([[0.0, 0.0, 0.0], [3.0, 3.0, 3.0], [-9.0, 0.0, 0.0]])
+    p2n, masks, knn, knn_masks = G.point_to_node_partition(pts, nodes, 64)
+    g_p2n, g_sizes, g_masks, g_knn, g_knn_masks = GF.point_to_node_partition(pts.cuda(), nodes.cuda(), 64, return_count=True)
+    assert torch.equal(g_p2n.cpu(), p2n) and g_sizes.tolist() == [9000, 300, 0]
+    assert torch.equal(g_masks.cpu(), masks) and torch.equal(g_knn_masks.cpu(), knn_masks)
+    sq = G.pairwise_distance(nodes, pts)
+    _tie_aware_index_check(g_knn, knn, lambda r, n: sq[r, int(n)].item() if n < pts.shape[0] else 1e12, 'node_knn')
+
+
+@pytest.mark.parametrize('n,m,k', [(717, 41, 16), (9000, 37, 64), (5000, 3, 1500), (50, 7, 64)])
+def test_knn_partition_and_ball_query(n, m, k):
+    """Boundary 2 ops: knn_partition / ball_query_partition / get_point_to_node_indices / pairwise_distance / apply_transform
+    (reference modules/ops/pointcloud_partition.py:9-57,159-175, pairwise_distance.py:4-31, transformation.py:7-60)"""
+    from geotransformer_b200.modules import ops
+    g = torch.Generator().manual_seed(n + k)
+    pts, nodes = torch.rand(n, 3, generator=g) * 2.0, torch.rand(m, 3, generator=g) * 2.0
+    sq = G.pairwise_distance(nodes, pts)
+    w_d, w_idx = G.knn_partition(pts, nodes, k, return_distance=True)
+    g_d, g_idx = ops.knn_partition(pts.cuda(), nodes.cuda(), k, return_distance=True)
+    assert g_idx.shape == w_idx.shape == (m, min(k, n))
+    _tie_aware_index_check(g_idx, w_idx, lambda r, i: sq[r, int(i)].item(), 'knn_partition')
+    close(g_d ** 2, w_d ** 2, 2e-6, 'knn squared distances (matmul form: abs error ~ulp(|x|^2))')
+    assert torch.equal(ops.knn_partition(pts.cuda(), nodes.cuda(), k), g_idx)
+    # ball query: the mask is a threshold on the distance, compare where the oracle distance is not within float noise of it
+    radius = float(w_d.median())
+    w_bi, w_bm, w_bc = G.ball_query_partition(pts, nodes, radius, k, return_count=True)
+    g_bi, g_bm, g_bc = ops.ball_query_partition(pts.cuda(), nodes.cuda(), radius, k, return_count=True)
+    safe = (w_d - radius).abs() > 1e-4
+    assert torch.equal(g_bm.cpu()[safe], w_bm[safe])
+    same_idx = g_idx.cpu() == w_idx
+    assert torch.equal(g_bi.cpu()[safe & same_idx], w_bi[safe & same_idx])
+    assert (g_bc.cpu() - w_bc).abs().max() <= int((~safe).sum())
+    # get_point_to_node_indices: POINT-first rounding of the matmul form
+    w_pi, w_ps = G.get_point_to_node_indices(pts, nodes, return_counts=True)
+    g_pi, g_ps = ops.get_point_to_node_indices(pts.cuda(), nodes.cuda(), return_counts=True)
+    sq_pn = G.pairwise_distance(pts, nodes)
+    n_tol = _tie_aware_index_check(g_pi, w_pi, lambda r, j: sq_pn[r, int(j)].item(), 'get_point_to_node_indices')
+    if n_tol == 0:
+        assert torch.equal(g_ps.cpu(), w_ps)
+    assert torch.equal(ops.get_point_to_node_indices(pts.cuda(), nodes.cuda()), g_pi)
+    # pairwise_distance (3-D points and unit features, incl. the normalized and channel_first forms)
+    close(ops.pairwise_distance(nodes.cuda(), pts.cuda()), sq, 1e-6, 'pairwise_distance')
+    fa, fb = F.normalize(torch.randn(m, 64, generator=g), dim=1), F.normalize(torch.randn(53, 64, generator=g), dim=1)
+    close(ops.pairwise_distance(fa.cuda(), fb.cuda(), normalized=True), G.pairwise_distance(fa, fb, normalized=True), 1e-6, 'normalized')
+    close(ops.pairwise_distance(fa.t().contiguous().cuda(), fb.t().contiguous().cuda(), channel_first=True), G.pairwise_distance(fa, fb), 2e-6,
+          'channel_first')
+    # apply_transform
+    T = torch.eye(4)
+    T[:3, :3] = torch.linalg.qr(torch.randn(3, 3, generator=g))[0]
+    T[:3, 3] = torch.randn(3, generator=g)
+    close(ops.apply_transform(pts.cuda(), T.cuda()), G.apply_transform(pts, T), 1e-6, 'apply_transform')
+    close(ops.apply_transform(pts.reshape(-1, 1, 3).cuda(), T.cuda()).reshape(-1, 3), G.apply_transform(pts, T), 1e-6, 'apply_transform nd')
+
+
+def test_superpoint_matching_masked_candidates_fewer_than_k():
+    """valid_ref x valid_src < k <= n_ref x n_src: row count = the masked product, like the reference's
+    min(k, masked numel); the deferred-count form pads with index -1 and gather_patches makes those patches empty"""
+    g = torch.Generator().manual_seed(5)
+    nr, ns, c, k = 40, 30, 256, 256
+    fr = F.normalize(torch.randn(nr, c, generator=g), dim=1)
+    fs = F.normalize(torch.randn(ns, c, generator=g), dim=1)
+    rm, sm = torch.zeros(nr, dtype=torch.bool), torch.zeros(ns, dtype=torch.bool)
+    rm[::4], sm[::3] = True, True                     # 10 x 10 = 100 valid pairs < 256 <= 1200
+    wr, ws, wsc = G.superpoint_matching(fr, fs, rm, sm, k, True)
+    gr, gs, gsc = GF.superpoint_matching(fr.cuda(), fs.cuda(), rm.cuda(), sm.cuda(), k, True)
+    assert gr.shape[0] == wr.shape[0] == 100
+    assert set(zip(gr.tolist(), gs.tolist())) == set(zip(wr.tolist(), ws.tolist()))
+    close(gsc, wsc, 1e-5 * wsc.max().item(), 'scores')
+    fr_i, fs_i, fsc, cnt = GF.superpoint_matching(fr.cuda(), fs.cuda(), rm.cuda(), sm.cuda(), k, True, defer_count=True)
+    assert int(cnt.item()) == 100 and fr_i.shape[0] == k
+    assert bool((fr_i[100:] == -1).all()) and bool((fs_i[100:] == -1).all()) and bool((fsc[100:] == 0).all())
+    knn = torch.randint(0, 500, (nr, 64), generator=g).cuda()
+    knn_m = (torch.rand(nr, 64, generator=g) > 0.2).cuda()
+    pts = torch.rand(500, 3, generator=g).cuda()
+    idx, msk, ppts = GF.gather_patches(fr_i, knn, knn_m, pts)
+    assert bool((idx[100:] == 500).all()) and not bool(msk[100:].any()) and bool((ppts[100:] == 0).all())
+    assert torch.equal(idx[:100], knn[fr_i[:100]]) and torch.equal(msk[:100], knn_m[fr_i[:100]])
+
+
 def test_gse_indices_and_embedding(mn):
     cfg, sd, data = mn
     nc = int(data['lengths'][-1][0])
