@@ -40,7 +40,10 @@ def parse():
     ap.add_argument('--workload', default='3dmatch20k')
     ap.add_argument('--gse-mode', type=int, default=None)
     ap.add_argument('--linear-persistent', type=int, default=None, help='1/0: persistent tile loop of the tcgen05 GEMM')
-    ap.add_argument('--streams', type=int, default=4, help='pairs in flight per GPU (one CUDA stream + host thread each)')
+    ap.add_argument('--batch', type=int, default=8, help='pairs per forward (GeoTransformer.forward_batch); 1 = one pair per forward')
+    ap.add_argument('--streams', type=int, default=None,
+                    help='forwards in flight per GPU (one CUDA stream + host thread each); default 2 in batch mode, 4 with --batch 1')
+    ap.add_argument('--pairs-per-step', type=int, default=None, help='pairs per GPU and step (default 2 x batch x streams)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     return ap.parse_args()
 
@@ -82,11 +85,44 @@ class ClockSampler(threading.Thread):
 
 
 def load_peaks():
+    """(bf16 dense TF/s BURST -- the roofline kernels are timed alone --, sustained, HBM GB/s, source)"""
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
         d = json.load(open(p))
-        return d.get('bf16_tflops_sustained', d.get('bf16_tflops')), d.get('hbm_gbs'), 'measured'
-    return 1400.0, 6650.0, 'fallback'
+        return d.get('bf16_tflops'), d.get('bf16_tflops_sustained', d.get('bf16_tflops')), d.get('hbm_gbs'), 'measured'
+    return 1690.0, 1400.0, 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def measure_tf32_peak(dev):
+    """Dense TF32 tensor throughput of this GPU, measured the way MEASURED_PEAKS.json's bf16 figure was (torch.matmul 8192^3,
+    best of 10, CUDA events) with fp32 operands and allow_tf32=True.  A library GEMM as a yardstick only -- not on the product path."""
+    try:
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        n = 8192
+        a = torch.randn(n, n, device=dev)
+        b = torch.randn(n, n, device=dev)
+        c = torch.empty(n, n, device=dev)
+        best = float('inf')
+        for i in range(13):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b, out=c)
+            e1.record()
+            e1.synchronize()
+            if i >= 3:
+                best = min(best, e0.elapsed_time(e1))
+        torch.backends.cuda.matmul.allow_tf32 = prev
+        del a, b, c
+        return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+    except Exception:
+        return None
+
+
+def load_traffic():
+    """per-launch DRAM traffic of the roofline kernels from the committed ncu --set full capture (profiles/r02_dram_traffic.json)"""
+    p = os.path.join(ROOT, 'profiles', 'r02_dram_traffic.json')
+    return json.load(open(p)) if os.path.exists(p) else {}
 
 
 def make_inputs(workload, n_pairs, rank, world):
@@ -106,9 +142,62 @@ def cpu_threads():
     return max(1, min(os.cpu_count() or 1, 16))
 
 
-def cpu_reference_pairs_per_s(workload, n_pairs, threads):
-    """The reference's CPU path: its own C++ collate ops (oracle/_ref, kind 'reference') when built, else the plain-C
-    port; the model forward is the torch-CPU restatement (kind 'port').  Returns (pairs/s, seconds, description)."""
+def _stats(xs):
+    a = np.sort(np.asarray(xs, dtype=np.float64))
+    q = lambda p: float(a[min(len(a) - 1, int(round(p * (len(a) - 1))))])
+    return {'median': q(0.5), 'p10': q(0.1), 'p90': q(0.9), 'n': int(len(a))}
+
+
+def gpu_eager_port(workload, n_pairs, device):
+    """What a drop-in user of the reference sees today on this GPU (engine/single_tester.py:52-58): collate on the
+    host CPU (the reference runs it in DataLoader workers), then the model forward as EAGER torch ops on the GPU.
+    /root/reference is not on the GPU box, so the forward is the pinned torch restatement (oracle/geo_oracle.py, bit-identical
+    to the reference on CPU) executed with device tensors -- cuBLAS / ATen kernels, allow_tf32 off as in the reference.
+    Returns a dict for the bench line (never raises)."""
+    try:
+        from geotransformer_b200.config import make_cfg
+        from geotransformer_b200.model import create_model
+        from geotransformer_b200.synth import make_pair, WORKLOADS
+        from geotransformer_b200.weights import synthetic_state_dict
+        from oracle import geo_oracle as G, collate_oracle, ref_ext
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        cfg = make_cfg(WORKLOADS[workload][0])
+        sd = {k: v.to(device) for k, v in synthetic_state_dict(create_model(cfg), 7351).items()}
+        impl = ref_ext if ref_ext.available() else collate_oracle
+        limits = cfg.neighbor_limits or [27, 75, 147, 157, 119][:cfg.backbone.num_stages]
+        sync = (lambda: torch.cuda.synchronize(device)) if torch.device(device).type == 'cuda' else (lambda: None)
+        t_col, t_fwd = [], []
+        for i in range(n_pairs + 1):                    # first pair = warm-up (cuBLAS handles, allocator)
+            pair = make_pair(workload, 2000 + i)
+            t0 = time.perf_counter()
+            data = G.collate_pair(pair, cfg, limits, impl=impl)
+            t1 = time.perf_counter()
+            data = {k: ([x.to(device) if isinstance(x, torch.Tensor) else x for x in v] if isinstance(v, list) else
+                        (v.to(device) if isinstance(v, torch.Tensor) else v)) for k, v in data.items()}
+            sync()
+            t2 = time.perf_counter()
+            with torch.no_grad(), torch.device(device):
+                out = G.forward(sd, cfg, data)
+                G.evaluate(cfg, out, data['transform'])
+            sync()
+            t3 = time.perf_counter()
+            if i > 0:
+                t_col.append(t1 - t0)
+                t_fwd.append(t3 - t1)                   # H2D of the collated dict + forward + metrics
+        tot = float(np.sum(t_col) + np.sum(t_fwd))
+        return {'value': n_pairs / tot, 'unit': 'pairs/s', 'kind': 'gpu_eager_port',
+                'forward_only_pairs_per_s': n_pairs / float(np.sum(t_fwd)),
+                'collate_s': _stats(t_col), 'h2d_forward_metrics_s': _stats(t_fwd),
+                'sample': f'{n_pairs} pair(s) of {workload} after 1 warm-up pair; host-CPU collate ({"reference C++" if impl is ref_ext else "C port"}, '
+                          f'1 thread, in line) + eager torch forward of the pinned restatement on {device}, allow_tf32=False'}
+    except Exception as ex:
+        return {'value': None, 'unit': 'pairs/s', 'kind': 'gpu_eager_port', 'sample': f'failed: {type(ex).__name__}: {ex}'}
+
+
+def cpu_reference_pairs_per_s(workload, n_pairs, threads, return_times=False):
+    """The reference's CPU path: its own C++ collate ops (oracle/_ref) when built, else the plain-C port; the model forward is
+    the torch-CPU restatement (a port, pinned bit-for-bit to the reference).  Returns (pairs/s, seconds, description)."""
     from geotransformer_b200.config import make_cfg
     from geotransformer_b200.model import create_model
     from geotransformer_b200.synth import make_pair, WORKLOADS
@@ -120,6 +209,7 @@ def cpu_reference_pairs_per_s(workload, n_pairs, threads):
     impl = ref_ext if ref_ext.available() else collate_oracle
     limits = cfg.neighbor_limits or [27, 75, 147, 157, 119][:cfg.backbone.num_stages]
     t_collate = t_fwd = 0.0
+    per_pair = []
     for i in range(n_pairs):
         pair = make_pair(workload, 1000 + i)
         t0 = time.perf_counter()
@@ -131,9 +221,13 @@ def cpu_reference_pairs_per_s(workload, n_pairs, threads):
         t2 = time.perf_counter()
         t_collate += t1 - t0
         t_fwd += t2 - t1
+        per_pair.append(t2 - t0)
     total = t_collate + t_fwd
-    kind = 'reference C++ collate + torch-CPU port of the forward' if impl is ref_ext else 'port'
-    return n_pairs / total, total, f'{n_pairs} pair(s) of {workload}: collate {t_collate:.1f}s + forward {t_fwd:.1f}s ({kind})'
+    kind = 'reference C++ collate + port forward' if impl is ref_ext else 'port'
+    desc = f'{n_pairs} pair(s) of {workload}: collate {t_collate:.1f}s + forward {t_fwd:.1f}s ({kind}; one reference search per table)'
+    if return_times:
+        return n_pairs / total, total, desc, per_pair, kind
+    return n_pairs / total, total, desc
 
 
 def main():
@@ -147,16 +241,22 @@ def main():
         threads = cpu_threads()
         # bounded sample per step: 1 pair of the workload (~3 s of CPU work on 16 threads); at most 20 timed + 2 warm-up pairs
         steps = max(1, min(args.steps, 20))
-        warm = max(0, min(args.warmup, 2))
+        warm = max(0, min(args.warmup, 3))
         for _ in range(warm):
             cpu_reference_pairs_per_s(args.workload, 1, threads)
-        v, secs, desc = cpu_reference_pairs_per_s(args.workload, steps, threads)
+        v, secs, desc, per_pair, kind = cpu_reference_pairs_per_s(args.workload, steps, threads, return_times=True)
+        v1, _, desc1 = cpu_reference_pairs_per_s(args.workload, 1, 1)          # the same path on ONE thread, one pair
         line = {'metric': METRIC, 'value': v, 'unit': 'pairs/s', 'n_gpus': args.gpus, 'steps': steps, 'warmup': warm,
                 'ms_per_step': 1000.0 * secs / steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                 'dtype': 'f32', 'data': 'synthetic', 'impl': 'reference',
                 'config': {'workload': args.workload, 'pairs_per_step': 1,
                            'note': f'CPU path, rank 0 only; --steps {args.steps} --warmup {args.warmup} bounded to {steps} / {warm} pairs'},
-                'cpu_baseline': {'value': v, 'unit': 'pairs/s', 'cores': threads, 'kind': 'reference', 'sample': desc},
+                'cpu_baseline': {'value': v, 'unit': 'pairs/s', 'cores': threads, 'kind': kind, 'sample': desc,
+                                 'seconds_per_pair': _stats(per_pair),
+                                 'one_thread': {'value': v1, 'unit': 'pairs/s', 'cores': 1, 'sample': desc1},
+                                 'host_cpus': os.cpu_count(),
+                                 'threads_note': 'min(cores, 16) intra-op threads is the fastest setting measured on the 128-vCPU host '
+                                                 '(more threads oversubscribe the thousands of tiny ATen ops); the 1-thread number is printed beside it'},
                 'e2e': {'value': v, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
                 'gpu_launches': 0}
         print(json.dumps(line))
@@ -201,7 +301,10 @@ def main():
     enable_native(model)
 
     from geotransformer_b200.engine import RegistrationEngine
-    W, K, S = args.warmup, args.steps, max(1, args.streams)
+    BATCH = max(1, args.batch)
+    LANES = max(1, args.streams if args.streams is not None else (2 if BATCH > 1 else 4))
+    W, K = args.warmup, args.steps
+    S = max(1, args.pairs_per_step if args.pairs_per_step is not None else (2 * BATCH * LANES if BATCH > 1 else LANES))   # pairs per GPU and step
     pairs = make_inputs(args.workload, (W + K) * S, rank, world)
     # host staging (pinned) and device-resident copies
     pinned = [{k: torch.from_numpy(v).pin_memory() for k, v in p.items()} for p in pairs]
@@ -209,7 +312,7 @@ def main():
     h2d_bytes = sum(v.numel() * v.element_size() for v in pinned[0].values()) * S
     from geotransformer_b200.loss import Evaluator
     evaluator = Evaluator(cfg)          # PIR/IR/RRE/RTE/RMSE/RR on the device, inside the timed region (one launch per pair)
-    engine = RegistrationEngine(model, cfg, limits, num_streams=S, device=dev, evaluator=evaluator, pin_cpu=True)
+    engine = RegistrationEngine(model, cfg, limits, num_streams=LANES, device=dev, evaluator=evaluator, pin_cpu=True, batch_size=BATCH)
 
     def barrier():
         if world > 1:
@@ -230,11 +333,21 @@ def main():
         ms = e0.elapsed_time(e1)
         if os.environ.get('GEOB_BENCH_DEBUG'):
             print(f'[rank {rank}] {n} steps x {S} pairs: {ms:.1f} ms', file=sys.stderr, flush=True)
+        per_rank = [ms]
+        if world > 1:                     # after the timed region: every rank's own time, so that a straggler is attributable
+            t = torch.tensor([ms], device=dev)
+            gathered = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(gathered, t)
+            per_rank = [float(g.item()) for g in gathered]
+        timed.per_rank = per_rank
         return max_over_ranks(ms, dev, world)
+
+    def segs():
+        return torch.cuda.memory_stats(dev).get('segment.all.allocated', 0)
 
     timed(resident, 0, W)
     timed(pinned, 0, W)
-    seg0 = torch.cuda.memory_stats(dev).get('segment.all.allocated', 0)
+    seg0 = segs()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -242,21 +355,26 @@ def main():
     l0 = lib.geob200_launch_count()
     GF.EVENTS = {}
     ms_res = timed(resident, W, K)
+    per_rank_res = timed.per_rank
+    mallocs_res = segs() - seg0
     launches = (lib.geob200_launch_count() - l0)
     events = GF.EVENTS
     GF.EVENTS = None
     results = []
+    seg_a = segs()
     ms_e2e = timed(pinned, W, K, sink=results)
+    per_rank_e2e = timed.per_rank
+    mallocs_e2e = segs() - seg_a
     # roofline pass: the dominant kernel timed ALONE (one pair in flight, so no other stream shares the SMs), same workload
-    solo = RegistrationEngine(model, cfg, limits, num_streams=1, device=dev, evaluator=evaluator)
+    solo = RegistrationEngine(model, cfg, limits, num_streams=1, device=dev, evaluator=evaluator, batch_size=BATCH)
     GF.EVENTS = {}
     barrier()
-    n_solo = min(K * S, 8)
+    n_solo = min(K * S, max(8, 2 * BATCH))
     lib.geob200_linear_profile_enable(1)          # CUDA events around every tcgen05 GEMM launch of these pairs
     solo.register(resident[W * S:W * S + n_solo])
     barrier()
     import ctypes
-    cap = 400 * n_solo
+    cap = 400 * max(n_solo, 8)
     shp, gms = (ctypes.c_int64 * (3 * cap))(), (ctypes.c_float * cap)()
     n_gemm = int(lib.geob200_linear_profile_read(cap, shp, gms))
     lib.geob200_linear_profile_enable(0)
@@ -266,7 +384,7 @@ def main():
     solo.close()
     sampler.stop_flag = True
     engine.close()
-    seg1 = torch.cuda.memory_stats(dev).get('segment.all.allocated', 0)
+    tf32_peak = measure_tf32_peak(dev) if rank == 0 else None
 
     # metric rows (RRE, RTE, nCorr, pair id, PIR, IR, RMSE, RR) gathered with ONE collective
     rows = []
@@ -289,18 +407,19 @@ def main():
     n_c = [r['num_superpoints'][0] for r in results] + [r['num_superpoints'][1] for r in results]
     mean_n2 = float(np.mean([n * n for n in n_c])) if n_c else 0.0
     flops = 2.0 * mean_n2 * 4 * C * C
-    peak_tf, peak_hbm, peak_src = load_peaks()
+    peak_tf, peak_tf_sustained, peak_hbm, peak_src = load_peaks()
+    traffic = load_traffic()
     avg_ms = float(np.mean(gse_solo_ms)) if gse_solo_ms else None
     achieved = flops / (avg_ms * 1e-3) / 1e12 if avg_ms else None
     avg_ms_concurrent = float(np.mean(gse_ms)) if gse_ms else None
     mode_name = {0: 'fp32 CUDA cores', 1: 'tcgen05 3xTF32', 2: 'tcgen05 1xTF32', 3: 'tcgen05 3xFP16 (fp32-accurate split)', 4: 'tcgen05 3xFP16 split, CTA-pair TMA multicast of B'}[GF.GSE_MODE]
     roofline_gse = {'kernel': 'gse_embed (structure-embedding contraction)', 'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf,
-                'unit': 'TFLOP/s', 'frac': (achieved / peak_tf) if achieved else None, 'traffic': None,
+                'unit': 'TFLOP/s', 'frac': (achieved / peak_tf) if achieved else None, 'traffic': traffic.get('gse_embed_bytes_per_launch'),
                 'avg_ms_per_launch': avg_ms, 'launches_timed': len(gse_solo_ms), 'flops_per_launch': flops,
                 'avg_ms_per_launch_with_other_streams_active': avg_ms_concurrent,
                 'timing': 'CUDA events around the launch, one pair in flight (kernel alone on the GPU), same workload, after the timed regions',
-                'share_of_gpu_time': (sum(gse_ms) / (ms_res * S)) if gse_ms else None, 'mode': mode_name,
-                'peak_source': f'{peak_src} bf16 dense (MEASURED_PEAKS.json); TF32 dense peak is half of it'}
+                'share_of_gpu_time': (sum(gse_ms) / (ms_res * LANES)) if gse_ms else None, 'mode': mode_name,
+                'peak_source': f'{peak_src} bf16 dense BURST (MEASURED_PEAKS.json; the kernel is timed alone)'}
 
     # dominant kernel by share of the step's GPU time: linear_tc_kernel (every nn.Linear and the KPConv contraction; ~80 launches
     # per pair, shapes M=40 000..320, K=32..3840, N=32..1024).  ALGORITHMIC flops = 2*M*N*K of the fp32 product the reference
@@ -311,33 +430,41 @@ def main():
     big = sorted(gemm, key=lambda r: -r[3])[:3]
     roofline = {'kernel': 'linear_tc_kernel (tcgen05 3xTF32 GEMM: all nn.Linear + KPConv contraction)', 'bound': 'tensor',
                 'achieved': (g_flops / (g_ms * 1e-3) / 1e12) if g_ms else None, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                'frac': (g_flops / (g_ms * 1e-3) / 1e12 / peak_tf) if g_ms else None, 'traffic': None,
+                'frac': (g_flops / (g_ms * 1e-3) / 1e12 / peak_tf) if g_ms else None,
+                'traffic': traffic.get('linear_tc_bytes_per_launch'), 'traffic_note': traffic.get('note'),
+                'algorithmic_bytes_per_launch': (g_bytes / n_gemm) if n_gemm else None,
+                'tf32_dense_peak_measured': tf32_peak,
+                'frac_of_3xtf32_ceiling': (g_flops / (g_ms * 1e-3) / 1e12 / (tf32_peak / 3.0)) if (g_ms and tf32_peak) else None,
                 'launches_timed': n_gemm, 'launches_per_pair': n_gemm / max(n_solo, 1), 'ms_per_pair': g_ms / max(n_solo, 1),
                 'flops_per_pair': g_flops / max(n_solo, 1), 'algorithmic_bytes_per_pair': g_bytes / max(n_solo, 1),
                 'achieved_GBps': (g_bytes / (g_ms * 1e-3) / 1e9) if g_ms else None, 'hbm_peak_GBps': peak_hbm,
                 'slowest_launches_m_n_k_ms': [[m, n, k, round(t, 4)] for m, n, k, t in big],
-                'share_of_gpu_time': (g_ms / max(n_solo, 1)) / (ms_res / (K * S) * S) if g_ms else None,
+                'share_of_gpu_time': (g_ms / max(n_solo, 1)) / (ms_res / (K * S) * LANES) if g_ms else None,
                 'timing': 'CUDA events around every launch, one pair in flight (kernel alone on the GPU), same workload, after the timed regions',
                 'note': 'a family of ~80 small GEMMs per pair: most launches cover <= 27 CTAs and are latency-bound (K-loop of one CTA), '
                         'see DESIGN.md section 5; share_of_gpu_time = its time per pair (kernel alone) / stream-time per pair (streams x wall)',
-                'peak_source': f'{peak_src} bf16 dense (MEASURED_PEAKS.json); the TF32 pipe peaks at half of it and 3 MMAs run per product'}
+                'peak_source': f'{peak_src} bf16 dense BURST (MEASURED_PEAKS.json; launches timed alone); tf32_dense_peak_measured = torch.matmul fp32 '
+                               f'8192^3 with allow_tf32, best of 10, this run; the kernel executes 3 TF32 MMAs per product term'}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
             threads = cpu_threads()
-            v, secs, desc = cpu_reference_pairs_per_s(args.workload, 1, threads)
-            cpu = {'value': v, 'unit': 'pairs/s', 'cores': threads, 'kind': 'reference' if 'reference' in desc else 'port',
-                   'sample': desc}
+            cpu_reference_pairs_per_s(args.workload, 1, threads)              # warm-up pair (thread pool, allocator)
+            v, secs, desc, per_pair, kind = cpu_reference_pairs_per_s(args.workload, 3, threads, return_times=True)
+            v1, _, desc1 = cpu_reference_pairs_per_s(args.workload, 1, 1)
+            cpu = {'value': v, 'unit': 'pairs/s', 'cores': threads, 'kind': kind, 'sample': desc, 'seconds_per_pair': _stats(per_pair),
+                   'one_thread': {'value': v1, 'unit': 'pairs/s', 'cores': 1, 'sample': desc1}, 'host_cpus': os.cpu_count()}
         except Exception as ex:   # the baseline must never take the bench line down
             cpu = {'value': None, 'unit': 'pairs/s', 'cores': os.cpu_count(), 'kind': 'port', 'sample': f'failed: {ex}'}
+    eager = gpu_eager_port(args.workload, 3, dev) if (world == 1 and not args.no_cpu_baseline) else None
 
     total_pairs = K * S * world
     line = {
         'metric': METRIC, 'value': total_pairs / (ms_res * 1e-3), 'unit': 'pairs/s', 'n_gpus': world, 'steps': K, 'warmup': W,
         'ms_per_step': ms_res / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic',
-        'config': {'workload': args.workload, 'pairs_per_step_per_gpu': S, 'streams': S, 'points_per_cloud': int(pairs[0]['ref_points'].shape[0]),
+        'config': {'workload': args.workload, 'pairs_per_step_per_gpu': S, 'pairs_per_forward': BATCH, 'forwards_in_flight': LANES, 'points_per_cloud': int(pairs[0]['ref_points'].shape[0]),
                    'superpoints_per_cloud': int(np.mean(n_c)) if n_c else None, 'sinkhorn_iterations': cfg.model.num_sinkhorn_iterations,
                    'parallelism': f'pairs sharded over {world} GPU(s), one all_gather of metric rows',
                    'host_threads_pinned_to_gpu_numa_node': bool(engine.pinned_cpu),
@@ -345,7 +472,9 @@ def main():
                    'weights': 'random init (synthetic_state_dict seed 7351)'},
         'e2e': {'value': total_pairs / (ms_e2e * 1e-3), 'unit': 'pairs/s', 'ms_per_step': ms_e2e / K,
                 'h2d_bytes_per_step': int(h2d_bytes), 'd2h_bytes_per_step': 96 * S},
-        'gpu_launches': int(launches), 'cuda_mallocs_in_timed_regions': int(seg1 - seg0), 'roofline': roofline, 'roofline_gse_embed': roofline_gse, 'cpu_baseline': cpu, 'clocks': sampler.summary(),
+        'gpu_launches': int(launches), 'gpu_launches_per_pair': launches / max(K * S, 1),
+        'cuda_mallocs': {'timed_region_resident': int(mallocs_res), 'timed_region_e2e': int(mallocs_e2e)},
+        'per_rank_ms': {'value': per_rank_res, 'e2e': per_rank_e2e}, 'roofline': roofline, 'roofline_gse_embed': roofline_gse, 'cpu_baseline': cpu, 'gpu_eager_port': eager, 'clocks': sampler.summary(),
         'quality': {'median_rre_deg': float(rows_t[:, 0].median()), 'median_rte': float(rows_t[:, 1].median()),
                     'mean_correspondences': float(rows_t[:, 2].mean()), 'pairs': int(rows_t.shape[0]),
                     'mean_PIR': float(rows_t[:, 4].nanmean()), 'mean_IR': float(rows_t[:, 5].nanmean()),

@@ -188,30 +188,39 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // them round-robin.  Each warp streams the E rows of its next ATS_DEPTH-1 groups into its private shared-memory ring with
 // cp.async (every lane later reads back exactly the 16-byte pieces it copied, so no barrier is needed): ~8 KB of E in flight
 // per warp without spending registers on it.
+// One launch covers a batch of independent attention problems (the clouds / pairs of a batched forward): the work units of all
+// items form one sequence (gprefix = running number of (query, 4-key group) units) that the persistent CTAs split evenly.
+// The descriptor travels by value in the kernel parameter space (no device allocation, no H2D copy).
+constexpr int ATT_MAX_ITEMS = 32;
+struct AttItem { const float *q, *k, *v, *qp, *qb, *E; float *out, *S; int N, M; };
+struct AttBatch { int n_items; int reserved; long long gprefix[ATT_MAX_ITEMS + 1]; AttItem it[ATT_MAX_ITEMS]; };
+
 template <int H, int J>
-__global__ void __launch_bounds__(128) att_scores_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk,
-                                                         const float* __restrict__ qp, const float* __restrict__ qb,
-                                                         const float* __restrict__ E, int N, int M, float div, float* __restrict__ S) {
+__global__ void __launch_bounds__(128) att_scores_kernel(const __grid_constant__ AttBatch b, int ldq, int ldk, float div) {
     constexpr int C = 128 * J;
     constexpr int D = C / H;
     constexpr int NV = ATS_G * H;                 // values reduced together: (key u, head h) -> v[u * H + h]
     extern __shared__ float4 ring_all[];          // [4 warps][ATS_DEPTH][ATS_G][J][32 lanes]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4* ring = ring_all + (size_t)warp * ATS_DEPTH * ATS_G * J * 32;
-    const bool has_e = (E != nullptr);
-    const int gpq = (M + ATS_G - 1) / ATS_G;      // groups per query
-    const long long groups = (long long)N * gpq;
+    const bool has_e = (b.it[0].E != nullptr);    // a batch is all self-attention (with E) or all cross-attention
+    const long long groups = b.gprefix[b.n_items];
     const long long g_begin = groups * blockIdx.x / gridDim.x, g_end = groups * (blockIdx.x + 1) / gridDim.x;
     float4 qv[J];
     float4 qpv[H][J];
     int hq[J];
 #pragma unroll
     for (int j = 0; j < J; ++j) hq[j] = (j * 128 + 4 * lane) / D;
+    int cp = 0, ci = 0;                           // item cursors of the prefetcher and of the consumer (work units only move forward)
 
     auto prefetch = [&](long long g, int slot) {           // E rows of group g -> ring slot (no-op group when g is out of range)
         if (has_e && g < g_end) {
-            const int n = (int)(g / gpq), m0 = (int)(g % gpq) * ATS_G;
-            const float* e_row = E + (long long)n * M * C;
+            while (g >= b.gprefix[cp + 1]) ++cp;
+            const int M = b.it[cp].M;
+            const int gpq = (M + ATS_G - 1) / ATS_G;      // groups per query
+            const long long gl = g - b.gprefix[cp];
+            const int n = (int)(gl / gpq), m0 = (int)(gl % gpq) * ATS_G;
+            const float* e_row = b.it[cp].E + (long long)n * M * C;
 #pragma unroll
             for (int u = 0; u < ATS_G; ++u) {
                 const int m = min(m0 + u, M - 1);
@@ -226,12 +235,19 @@ __global__ void __launch_bounds__(128) att_scores_kernel(const float* __restrict
     const long long first = g_begin + warp;
 #pragma unroll
     for (int d = 0; d < ATS_DEPTH - 1; ++d) prefetch(first + 4ll * d, d);
-    int n_loaded = -1;
+    long long n_loaded = -1;
     int slot = 0;
     for (long long g = first; g < g_end; g += 4) {
         prefetch(g + 4ll * (ATS_DEPTH - 1), (slot + ATS_DEPTH - 1) % ATS_DEPTH);
-        const int n = (int)(g / gpq), m0 = (int)(g % gpq) * ATS_G;
-        if (n != n_loaded) {                                  // warp-uniform
+        while (g >= b.gprefix[ci + 1]) ++ci;
+        const int M = b.it[ci].M;
+        const int gpq = (M + ATS_G - 1) / ATS_G;
+        const long long gl = g - b.gprefix[ci];
+        const int n = (int)(gl / gpq), m0 = (int)(gl % gpq) * ATS_G;
+        const float* __restrict__ k = b.it[ci].k;
+        if ((((long long)ci << 32) | n) != n_loaded) {        // warp-uniform
+            const float* __restrict__ q = b.it[ci].q;
+            const float* __restrict__ qp = b.it[ci].qp;
 #pragma unroll
             for (int j = 0; j < J; ++j) {
                 const int c = j * 128 + 4 * lane;
@@ -240,7 +256,7 @@ __global__ void __launch_bounds__(128) att_scores_kernel(const float* __restrict
                 for (int h = 0; h < H; ++h)
                     qpv[h][j] = has_e ? *reinterpret_cast<const float4*>(qp + ((long long)n * H + h) * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            n_loaded = n;
+            n_loaded = ((long long)ci << 32) | n;
         }
         float4 kk[ATS_G][J];
 #pragma unroll
@@ -271,8 +287,8 @@ __global__ void __launch_bounds__(128) att_scores_kernel(const float* __restrict
         const int idx = lane >> SH;
         const int u = idx / H, h = idx % H;
         if ((lane & ((1 << SH) - 1)) == 0 && m0 + u < M) {
-            const float bias = has_e ? qb[(long long)n * H + h] : 0.f;
-            S[((long long)n * H + h) * M + m0 + u] = (v[0] + bias) / div;
+            const float bias = has_e ? b.it[ci].qb[(long long)n * H + h] : 0.f;
+            b.it[ci].S[((long long)n * H + h) * M + m0 + u] = (v[0] + bias) / div;
         }
         slot = (slot + 1) % ATS_DEPTH;
     }
@@ -281,11 +297,16 @@ __global__ void __launch_bounds__(128) att_scores_kernel(const float* __restrict
 
 // softmax over the keys and P.V for R = 2 queries per CTA (value rows fetched once for both); thread <-> channel
 template <int H>
-__global__ void __launch_bounds__(512) att_softmax_pv_kernel(const float* __restrict__ S, const float* __restrict__ v, int ldv, int N,
-                                                             int M, int C, float* __restrict__ out, int ldo) {
+__global__ void __launch_bounds__(512) att_softmax_pv_kernel(const __grid_constant__ AttBatch b, int ldv, int C, int ldo) {
     extern __shared__ float sm[];
     float* sc = sm;                               // [R][H][M]
+    const AttItem& item = b.it[blockIdx.y];
+    const int N = item.N, M = item.M;
     const int n0 = blockIdx.x * ATT_R;
+    if (n0 >= N) return;                          // grid.x covers the largest item of the batch
+    const float* __restrict__ S = item.S;
+    const float* __restrict__ v = item.v;
+    float* __restrict__ out = item.out;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int d = C / H;
     for (int rh = warp; rh < ATT_R * H; rh += (int)(blockDim.x >> 5)) {
@@ -358,8 +379,7 @@ __global__ void __launch_bounds__(512) att_softmax_pv_kernel(const float* __rest
 }
 
 template <int H, int J>
-static int launch_streaming(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, const float* qp, const float* qb,
-                            const float* E, int N, int M, float div, float* out, int ldo, float* S, cudaStream_t st) {
+static int launch_streaming(const AttBatch& b, int ldq, int ldk, int ldv, float div, int ldo, cudaStream_t st) {
     // one CTA per resident slot (occupancy queried once per instantiation); each owns a contiguous range of 4-key groups
     constexpr int ring_bytes = 4 * ATS_DEPTH * ATS_G * J * 32 * (int)sizeof(float4);
     if (ring_bytes > 48 * 1024 && ensure_max_smem((const void*)att_scores_kernel<H, J>)) return -1;
@@ -368,13 +388,16 @@ static int launch_streaming(const float* q, int ldq, const float* k, int ldk, co
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, att_scores_kernel<H, J>, 128, ring_bytes) != cudaSuccess || per_sm < 1)
             per_sm = 1;
     }
-    const long long groups = (long long)N * ((M + ATS_G - 1) / ATS_G);
+    const long long groups = b.gprefix[b.n_items];
     long long grid = (long long)per_sm * num_sms();
     if (grid * 4 > groups) grid = (groups + 3) / 4;
-    att_scores_kernel<H, J><<<(unsigned)grid, 128, ring_bytes, st>>>(q, ldq, k, ldk, qp, qb, E, N, M, div, S);
-    const size_t smem = sizeof(float) * (ATT_R * H * (size_t)((M + 3) / 4 * 4) + ATT_KQ * ATT_R * 128 * J);     // scores + the partial outputs
+    att_scores_kernel<H, J><<<(unsigned)grid, 128, ring_bytes, st>>>(b, ldq, ldk, div);
+    int max_n = 0, max_m = 0;
+    for (int i = 0; i < b.n_items; ++i) { max_n = b.it[i].N > max_n ? b.it[i].N : max_n; max_m = b.it[i].M > max_m ? b.it[i].M : max_m; }
+    const size_t smem = sizeof(float) * (ATT_R * H * (size_t)((max_m + 3) / 4 * 4) + ATT_KQ * ATT_R * 128 * J);     // scores + the partial outputs
     if (smem > 48 * 1024 && ensure_max_smem((const void*)att_softmax_pv_kernel<H>)) return -1;
-    att_softmax_pv_kernel<H><<<(unsigned)((N + ATT_R - 1) / ATT_R), 64 * ATT_KQ, smem, st>>>(S, v, ldv, N, M, 128 * J, out, ldo);
+    const dim3 pv_grid((unsigned)((max_n + ATT_R - 1) / ATT_R), (unsigned)b.n_items);
+    att_softmax_pv_kernel<H><<<pv_grid, 64 * ATT_KQ, smem, st>>>(b, ldv, 128 * J, ldo);
     return 0;
 }
 
@@ -433,44 +456,100 @@ size_t geob200_attention_workspace_bytes(int64_t n_query, int64_t n_key, int64_t
     return (size_t)n_query * (size_t)n_key * (size_t)heads * sizeof(float) + 256;
 }
 
+// Streaming path for a batch of items sharing channels / heads / row strides.  Returns 1 when the shape is not handled by it.
+static int attention_streaming_batch(const geob200_att_item_t* items, int64_t n_items, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
+                                     int64_t channels, int64_t heads, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    if (!(channels == 128 || channels == 256) || workspace == nullptr) return 1;
+    GEOB_REQUIRE(n_items >= 1 && n_items <= ATT_MAX_ITEMS, "attention: 1..%d items per launch", ATT_MAX_ITEMS);
+    AttBatch b{};
+    b.n_items = (int)n_items;
+    b.gprefix[0] = 0;
+    size_t need = 0;
+    for (int i = 0; i < (int)n_items; ++i) {
+        const geob200_att_item_t& it = items[i];
+        GEOB_REQUIRE(it.n_query > 0 && it.n_key > 0, "attention: empty input");
+        GEOB_REQUIRE((it.embed == nullptr) == (it.qp == nullptr) && (it.embed == nullptr) == (it.qb == nullptr), "attention: qp/qb/embed must come together");
+        GEOB_REQUIRE((it.embed == nullptr) == (items[0].embed == nullptr), "attention: a batch is all self- or all cross-attention");
+        GEOB_REQUIRE(((uintptr_t)it.q % 16) == 0 && ((uintptr_t)it.k % 16) == 0 && ((uintptr_t)it.v % 16) == 0 &&
+                         (it.qp == nullptr || ((uintptr_t)it.qp % 16) == 0) && (it.embed == nullptr || ((uintptr_t)it.embed % 16) == 0),
+                     "attention: q, k, v, qp, embed must be 16-byte aligned");
+        const size_t smem_pv = sizeof(float) * (ATT_R * heads * (size_t)((it.n_key + 3) / 4 * 4) + ATT_KQ * ATT_R * channels);
+        if (smem_pv > 200 * 1024) return 1;
+        AttItem& d = b.it[i];
+        d.q = it.q; d.k = it.k; d.v = it.v; d.qp = it.qp; d.qb = it.qb; d.E = it.embed; d.out = it.out;
+        d.N = (int)it.n_query; d.M = (int)it.n_key;
+        d.S = (float*)((char*)workspace + need);
+        need += align_up((size_t)it.n_query * (size_t)it.n_key * (size_t)heads * sizeof(float), 256);
+        b.gprefix[i + 1] = b.gprefix[i] + (long long)it.n_query * ((it.n_key + ATS_G - 1) / ATS_G);
+    }
+    GEOB_REQUIRE(workspace_bytes >= need, "attention: workspace too small");
+    const float div = sqrtf((float)(channels / heads));   // d_model_per_head ** 0.5
+    int rc = -2;
+#define LAUNCH_STREAM(HV)                                                                                             \
+    rc = (channels == 256) ? launch_streaming<HV, 2>(b, (int)ldq, (int)ldk, (int)ldv, div, (int)ldo, st)              \
+                           : launch_streaming<HV, 1>(b, (int)ldq, (int)ldk, (int)ldv, div, (int)ldo, st)
+    switch (heads) {
+        case 1: LAUNCH_STREAM(1); break;
+        case 2: LAUNCH_STREAM(2); break;
+        case 4: LAUNCH_STREAM(4); break;
+        default: LAUNCH_STREAM(8); break;
+    }
+#undef LAUNCH_STREAM
+    GEOB_REQUIRE(rc == 0, "attention: could not configure the softmax kernel");
+    GEOB_CHECK_LAUNCH();
+    count_launches(2);
+    return 0;
+}
+
+static int attention_check(int64_t channels, int64_t heads, int64_t ldq, int64_t ldk, int64_t ldv) {
+    GEOB_REQUIRE(channels % 4 == 0 && channels <= 256 && heads > 0 && heads <= ATT_MAXH && channels % heads == 0 &&
+                     (channels / heads) % 4 == 0,
+                 "attention: unsupported channels=%lld heads=%lld", (long long)channels, (long long)heads);
+    GEOB_REQUIRE(ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0, "attention: row strides must be multiples of 4 floats");
+    GEOB_REQUIRE(heads == 1 || heads == 2 || heads == 4 || heads == 8, "attention: heads must be 1, 2, 4 or 8");
+    return 0;
+}
+
+size_t geob200_attention_batched_workspace_bytes(const geob200_att_item_t* items, int64_t n_items, int64_t heads) {
+    size_t need = 256;
+    for (int64_t i = 0; i < n_items; ++i)
+        need += align_up((size_t)items[i].n_query * (size_t)items[i].n_key * (size_t)heads * sizeof(float), 256);
+    return need;
+}
+
+int geob200_attention_batched(const geob200_att_item_t* items, int64_t n_items, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
+                              int64_t channels, int64_t heads, void* workspace, size_t workspace_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_items == 0) return 0;
+    if (attention_check(channels, heads, ldq, ldk, ldv)) return -2;
+    for (int64_t i0 = 0; i0 < n_items; i0 += ATT_MAX_ITEMS) {
+        const int64_t cnt = (n_items - i0 < ATT_MAX_ITEMS) ? n_items - i0 : ATT_MAX_ITEMS;
+        const int rc = attention_streaming_batch(items + i0, cnt, ldq, ldk, ldv, ldo, channels, heads, workspace, workspace_bytes, st);
+        if (rc < 0) return rc;
+        if (rc == 1)          // shape outside the streaming path: one single-kernel launch per item
+            for (int64_t i = i0; i < i0 + cnt; ++i) {
+                const geob200_att_item_t& it = items[i];
+                const int r2 = geob200_attention(it.q, ldq, it.k, ldk, it.v, ldv, it.qp, it.qb, it.embed, it.n_query, it.n_key, channels, heads,
+                                                 it.out, ldo, nullptr, 0, stream);
+                if (r2 != 0) return r2;
+            }
+    }
+    return 0;
+}
+
 int geob200_attention(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv, const float* qp,
                       const float* qb, const float* embed, int64_t n_query, int64_t n_key, int64_t channels, int64_t heads,
                       float* out, int64_t ldo, void* workspace, size_t workspace_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     GEOB_REQUIRE(n_query > 0 && n_key > 0, "attention: empty input");
-    GEOB_REQUIRE(channels % 4 == 0 && channels <= 256 && heads > 0 && heads <= ATT_MAXH && channels % heads == 0 &&
-                     (channels / heads) % 4 == 0,
-                 "attention: unsupported channels=%lld heads=%lld", (long long)channels, (long long)heads);
+    if (attention_check(channels, heads, ldq, ldk, ldv)) return -2;
     GEOB_REQUIRE((embed == nullptr) == (qp == nullptr) && (embed == nullptr) == (qb == nullptr), "attention: qp/qb/embed must come together");
-    GEOB_REQUIRE(ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0, "attention: row strides must be multiples of 4 floats");
-    GEOB_REQUIRE(heads == 1 || heads == 2 || heads == 4 || heads == 8, "attention: heads must be 1, 2, 4 or 8");
     const float div = sqrtf((float)(channels / heads));   // d_model_per_head ** 0.5
-    const size_t smem_pv = sizeof(float) * (ATT_R * heads * (size_t)((n_key + 3) / 4 * 4) + ATT_KQ * ATT_R * channels);
-    if ((channels == 128 || channels == 256) && smem_pv <= 200 * 1024 && workspace != nullptr) {
+    if (workspace != nullptr) {
         // streaming path: lanes <-> channels, (query, key-chunk) grid, scores through the workspace
-        GEOB_REQUIRE(workspace_bytes >= geob200_attention_workspace_bytes(n_query, n_key, heads), "attention: workspace too small");
-        GEOB_REQUIRE(((uintptr_t)q % 16) == 0 && ((uintptr_t)k % 16) == 0 && ((uintptr_t)v % 16) == 0 &&
-                         (qp == nullptr || ((uintptr_t)qp % 16) == 0) &&
-                         (embed == nullptr || ((uintptr_t)embed % 16) == 0),
-                     "attention: q, k, v, qp, embed must be 16-byte aligned");
-        float* S = (float*)workspace;
-        int rc = -2;
-#define LAUNCH_STREAM(HV)                                                                                                            \
-    rc = (channels == 256) ? launch_streaming<HV, 2>(q, (int)ldq, k, (int)ldk, v, (int)ldv, qp, qb, embed, (int)n_query, (int)n_key, \
-                                                     div, out, (int)ldo, S, st)                                                       \
-                           : launch_streaming<HV, 1>(q, (int)ldq, k, (int)ldk, v, (int)ldv, qp, qb, embed, (int)n_query, (int)n_key, \
-                                                     div, out, (int)ldo, S, st)
-        switch (heads) {
-            case 1: LAUNCH_STREAM(1); break;
-            case 2: LAUNCH_STREAM(2); break;
-            case 4: LAUNCH_STREAM(4); break;
-            default: LAUNCH_STREAM(8); break;
-        }
-#undef LAUNCH_STREAM
-        GEOB_REQUIRE(rc == 0, "attention: could not configure the softmax kernel");
-        GEOB_CHECK_LAUNCH();
-        count_launches(2);
-        return 0;
+        const geob200_att_item_t one{q, k, v, qp, qb, embed, out, n_query, n_key};
+        const int rc = attention_streaming_batch(&one, 1, ldq, ldk, ldv, ldo, channels, heads, workspace, workspace_bytes, st);
+        if (rc <= 0) return rc;
     }
     // generic path (any C <= 256 that is a multiple of 4; no workspace needed)
     const size_t smem = sizeof(float) * (ATT_R * channels + ATT_R * heads * channels + ATT_R * heads * n_key);

@@ -167,7 +167,13 @@ __global__ void __launch_bounds__(1024) evaluate_kernel(const long long* __restr
                                                         const float* __restrict__ ref_corr_pts, const float* __restrict__ src_corr_pts,
                                                         int n_corr, float acc_radius, const float* __restrict__ T_gt,
                                                         const float* __restrict__ T_est, const float* __restrict__ src_points, int n_src,
-                                                        int mode, float acc_rmse, float acc_rre, float acc_rte, float* __restrict__ metrics) {
+                                                        int mode, float acc_rmse, float acc_rre, float acc_rte, float* __restrict__ metrics,
+                                                        const int* __restrict__ n_gt_dev, const int* __restrict__ n_node_corr_dev,
+                                                        const int* __restrict__ n_corr_dev) {
+    // counts produced on the device by earlier stages (no host read-back between them and this kernel)
+    if (n_gt_dev != nullptr) n_gt = *n_gt_dev;
+    if (n_node_corr_dev != nullptr) n_node_corr = min(n_node_corr, *n_node_corr_dev);
+    if (n_corr_dev != nullptr) n_corr = *n_corr_dev;
     __shared__ double red[32];
     __shared__ float Tg[16], Te[16], Tr[16];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -307,13 +313,25 @@ int geob200_evaluate(const int64_t* gt_node_corr_indices, const float* gt_node_c
                      const float* ref_corr_points, const float* src_corr_points, int64_t n_corr, float acceptance_radius,
                      const float* gt_transform, const float* est_transform, const float* src_points, int64_t n_src_points, int mode,
                      float rmse_threshold, float rre_threshold, float rte_threshold, float* metrics, void* stream) {
+    return geob200_evaluate_counts(gt_node_corr_indices, gt_node_corr_overlaps, n_gt, nullptr, acceptance_overlap, ref_node_corr_indices,
+                                   src_node_corr_indices, n_node_corr, nullptr, ref_corr_points, src_corr_points, n_corr, nullptr,
+                                   acceptance_radius, gt_transform, est_transform, src_points, n_src_points, mode, rmse_threshold,
+                                   rre_threshold, rte_threshold, metrics, stream);
+}
+
+int geob200_evaluate_counts(const int64_t* gt_node_corr_indices, const float* gt_node_corr_overlaps, int64_t n_gt, const int32_t* n_gt_dev,
+                            float acceptance_overlap, const int64_t* ref_node_corr_indices, const int64_t* src_node_corr_indices,
+                            int64_t n_node_corr, const int32_t* n_node_corr_dev, const float* ref_corr_points, const float* src_corr_points,
+                            int64_t n_corr, const int32_t* n_corr_dev, float acceptance_radius, const float* gt_transform,
+                            const float* est_transform, const float* src_points, int64_t n_src_points, int mode, float rmse_threshold,
+                            float rre_threshold, float rte_threshold, float* metrics, void* stream) {
     GEOB_REQUIRE(mode >= 0 && mode <= 2, "evaluate: mode must be 0 (3DMatch), 1 (KITTI) or 2 (ModelNet)");
     evaluate_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>((const long long*)gt_node_corr_indices, gt_node_corr_overlaps, (int)n_gt,
                                                           acceptance_overlap, (const long long*)ref_node_corr_indices,
                                                           (const long long*)src_node_corr_indices, (int)n_node_corr, ref_corr_points,
                                                           src_corr_points, (int)n_corr, acceptance_radius, gt_transform, est_transform,
                                                           src_points, (int)n_src_points, mode, rmse_threshold, rre_threshold,
-                                                          rte_threshold, metrics);
+                                                          rte_threshold, metrics, n_gt_dev, n_node_corr_dev, n_corr_dev);
     GEOB_CHECK_LAUNCH();
     count_launches(1);
     return 0;

@@ -266,9 +266,17 @@ size_t geob200_gse_embed_workspace_bytes(int64_t n, int64_t channels) {
 int geob200_gse_embed(const float* d_indices, const float* a_indices, int64_t n, int64_t channels, const float* div_term,
                       const float* wd_t, const float* wa_t, const float* wd, const float* wa, const float* bd, const float* ba,
                       float* embeddings, int mode, void* workspace, size_t workspace_bytes, void* stream) {
+    GEOB_REQUIRE(n > 0, "gse_embed: bad shape");
+    return geob200_gse_embed_pairs(d_indices, a_indices, n * n, channels, div_term, wd_t, wa_t, wd, wa, bd, ba, embeddings, mode, workspace,
+                                   workspace_bytes, stream);
+}
+
+int geob200_gse_embed_pairs(const float* d_indices, const float* a_indices, int64_t n_rows, int64_t channels, const float* div_term,
+                            const float* wd_t, const float* wa_t, const float* wd, const float* wa, const float* bd, const float* ba,
+                            float* embeddings, int mode, void* workspace, size_t workspace_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    GEOB_REQUIRE(n > 0 && channels > 0 && channels % 4 == 0, "gse_embed: bad shape");
-    const long long n_pairs = (long long)n * n;
+    GEOB_REQUIRE(n_rows > 0 && channels > 0 && channels % 4 == 0, "gse_embed: bad shape");
+    const long long n_pairs = (long long)n_rows;
     if (mode != 0) {
         int rc = geob200_gse_embed_tc(d_indices, a_indices, n_pairs, (int)channels, div_term, wd, wa, bd, ba, embeddings, mode,
                                       workspace, workspace_bytes, st);

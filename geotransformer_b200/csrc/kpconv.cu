@@ -564,6 +564,117 @@ __global__ void __launch_bounds__(1024) gn_finalize_kernel(const double* __restr
     }
 }
 
+// ---- per-pair statistics for batched execution (GnSeg) ---------------------------------------------------------------------
+// Same per-128-row-tile partial layout as the GEMM epilogue produces ([tile][slot][2] doubles, slot = min(cpg, 32) channels),
+// for activations whose producer has no fused statistics (fp32 fallbacks, split-K GEMMs, the c_in = 1 first KPConv).
+__global__ void __launch_bounds__(256) gn_tile_stats_kernel(const float* __restrict__ x, int N, int C, int slot_width,
+                                                            double* __restrict__ partial) {
+    extern __shared__ double sh[];           // [C / slot_width][2]
+    const int slots = C / slot_width;
+    for (int i = threadIdx.x; i < 2 * slots; i += blockDim.x) sh[i] = 0.0;
+    __syncthreads();
+    const int r0 = blockIdx.x * 128, r1 = min(N, r0 + 128);
+    const int cw = C < 256 ? C : 256;        // channels walked concurrently
+    const int rpb = 256 / cw;                // row lanes
+    const int rr = threadIdx.x / cw;
+    if (rr < rpb)
+        for (int c = threadIdx.x % cw; c < C; c += cw) {
+            double s = 0.0, s2 = 0.0;
+            for (int r = r0 + rr; r < r1; r += rpb) {
+                const double v = (double)x[(long long)r * C + c];
+                s += v;
+                s2 += v * v;
+            }
+            atomicAdd(&sh[2 * (c / slot_width)], s);
+            atomicAdd(&sh[2 * (c / slot_width) + 1], s2);
+        }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * slots; i += blockDim.x) partial[(long long)blockIdx.x * 2 * slots + i] = sh[i];
+}
+
+// One CTA per pair: folds the tile partials of the tiles lying completely inside one of the pair's clouds and adds the rows of
+// the (at most two per cloud) tiles that straddle a cloud boundary directly from the activations.  mean_rstd [pair][G][2].
+__global__ void __launch_bounds__(1024) gn_seg_finalize_kernel(const double* __restrict__ partial, const float* __restrict__ x, int C,
+                                                               int slots_total, int spg, int G, double eps, GnSeg seg,
+                                                               float* __restrict__ mean_rstd) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int p = blockIdx.x;
+    const int cpg = C / G;
+    const double2* part = reinterpret_cast<const double2*>(partial);
+    for (int g = warp; g < G; g += 32) {
+        double sa = 0.0, sb = 0.0;
+        long long rows = 0;
+        for (int c = p; c < seg.n_clouds; c += seg.n_pairs) {
+            const int r0 = seg.start[c], r1 = seg.start[c + 1];
+            rows += r1 - r0;
+            int t0 = (r0 + 127) / 128, t1 = r1 / 128;          // full tiles [t0, t1)
+            if (t1 < t0) t1 = t0;                              // the cloud lies inside one tile: all rows direct
+            for (int sl = 0; sl < spg; ++sl)
+                for (int t = t0 + lane; t < t1; t += 32) {
+                    const double2 v = part[(long long)t * slots_total + (long long)g * spg + sl];
+                    sa += v.x;
+                    sb += v.y;
+                }
+            const int e0 = min(r1, t0 * 128);                  // rows [r0, e0) and [b1, r1) are in straddling tiles
+            const int b1 = min(r1, max(e0, t1 * 128));
+            const int n_edge = (e0 - r0) + (r1 - b1);
+            for (int i = lane; i < n_edge * cpg; i += 32) {
+                const int ri = i / cpg, j = i % cpg;
+                const int r = ri < e0 - r0 ? r0 + ri : b1 + (ri - (e0 - r0));
+                const double v = (double)x[(long long)r * C + g * cpg + j];
+                sa += v;
+                sb += v * v;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sa += __shfl_xor_sync(0xffffffffu, sa, o);
+            sb += __shfl_xor_sync(0xffffffffu, sb, o);
+        }
+        if (lane == 0) {
+            const double count = (double)cpg * (double)rows;
+            const double mean = sa / count;
+            double var = sb / count - mean * mean;
+            if (var < 0.0) var = 0.0;
+            mean_rstd[((long long)p * G + g) * 2] = (float)mean;
+            mean_rstd[((long long)p * G + g) * 2 + 1] = (float)(1.0 / sqrt(var + eps));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) gn_seg_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean_rstd,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           const float* __restrict__ residual, float* __restrict__ y, long long total4,
+                                                           int C, int cpg, int G, int leaky, float slope, GnSeg seg) {
+    __shared__ int starts[GEOB_MAX_CLOUDS + 1];
+    for (int i = threadIdx.x; i <= seg.n_clouds; i += blockDim.x) starts[i] = seg.start[i];
+    __syncthreads();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total4) return;
+    const int row = (int)((i * 4) / C);
+    int lo = 0, hi = seg.n_clouds;                             // cloud with starts[lo] <= row < starts[lo + 1]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (starts[mid] <= row) lo = mid; else hi = mid;
+    }
+    const float* mr = mean_rstd + (long long)(lo % seg.n_pairs) * 2 * G;
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    const int c = (int)((i * 4) % C);
+    float in[4] = {v.x, v.y, v.z, v.w}, o[4];
+    float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (residual != nullptr) rv = reinterpret_cast<const float4*>(residual)[i];
+    const float rs[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int g = (c + u) / cpg;
+        float t = (in[u] - mr[2 * g]) * mr[2 * g + 1] * gamma[c + u] + beta[c + u];
+        t += rs[u];
+        if (leaky) t = t > 0.f ? t : t * slope;
+        o[u] = t;
+    }
+    reinterpret_cast<float4*>(y)[i] = make_float4(o[0], o[1], o[2], o[3]);
+}
+
 __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean_rstd,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        const float* __restrict__ residual, float* __restrict__ y,
@@ -759,15 +870,40 @@ size_t geob200_fused_group_norm_workspace_bytes(int64_t n_rows, int64_t channels
     return (fused > plain ? fused : plain) + (size_t)(2 * groups * 4) + 256 + 1024;
 }
 
+}  // extern "C"
+
 namespace geob200 {
+size_t fused_group_norm_workspace_bytes_batched(int64_t n_rows, int64_t channels, int64_t groups, int64_t n_pairs) {
+    return geob200_fused_group_norm_workspace_bytes(n_rows, channels, groups) + (size_t)(2 * groups * 4) * (size_t)(n_pairs > 1 ? n_pairs : 1) + 512;
+}
 struct GnWs { unsigned* ticket; float* mean_rstd; double* partial; };
-static GnWs gn_carve(void* workspace, size_t bytes, int64_t groups) {
+static GnWs gn_carve(void* workspace, size_t bytes, int64_t groups, int64_t n_pairs = 1) {
     Arena ar(workspace, bytes);
     GnWs w;
     w.ticket = ar.take<unsigned>(64);                   // must be zero on first use: the caller provides a zeroed workspace once
-    w.mean_rstd = ar.take<float>(2 * groups);
+    w.mean_rstd = ar.take<float>(2 * groups * n_pairs);
     w.partial = ar.take<double>(1);
     return w;
+}
+// per-pair statistics (batched execution): fold the tile partials per pair, then normalise with the row's pair statistics
+static void launch_gn_seg_apply(const float* x, const GnWs& w, const float* gamma, const float* beta, const float* residual, float* y,
+                                int64_t n_rows, int64_t channels, int64_t groups, float eps, int leaky, float slope, const GnSeg& seg,
+                                cudaStream_t st) {
+    const int cpg = (int)(channels / groups);
+    const int slot_width = cpg < 32 ? cpg : 32;
+    gn_seg_finalize_kernel<<<seg.n_pairs, 1024, 0, st>>>(w.partial, x, (int)channels, (int)(channels / slot_width), cpg / slot_width,
+                                                         (int)groups, (double)eps, seg, w.mean_rstd);
+    const long long total4 = n_rows * channels / 4;
+    gn_seg_apply_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(x, w.mean_rstd, gamma, beta, residual, y, total4, (int)channels,
+                                                                         cpg, (int)groups, leaky, slope, seg);
+    count_launches(2);
+}
+static void launch_gn_tile_stats(const float* x, const GnWs& w, int64_t n_rows, int64_t channels, int64_t groups, cudaStream_t st) {
+    const int cpg = (int)(channels / groups);
+    const int slot_width = cpg < 32 ? cpg : 32;
+    gn_tile_stats_kernel<<<(unsigned)((n_rows + 127) / 128), 256, sizeof(double) * 2 * (channels / slot_width), st>>>(
+        x, (int)n_rows, (int)channels, slot_width, w.partial);
+    count_launches(1);
 }
 // statistics came out of the GEMM epilogue as per-tile partials: fold them (one small CTA), then normalise
 static void launch_gn_apply(const float* x, const GnWs& w, const float* gamma, const float* beta, const float* residual, float* y,
@@ -782,12 +918,32 @@ static void launch_gn_apply(const float* x, const GnWs& w, const float* gamma, c
 }
 }  // namespace geob200
 
+extern "C" {
+
 int geob200_group_norm(const float* x, int64_t n_rows, int64_t channels, int64_t groups, const float* gamma,
                        const float* beta, float eps, const float* residual, int leaky, float slope, float* y,
                        void* workspace, size_t workspace_bytes, void* stream) {
+    return geob200::group_norm_impl(x, n_rows, channels, groups, gamma, beta, eps, residual, leaky, slope, y, workspace, workspace_bytes,
+                                    stream, nullptr);
+}
+}  // extern "C"
+
+namespace geob200 {
+int group_norm_impl(const float* x, int64_t n_rows, int64_t channels, int64_t groups, const float* gamma, const float* beta, float eps,
+                    const float* residual, int leaky, float slope, float* y, void* workspace, size_t workspace_bytes, void* stream,
+                    const GnSeg* seg) {
     cudaStream_t st = (cudaStream_t)stream;
     GEOB_REQUIRE(n_rows > 0 && channels > 0 && groups > 0 && channels % groups == 0, "group_norm: bad shape");
     GEOB_REQUIRE(channels % 4 == 0, "group_norm: channels must be a multiple of 4");
+    if (seg != nullptr && seg->n_pairs > 1) {
+        GEOB_REQUIRE(workspace_bytes >= fused_group_norm_workspace_bytes_batched(n_rows, channels, groups, seg->n_pairs),
+                     "group_norm: workspace too small (batched)");
+        const GnWs w = gn_carve(workspace, workspace_bytes, groups, seg->n_pairs);
+        launch_gn_tile_stats(x, w, n_rows, channels, groups, st);
+        launch_gn_seg_apply(x, w, gamma, beta, residual, y, n_rows, channels, groups, eps, leaky, slope, *seg, st);
+        GEOB_CHECK_LAUNCH();
+        return 0;
+    }
     GEOB_REQUIRE(workspace_bytes >= geob200_group_norm_workspace_bytes(groups), "group_norm: workspace too small");
     Arena ar(workspace, workspace_bytes);
     unsigned* ticket = ar.take<unsigned>(64);           // must be zero on first use: caller provides zeroed ws once
@@ -805,6 +961,9 @@ int geob200_group_norm(const float* x, int64_t n_rows, int64_t channels, int64_t
     count_launches(2);
     return 0;
 }
+}  // namespace geob200
+
+extern "C" {
 
 int geob200_maxpool(const float* x, const int64_t* neighbors, int64_t n_query, int64_t n_support, int64_t n_neighbors,
                     int64_t channels, float* y, void* stream) {
@@ -830,25 +989,44 @@ int geob200_upsample_concat(const float* x, const int64_t* up_indices, int64_t u
 int geob200_linear_group_norm(const float* x, int64_t ldx, const float* weight, const float* bias, int64_t m, int64_t n, int64_t k,
                               int64_t groups, const float* gamma, const float* beta, float eps, const float* residual, int leaky,
                               float slope, float* pre_norm, float* y, void* workspace, size_t workspace_bytes, void* stream) {
+    return geob200::linear_group_norm_impl(x, ldx, weight, bias, m, n, k, groups, gamma, beta, eps, residual, leaky, slope, pre_norm, y,
+                                           workspace, workspace_bytes, stream, nullptr);
+}
+}  // extern "C"
+
+namespace geob200 {
+int linear_group_norm_impl(const float* x, int64_t ldx, const float* weight, const float* bias, int64_t m, int64_t n, int64_t k,
+                           int64_t groups, const float* gamma, const float* beta, float eps, const float* residual, int leaky,
+                           float slope, float* pre_norm, float* y, void* workspace, size_t workspace_bytes, void* stream,
+                           const GnSeg* seg) {
     cudaStream_t st = (cudaStream_t)stream;
+    const int64_t np = (seg != nullptr && seg->n_pairs > 1) ? seg->n_pairs : 1;
     GEOB_REQUIRE(m > 0 && n > 0 && k > 0 && groups > 0 && n % groups == 0 && n % 4 == 0, "linear_group_norm: bad shape");
-    GEOB_REQUIRE(workspace_bytes >= geob200_fused_group_norm_workspace_bytes(m, n, groups), "linear_group_norm: workspace too small");
+    GEOB_REQUIRE(workspace_bytes >= (np > 1 ? fused_group_norm_workspace_bytes_batched(m, n, groups, np)
+                                            : geob200_fused_group_norm_workspace_bytes(m, n, groups)), "linear_group_norm: workspace too small");
     if (g_linear_mode == 1) {
-        const GnWs w = gn_carve(workspace, workspace_bytes, groups);
+        const GnWs w = gn_carve(workspace, workspace_bytes, groups, np);
         GnFuse gn{(int)groups, 0, w.partial};
         const int rc = linear_tc(x, ldx, weight, k, bias, nullptr, pre_norm, n, m, n, k, 0, st, &gn);
         if (rc < 0) return rc;
         if (rc == 0) {
-            launch_gn_apply(pre_norm, w, gamma, beta, residual, y, m, n, groups, eps, leaky, slope, st);
+            if (np > 1) {
+                launch_gn_seg_apply(pre_norm, w, gamma, beta, residual, y, m, n, groups, eps, leaky, slope, *seg, st);
+            } else {
+                launch_gn_apply(pre_norm, w, gamma, beta, residual, y, m, n, groups, eps, leaky, slope, st);
+                count_launches(2);
+            }
             GEOB_CHECK_LAUNCH();
-            count_launches(2);
             return 0;
         }
     }
     int rc = geob200_linear(x, ldx, weight, bias, pre_norm, n, m, n, k, 0, stream);
     if (rc != 0) return rc;
-    return geob200_group_norm(pre_norm, m, n, groups, gamma, beta, eps, residual, leaky, slope, y, workspace, workspace_bytes, stream);
+    return group_norm_impl(pre_norm, m, n, groups, gamma, beta, eps, residual, leaky, slope, y, workspace, workspace_bytes, stream, seg);
 }
+}  // namespace geob200
+
+extern "C" {
 
 // KPConv (gather + tcgen05 GEMM) -> GroupNorm (+ LeakyReLU): ConvBlock / the conv part of ResidualBlock (modules.py:107-147,205-207)
 size_t geob200_kpconv_group_norm_workspace_bytes(int64_t n_query, int64_t n_support, int64_t c_in, int64_t c_out, int64_t groups) {
@@ -861,14 +1039,29 @@ int geob200_kpconv_group_norm(const float* s_feats, const float* q_points, const
                               const float* weights_t, const float* bias, int64_t c_in, int64_t c_out, float sigma, int64_t groups,
                               const float* gamma, const float* beta, float eps, int leaky, float slope, float* pre_norm, float* y,
                               void* gn_workspace, size_t gn_workspace_bytes, void* workspace, size_t workspace_bytes, void* stream) {
+    return geob200::kpconv_group_norm_impl(s_feats, q_points, s_points, neighbors, n_query, n_support, n_neighbors, kernel_points, n_kernel,
+                                           weights_t, bias, c_in, c_out, sigma, groups, gamma, beta, eps, leaky, slope, pre_norm, y,
+                                           gn_workspace, gn_workspace_bytes, workspace, workspace_bytes, stream, nullptr);
+}
+}  // extern "C"
+
+namespace geob200 {
+int kpconv_group_norm_impl(const float* s_feats, const float* q_points, const float* s_points, const int64_t* neighbors,
+                           int64_t n_query, int64_t n_support, int64_t n_neighbors, const float* kernel_points, int64_t n_kernel,
+                           const float* weights_t, const float* bias, int64_t c_in, int64_t c_out, float sigma, int64_t groups,
+                           const float* gamma, const float* beta, float eps, int leaky, float slope, float* pre_norm, float* y,
+                           void* gn_workspace, size_t gn_workspace_bytes, void* workspace, size_t workspace_bytes, void* stream,
+                           const GnSeg* seg) {
     cudaStream_t st = (cudaStream_t)stream;
+    const int64_t np = (seg != nullptr && seg->n_pairs > 1) ? seg->n_pairs : 1;
     GEOB_REQUIRE(n_kernel == KP, "kpconv_group_norm: kernel_size %lld unsupported", (long long)n_kernel);
     GEOB_REQUIRE(n_query > 0 && n_support > 0 && n_neighbors > 0, "kpconv_group_norm: empty input");
     GEOB_REQUIRE(c_in % 32 == 0 && c_out % 16 == 0 && c_out >= 32 && (c_out <= 128 || c_out % 128 == 0) && n_query >= 64,
                  "kpconv_group_norm: unsupported shape (%lld -> %lld, %lld queries)", (long long)c_in, (long long)c_out,
                  (long long)n_query);
     GEOB_REQUIRE(groups > 0 && c_out % groups == 0, "kpconv_group_norm: bad group count");
-    GEOB_REQUIRE(gn_workspace_bytes >= geob200_fused_group_norm_workspace_bytes(n_query, c_out, groups),
+    GEOB_REQUIRE(gn_workspace_bytes >= (np > 1 ? fused_group_norm_workspace_bytes_batched(n_query, c_out, groups, np)
+                                               : geob200_fused_group_norm_workspace_bytes(n_query, c_out, groups)),
                  "kpconv_group_norm: GroupNorm workspace too small");
     GEOB_REQUIRE(workspace_bytes >= geob200_kpconv_tc_workspace_bytes(n_query, n_support, c_in), "kpconv_group_norm: workspace too small");
     Arena ar(workspace, workspace_bytes);
@@ -880,21 +1073,61 @@ int geob200_kpconv_group_norm(const float* s_feats, const float* q_points, const
                          (int)n_support, (int)n_query, (int)c_in, wf, inv_count, st);
     GEOB_CHECK_LAUNCH();
     count_launches(2);
-    const GnWs w = gn_carve(gn_workspace, gn_workspace_bytes, groups);
+    const GnWs w = gn_carve(gn_workspace, gn_workspace_bytes, groups, np);
     GnFuse gn{(int)groups, 0, w.partial};
     int rc = linear_tc(wf, KP * c_in, weights_t, KP * c_in, bias, inv_count, pre_norm, c_out, n_query, c_out, KP * c_in, 0, st, &gn);
     if (rc < 0) return rc;
     if (rc == 0) {
-        launch_gn_apply(pre_norm, w, gamma, beta, nullptr, y, n_query, c_out, groups, eps, leaky, slope, st);
+        if (np > 1) {
+            launch_gn_seg_apply(pre_norm, w, gamma, beta, nullptr, y, n_query, c_out, groups, eps, leaky, slope, *seg, st);
+        } else {
+            launch_gn_apply(pre_norm, w, gamma, beta, nullptr, y, n_query, c_out, groups, eps, leaky, slope, st);
+            count_launches(2);
+        }
         GEOB_CHECK_LAUNCH();
-        count_launches(2);
         return 0;
     }
     // group layout not expressible in the epilogue: plain GEMM, then the stand-alone statistics kernel
     rc = linear_tc(wf, KP * c_in, weights_t, KP * c_in, bias, inv_count, pre_norm, c_out, n_query, c_out, KP * c_in, 0, st);
     GEOB_REQUIRE(rc == 0, "kpconv_group_norm: tensor-core GEMM rejected the shape");
-    return geob200_group_norm(pre_norm, n_query, c_out, groups, gamma, beta, eps, nullptr, leaky, slope, y, gn_workspace,
-                              gn_workspace_bytes, stream);
+    return group_norm_impl(pre_norm, n_query, c_out, groups, gamma, beta, eps, nullptr, leaky, slope, y, gn_workspace, gn_workspace_bytes,
+                           stream, seg);
+}
+}  // namespace geob200
+
+namespace geob200 {
+static int make_seg(GnSeg* g, int64_t n_pairs, const int64_t* cloud_rows_h, int64_t n_rows) {
+    GEOB_REQUIRE(n_pairs >= 1 && 2 * n_pairs <= GEOB_MAX_CLOUDS && cloud_rows_h != nullptr, "group_norm: 1 <= pairs per batch <= %d", GEOB_MAX_CLOUDS / 2);
+    g->n_pairs = (int)n_pairs; g->n_clouds = (int)(2 * n_pairs); g->start[0] = 0;
+    for (int c = 0; c < g->n_clouds; ++c) g->start[c + 1] = g->start[c] + (int)cloud_rows_h[c];
+    GEOB_REQUIRE(g->start[g->n_clouds] == n_rows, "group_norm: cloud rows do not add up to n_rows");
+    return 0;
+}
+}  // namespace geob200
+
+extern "C" {
+
+size_t geob200_group_norm_batched_workspace_bytes(int64_t n_rows, int64_t channels, int64_t groups, int64_t n_pairs) {
+    return geob200::fused_group_norm_workspace_bytes_batched(n_rows, channels, groups, n_pairs);
+}
+
+int geob200_group_norm_batched(const float* x, int64_t n_rows, int64_t channels, int64_t groups, const float* gamma, const float* beta,
+                               float eps, const float* residual, int leaky, float slope, float* y, void* workspace, size_t workspace_bytes,
+                               void* stream, int64_t n_pairs, const int64_t* cloud_rows_h) {
+    geob200::GnSeg seg;
+    if (geob200::make_seg(&seg, n_pairs, cloud_rows_h, n_rows)) return -2;
+    return geob200::group_norm_impl(x, n_rows, channels, groups, gamma, beta, eps, residual, leaky, slope, y, workspace, workspace_bytes,
+                                    stream, &seg);
+}
+
+int geob200_linear_group_norm_batched(const float* x, int64_t ldx, const float* weight, const float* bias, int64_t m, int64_t n, int64_t k,
+                                      int64_t groups, const float* gamma, const float* beta, float eps, const float* residual, int leaky,
+                                      float slope, float* pre_norm, float* y, void* workspace, size_t workspace_bytes, void* stream,
+                                      int64_t n_pairs, const int64_t* cloud_rows_h) {
+    geob200::GnSeg seg;
+    if (geob200::make_seg(&seg, n_pairs, cloud_rows_h, m)) return -2;
+    return geob200::linear_group_norm_impl(x, ldx, weight, bias, m, n, k, groups, gamma, beta, eps, residual, leaky, slope, pre_norm, y,
+                                           workspace, workspace_bytes, stream, &seg);
 }
 
 }  // extern "C"

@@ -51,12 +51,14 @@ def _detach(t):
 _GN_WS = {}
 
 
-def _gn_workspace(device, groups, rows=0, channels=0):
+def _gn_workspace(device, groups, rows=0, channels=0, n_pairs=1):
     """zero-initialised (ticket) GroupNorm scratch per (device, stream, groups); large enough for the statistics of a
-    (rows, channels) activation produced by the GEMM epilogue (geob200_fused_group_norm_workspace_bytes)"""
+    (rows, channels) activation produced by the GEMM epilogue (geob200_fused_group_norm_workspace_bytes) and the per-pair
+    mean / rstd of a batch of n_pairs pairs"""
     key = (device.index, L.stream_ptr(), groups)
     lib = L.lib()
     need = lib.geob200_fused_group_norm_workspace_bytes(rows, channels, groups) if rows else lib.geob200_group_norm_workspace_bytes(groups)
+    need += 8 * groups * max(int(n_pairs), 1) + 1024
     ws = _GN_WS.get(key)
     if ws is None or ws.numel() < need:
         ws = torch.zeros(max(int(need * 1.5), 1 << 20), dtype=_u8, device=device)
@@ -168,6 +170,42 @@ def kpconv_group_norm(s_feats, q_points, s_points, neighbor_indices, kernel_poin
                                           int(negative_slope is not None), float(negative_slope or 0.0), pre.data_ptr(),
                                           y.data_ptr(), gws.data_ptr(), gws.numel(), ws.data_ptr(), ws.numel(), L.stream_ptr()),
             'kpconv_group_norm')
+    return y
+
+
+def _cloud_rows(cloud_rows):
+    import ctypes
+    return (ctypes.c_int64 * len(cloud_rows))(*[int(r) for r in cloud_rows])
+
+
+def group_norm_batched(x, weight, bias, groups, cloud_rows, eps=1e-5, negative_slope=None, residual=None):
+    """GroupNorm with per-PAIR statistics for rows in stack order [ref_1..ref_B, src_1..src_B] (``cloud_rows``: 2B host ints)"""
+    x, weight, bias = _detach(x), _detach(weight), _detach(bias)
+    _f(x, 'x')
+    n, c = x.shape
+    np_ = len(cloud_rows) // 2
+    ws = _gn_workspace(x.device, groups, n, c, n_pairs=np_)
+    y = torch.empty_like(x)
+    L.check(L.lib().geob200_group_norm_batched(x.data_ptr(), n, c, groups, weight.data_ptr(), bias.data_ptr(), float(eps), L.ptr(residual),
+                                               int(negative_slope is not None), float(negative_slope or 0.0), y.data_ptr(), ws.data_ptr(),
+                                               ws.numel(), L.stream_ptr(), np_, _cloud_rows(cloud_rows)), 'group_norm_batched')
+    return y
+
+
+def linear_group_norm_batched(x, weight, bias, gn_weight, gn_bias, groups, cloud_rows, eps=1e-5, negative_slope=None, residual=None):
+    """linear_group_norm with per-pair GroupNorm statistics (see group_norm_batched)"""
+    x, weight, bias, gn_weight, gn_bias = _detach(x), _detach(weight), _detach(bias), _detach(gn_weight), _detach(gn_bias)
+    m, k = x.shape
+    n = weight.shape[0]
+    np_ = len(cloud_rows) // 2
+    pre = scratch((m, n), x.device, 'pre_norm')
+    y = torch.empty((m, n), dtype=_f32, device=x.device)
+    ws = _gn_workspace(x.device, groups, m, n, n_pairs=np_)
+    L.check(L.lib().geob200_linear_group_norm_batched(x.data_ptr(), x.stride(0), weight.data_ptr(), L.ptr(bias), m, n, k, groups,
+                                                      gn_weight.data_ptr(), gn_bias.data_ptr(), float(eps), L.ptr(residual),
+                                                      int(negative_slope is not None), float(negative_slope or 0.0), pre.data_ptr(),
+                                                      y.data_ptr(), ws.data_ptr(), ws.numel(), L.stream_ptr(), np_, _cloud_rows(cloud_rows)),
+            'linear_group_norm_batched')
     return y
 
 
@@ -285,11 +323,15 @@ def gather_rows(table, indices):
 
 # ------------------------------------------------------------------------------------------------ transformer
 
-def gse_indices(points, sigma_d, sigma_a, angle_k):
+def gse_indices(points, sigma_d, sigma_a, angle_k, out=None):
+    """``out``: optional (d, a) contiguous float buffers of n*n and n*n*angle_k elements to write into"""
     _f(points, 'points')
     n = points.shape[0]
-    d = torch.empty((n, n), dtype=_f32, device=points.device)
-    a = torch.empty((n, n, angle_k), dtype=_f32, device=points.device)
+    if out is not None:
+        d, a = out[0].view(n, n), out[1].view(n, n, angle_k)
+    else:
+        d = torch.empty((n, n), dtype=_f32, device=points.device)
+        a = torch.empty((n, n, angle_k), dtype=_f32, device=points.device)
     factor_a = 180.0 / (sigma_a * math.pi)
     L.check(L.lib().geob200_gse_indices(points.data_ptr(), n, float(sigma_d), float(factor_a), angle_k, d.data_ptr(),
                                         a.data_ptr(), L.stream_ptr()), 'gse_indices')
@@ -324,6 +366,23 @@ def scratch_arange(n, device, tag='arange'):
         torch.cuda.current_stream(device).synchronize()      # other streams may read it right away
         _ARANGE[key] = buf
     return buf[:n]
+
+
+def gse_embed_flat(d_indices, a_indices, n_rows, div_term, wd, wa, bd, ba, wd_t, wa_t, out, mode=None):
+    """structure embedding of ``n_rows`` (anchor, point) pairs given as flat index arrays -- the (i, j) pairs of SEVERAL clouds
+    concatenated (d (n_rows,), a (n_rows, k)) -> out (n_rows, C): one launch for a whole batch of clouds."""
+    c = wd.shape[0]
+    mode = GSE_MODE if mode is None else mode
+    if c != 256:
+        mode = 0                     # the tcgen05 contraction is specialised for hidden_dim 256 (3DMatch / ModelNet)
+    lib = L.lib()
+    ws = L.workspace(lib.geob200_gse_embed_workspace_bytes(1, c), d_indices.device, 'gse')
+    with _timed('gse_embed'):
+        L.check(lib.geob200_gse_embed_pairs(d_indices.data_ptr(), a_indices.data_ptr(), int(n_rows), c, div_term.data_ptr(),
+                                            wd_t.data_ptr(), wa_t.data_ptr(), wd.data_ptr(), wa.data_ptr(), bd.data_ptr(),
+                                            ba.data_ptr(), out.data_ptr(), int(mode), ws.data_ptr(), ws.numel(), L.stream_ptr()),
+                'gse_embed_pairs')
+    return out
 
 
 def gse_embed(d_indices, a_indices, div_term, wd, wa, bd, ba, wd_t, wa_t, mode=None, out=None):
@@ -473,7 +532,9 @@ def sinkhorn(scores, row_masks, col_masks, alpha, num_iterations, inf=1e12):
 
 def local_global_registration(ref_knn_points, src_knn_points, ref_knn_masks, src_knn_masks, score_mat, k, acceptance_radius,
                               mutual, confidence_threshold, correspondence_threshold, num_refinement_steps,
-                              return_details=False):
+                              return_details=False, defer_count=False, transform_out=None):
+    """``defer_count``: no host read-back -- returns the full-capacity correspondence tensors and the device count
+    ``(ref_c, src_c, scores, T, n)``; rows ``[:n]`` are valid.  ``transform_out``: (16,) float view to write T into."""
     p, kk = ref_knn_masks.shape
     ld = score_mat.shape[1]
     dev = score_mat.device
@@ -484,7 +545,7 @@ def local_global_registration(ref_knn_points, src_knn_points, ref_knn_masks, src
     sc = torch.empty((cap,), dtype=_f32, device=dev)
     cp = torch.empty((cap,), dtype=_i32, device=dev)
     n = torch.empty((1,), dtype=_i32, device=dev)
-    T = torch.empty((4, 4), dtype=_f32, device=dev)
+    T = torch.empty((4, 4), dtype=_f32, device=dev) if transform_out is None else transform_out
     pT = torch.empty((p, 4, 4), dtype=_f32, device=dev)
     pin = torch.empty((p,), dtype=_i32, device=dev)
     best = torch.empty((1,), dtype=_i32, device=dev)
@@ -495,6 +556,8 @@ def local_global_registration(ref_knn_points, src_knn_points, ref_knn_masks, src
         int(correspondence_threshold), int(num_refinement_steps), ref_c.data_ptr(), src_c.data_ptr(), sc.data_ptr(),
         cp.data_ptr(), n.data_ptr(), T.data_ptr(), pT.data_ptr(), pin.data_ptr(), best.data_ptr(), ws.data_ptr(),
         ws.numel(), L.stream_ptr()), 'local_global_registration')
+    if defer_count:
+        return ref_c, src_c, sc, T, n
     c = int(n.item())    # the one D2H of the stage: the number of correspondences sizes the returned tensors
     if return_details:
         return ref_c[:c], src_c[:c], sc[:c], T, dict(corr_patch=cp[:c], patch_transforms=pT, patch_inliers=pin, best=best)
@@ -551,9 +614,10 @@ EVAL_MODES = {'3dmatch': 0, 'kitti': 1, 'modelnet': 2}
 
 def evaluate(gt_node_corr_indices, gt_node_corr_overlaps, ref_node_corr_indices, src_node_corr_indices, ref_corr_points,
              src_corr_points, gt_transform, est_transform, src_points, mode, acceptance_overlap, acceptance_radius,
-             rmse_threshold=0.0, rre_threshold=0.0, rte_threshold=0.0, out=None):
+             rmse_threshold=0.0, rre_threshold=0.0, rte_threshold=0.0, out=None, n_gt=None, n_node_corr=None, n_corr=None):
     """Evaluator.forward (reference experiments/<exp>/loss.py:95-159) as one launch; returns a device tensor
-    ``[PIR, IR, RRE, RTE, RMSE, RR, #corr, #gt_node_corr]``."""
+    ``[PIR, IR, RRE, RTE, RMSE, RR, #corr, #gt_node_corr]``.  ``n_gt / n_node_corr / n_corr``: optional device int32 counts
+    of valid rows when the index / point tensors are full-capacity buffers (no host read-back in between)."""
     dev = est_transform.device
     if out is None:
         out = torch.empty((8,), dtype=_f32, device=dev)
@@ -563,12 +627,13 @@ def evaluate(gt_node_corr_indices, gt_node_corr_overlaps, ref_node_corr_indices,
     for t, name in ((gt_node_corr_indices, 'gt_node_corr_indices'), (ref_node_corr_indices, 'ref_node_corr_indices'),
                     (src_node_corr_indices, 'src_node_corr_indices')):
         L.require_cuda(t, name, _i64)
-    L.check(L.lib().geob200_evaluate(gt_node_corr_indices.data_ptr(), gt_node_corr_overlaps.data_ptr(),
-                                     gt_node_corr_indices.shape[0], float(acceptance_overlap),
-                                     ref_node_corr_indices.data_ptr(), src_node_corr_indices.data_ptr(),
-                                     ref_node_corr_indices.shape[0], ref_corr_points.data_ptr(), src_corr_points.data_ptr(),
-                                     ref_corr_points.shape[0], float(acceptance_radius), gt_transform.data_ptr(),
-                                     est_transform.data_ptr(), src_points.data_ptr(), src_points.shape[0], int(mode),
-                                     float(rmse_threshold), float(rre_threshold), float(rte_threshold), out.data_ptr(),
-                                     L.stream_ptr()), 'evaluate')
+    L.check(L.lib().geob200_evaluate_counts(gt_node_corr_indices.data_ptr(), gt_node_corr_overlaps.data_ptr(),
+                                            gt_node_corr_indices.shape[0], L.ptr(n_gt), float(acceptance_overlap),
+                                            ref_node_corr_indices.data_ptr(), src_node_corr_indices.data_ptr(),
+                                            ref_node_corr_indices.shape[0], L.ptr(n_node_corr), ref_corr_points.data_ptr(),
+                                            src_corr_points.data_ptr(), ref_corr_points.shape[0], L.ptr(n_corr),
+                                            float(acceptance_radius), gt_transform.data_ptr(),
+                                            est_transform.data_ptr(), src_points.data_ptr(), src_points.shape[0], int(mode),
+                                            float(rmse_threshold), float(rre_threshold), float(rte_threshold), out.data_ptr(),
+                                            L.stream_ptr()), 'evaluate')
     return out

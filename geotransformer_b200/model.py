@@ -8,6 +8,7 @@ whenever ``data_dict`` carries the ground-truth ``transform``; the reference req
 import torch
 import torch.nn as nn
 
+from . import _lib
 from . import functional as GF
 from .backbone import KPConvFPN
 from .modules.geotransformer import GeometricTransformer, SuperPointMatching, LocalGlobalRegistration
@@ -39,7 +40,168 @@ class GeoTransformer(nn.Module):
         self.optimal_transport = LearnableLogOptimalTransport(cfg.model.num_sinkhorn_iterations)
 
     @torch.no_grad()
+    def forward_batch(self, data_dict, evaluator=None, results=None, side_streams=None, keep_outputs=True):
+        """Several pairs per forward (``data_dict['batch_size'] = B > 1`` from ``registration_collate_fn_stack_mode``, stack
+        order ``[ref_1..ref_B, src_1..src_B]`` at every level) -- the reference asserts batch_size == 1
+        (``engine/single_tester.py:39-74``, README "only batch_size=1 is supported").  Backbone and transformer run ONCE over
+        the stacked rows of all pairs (per-pair GroupNorm statistics, batched attention launches, one structure-embedding
+        launch); the per-pair stages (grouping, matching, Sinkhorn, LGR, metrics) are enqueued round-robin on
+        ``side_streams`` so that their small kernels overlap.  Per pair the arithmetic is the single-pair forward's.
+
+        Returns a list of per-pair output dicts (``keep_outputs``), each like ``forward``'s.  With ``results`` (a (B, 24)
+        float device tensor) the estimated transform (16) and, with ``evaluator``, the metrics (8) of pair p are written to
+        row p WITHOUT any host synchronisation in this call (correspondence tensors then stay full-capacity)."""
+        native = getattr(self, '_native', None)
+        if native is None:
+            raise RuntimeError('forward_batch needs the native stage drivers: call enable_native(model) first')
+        B = int(data_dict['batch_size'])
+        lens_h = data_dict.get('lengths_host') or [l.tolist() for l in data_dict['lengths']]
+        fl, K = self.fine_level, self.num_points_in_patch
+        dev = data_dict['features'].device
+        offs = []
+        for lv in lens_h:
+            o = [0]
+            for v in lv:
+                o.append(o[-1] + int(v))
+            offs.append(o)
+        oc, of, o0 = offs[-1], offs[fl], offs[0]
+        points_c, points_f, points0 = data_dict['points'][-1], data_dict['points'][fl], data_dict['points'][0]
+        cloud = lambda t, o, c: t[o[c]:o[c + 1]]
+        main = torch.cuda.current_stream()
+        sides = side_streams or [main]
+        no_sync = results is not None
+
+        def fork():
+            ev = torch.cuda.Event()
+            ev.record(main)
+            for s in sides:
+                if s is not main:
+                    s.wait_event(ev)
+
+        def join():
+            for s in sides:
+                if s is not main:
+                    ev = torch.cuda.Event()
+                    ev.record(s)
+                    main.wait_event(ev)
+
+        class on:          # run the body on side stream i (also for the ctypes calls: thread-local stream pointer)
+            def __init__(self, i):
+                self.s = sides[i % len(sides)]
+            def __enter__(self):
+                self.a = torch.cuda.stream(self.s); self.a.__enter__()
+                self.b = _lib.stream_scope(self.s.cuda_stream); self.b.__enter__()
+            def __exit__(self, *e):
+                self.b.__exit__(*e); self.a.__exit__(*e)
+
+        # ---- per-cloud grouping and per-pair ground-truth superpoint correspondences (side streams)
+        part = [None] * (2 * B)
+        gt = [None] * B
+        transforms = data_dict.get('transform')
+        if transforms is not None and not isinstance(transforms, (list, tuple)):
+            transforms = [transforms[i] for i in range(B)] if transforms.ndim == 3 else [transforms]
+        fork()
+        for p in range(B):
+            with on(p):
+                for c in (p, B + p):
+                    part[c] = GF.point_to_node_partition(cloud(points_f, of, c), cloud(points_c, oc, c), K)
+                if transforms is not None:
+                    rp, sp = part[p], part[B + p]
+                    ref_c, src_c = cloud(points_c, oc, p), cloud(points_c, oc, B + p)
+                    ar_r = GF.scratch_arange(ref_c.shape[0], dev, 'ar_ref')
+                    ar_s = GF.scratch_arange(src_c.shape[0], dev, 'ar_src')
+                    _, _, ref_all = GF.gather_patches(ar_r, rp[2], rp[3], cloud(points_f, of, p))
+                    _, _, src_all = GF.gather_patches(ar_s, sp[2], sp[3], cloud(points_f, of, B + p))
+                    gt[p] = GF.node_correspondences(ref_c, src_c, ref_all, src_all, transforms[p], self.matching_radius, rp[1], sp[1],
+                                                    rp[3], sp[3])
+
+        # ---- backbone over all pairs (main stream, overlaps the grouping)
+        feats_list = native.backbone_forward(data_dict['features'], data_dict)
+        feats_c, feats_f = feats_list[-1], feats_list[0]
+
+        # ---- structure embeddings of all clouds in one launch, transformer over all rows
+        tr = self.transformer
+        emb_mod = tr.embedding
+        rows_c = [int(v) for v in lens_h[-1]]
+        n2 = [r * r for r in rows_c]
+        eo = [0]
+        for v in n2:
+            eo.append(eo[-1] + v)
+        C = tr.in_proj.out_features
+        d_all = GF.scratch((eo[-1],), dev, 'gse_d_all')
+        a_all = GF.scratch((eo[-1], emb_mod.angle_k), dev, 'gse_a_all')
+        E_all = GF.scratch((eo[-1], C), dev, 'gse_E_all')
+        for c in range(2 * B):
+            GF.gse_indices(cloud(points_c, oc, c).contiguous(), emb_mod.sigma_d, emb_mod.sigma_a, emb_mod.angle_k,
+                           out=(d_all[eo[c]:eo[c + 1]], a_all[eo[c]:eo[c + 1]]))
+        wd_t = emb_mod._cache.get('wd_t', emb_mod.proj_d.weight, lambda w: w.t().contiguous())
+        wa_t = emb_mod._cache.get('wa_t', emb_mod.proj_a.weight, lambda w: w.t().contiguous())
+        GF.gse_embed_flat(d_all, a_all, eo[-1], emb_mod.embedding.div_term, emb_mod.proj_d.weight.detach(), emb_mod.proj_a.weight.detach(),
+                          emb_mod.proj_d.bias.detach(), emb_mod.proj_a.bias.detach(), wd_t, wa_t, E_all)
+        embs = [E_all[eo[c]:eo[c + 1]] for c in range(2 * B)]
+        x = GF.linear(feats_c, tr.in_proj.weight, tr.in_proj.bias)
+        x = native.transformer_forward_batched(x, rows_c, embs)
+        y = GF.linear(x, tr.out_proj.weight, tr.out_proj.bias)
+        y_n = GF.l2_normalize(y)
+
+        # ---- per-pair tail on the side streams
+        join()          # grouping results are consumed below on arbitrary side streams
+        fork()
+        outs = []
+        cm, fm = self.coarse_matching, self.fine_matching
+        for p in range(B):
+            with on(p):
+                rp, sp = part[p], part[B + p]
+                ref_c, src_c = cloud(points_c, oc, p), cloud(points_c, oc, B + p)
+                ref_f, src_f = cloud(points_f, of, p), cloud(points_f, of, B + p)
+                ref_fc, src_fc = cloud(y_n, oc, p), cloud(y_n, oc, B + p)
+                ref_ff, src_ff = cloud(feats_f, of, p), cloud(feats_f, of, B + p)
+                ref_corr, src_corr, node_scores, corr_count = cm(ref_fc, src_fc, rp[1], sp[1], defer_count=True)
+                rk_idx, rk_masks, rk_pts = GF.gather_patches(ref_corr, rp[2], rp[3], ref_f)
+                sk_idx, sk_masks, sk_pts = GF.gather_patches(src_corr, sp[2], sp[3], src_f)
+                scores = GF.patch_scores(ref_ff, src_ff, rk_idx, sk_idx)
+                scores = self.optimal_transport(scores, rk_masks, sk_masks)
+                t_out = results[p, :16] if no_sync else None
+                rc, sc, cs, T, n_corr = GF.local_global_registration(
+                    rk_pts, sk_pts, rk_masks, sk_masks, scores, fm.k, fm.acceptance_radius, fm.mutual, fm.confidence_threshold,
+                    fm.correspondence_threshold, fm.num_refinement_steps, defer_count=True, transform_out=t_out)
+                o = dict(ref_points_c=ref_c, src_points_c=src_c, ref_points_f=ref_f, src_points_f=src_f,
+                         ref_points=cloud(points0, o0, p), src_points=cloud(points0, o0, B + p), ref_feats_c=ref_fc, src_feats_c=src_fc,
+                         ref_feats_f=ref_ff, src_feats_f=src_ff, ref_node_corr_indices=ref_corr, src_node_corr_indices=src_corr,
+                         node_corr_scores=node_scores, ref_node_corr_knn_points=rk_pts, src_node_corr_knn_points=sk_pts,
+                         ref_node_corr_knn_masks=rk_masks, src_node_corr_knn_masks=sk_masks, matching_scores=scores,
+                         ref_corr_points=rc, src_corr_points=sc, corr_scores=cs, estimated_transform=T.reshape(4, 4),
+                         _counts=dict(node_corr=corr_count, corr=n_corr, gt=None if gt[p] is None else gt[p][2]))
+                if gt[p] is not None:
+                    o['gt_node_corr_indices'], o['gt_node_corr_overlaps'] = gt[p][0], gt[p][1]
+                    if evaluator is not None and no_sync:
+                        GF.evaluate(gt[p][0], gt[p][1], ref_corr, src_corr, rc, sc, transforms[p], T, o['src_points'], evaluator.mode,
+                                    evaluator.acceptance_overlap, evaluator.acceptance_radius, evaluator.acceptance_rmse,
+                                    evaluator.acceptance_rre, evaluator.acceptance_rte, out=results[p, 16:], n_gt=gt[p][2],
+                                    n_node_corr=corr_count, n_corr=n_corr)
+                outs.append(o)
+        join()
+        if no_sync:
+            return outs if keep_outputs else None
+        # trim the capacity tensors to the counts (one host sync for the whole batch)
+        main.synchronize()
+        for o in outs:
+            cnt = o.pop('_counts')
+            kk, c = int(cnt['node_corr'].item()), int(cnt['corr'].item())
+            for key in ('ref_node_corr_indices', 'src_node_corr_indices', 'node_corr_scores', 'ref_node_corr_knn_points',
+                        'src_node_corr_knn_points', 'ref_node_corr_knn_masks', 'src_node_corr_knn_masks', 'matching_scores'):
+                o[key] = o[key][:kk]
+            for key in ('ref_corr_points', 'src_corr_points', 'corr_scores'):
+                o[key] = o[key][:c]
+            if cnt['gt'] is not None:
+                g = int(cnt['gt'].item())
+                o['gt_node_corr_indices'], o['gt_node_corr_overlaps'] = o['gt_node_corr_indices'][:g], o['gt_node_corr_overlaps'][:g]
+        return outs
+
+    @torch.no_grad()
     def forward(self, data_dict, taps=None):
+        if int(data_dict.get('batch_size', 1)) > 1:
+            return self.forward_batch(data_dict)
         out = {}
         marks = data_dict.get('_stage_events')            # profiling hook: list receiving (label, CUDA event) pairs
         def mark(label):

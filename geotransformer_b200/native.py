@@ -153,11 +153,37 @@ class NativeModel:
         oarr = (P * len(outs))(*[o.data_ptr() for o in outs])
         ws_bytes = lib.geob200_backbone_workspace_bytes(ctypes.byref(self.backbone), rows)
         ws = L.workspace(ws_bytes, dev, 'native_backbone')
-        gn = GF._gn_workspace(dev, self.backbone.groups, pts[0].shape[0], self.backbone.init_dim << S)
-        L.check(lib.geob200_backbone_forward(ctypes.byref(self.backbone), feats.data_ptr(), parr, rows, narr, nw, sarr, sw, uarr, uw, oarr,
-                                             gn.data_ptr(), gn.numel(), ws.data_ptr(), ws.numel(), L.stream_ptr()), 'backbone_forward')
+        n_pairs = int(data_dict.get('batch_size', 1))
+        gn = GF._gn_workspace(dev, self.backbone.groups, pts[0].shape[0], self.backbone.init_dim << S, n_pairs=n_pairs)
+        if n_pairs > 1:
+            # batch of pairs in stack order [ref_1..ref_B, src_1..src_B]: per-pair GroupNorm statistics need the cloud rows
+            lens = data_dict['lengths_host']
+            keep = [(I64 * (2 * n_pairs))(*[int(v) for v in lens[l]]) for l in range(S)]
+            carr = (P * S)(*[ctypes.cast(k, P).value for k in keep])
+            L.check(lib.geob200_backbone_forward_batched(ctypes.byref(self.backbone), feats.data_ptr(), parr, rows, narr, nw, sarr, sw,
+                                                         uarr, uw, oarr, gn.data_ptr(), gn.numel(), ws.data_ptr(), ws.numel(),
+                                                         L.stream_ptr(), n_pairs, carr), 'backbone_forward_batched')
+        else:
+            L.check(lib.geob200_backbone_forward(ctypes.byref(self.backbone), feats.data_ptr(), parr, rows, narr, nw, sarr, sw, uarr, uw,
+                                                 oarr, gn.data_ptr(), gn.numel(), ws.data_ptr(), ws.numel(), L.stream_ptr()),
+                    'backbone_forward')
         outs.reverse()
         return outs
+
+    def transformer_forward_batched(self, x, cloud_rows, embeddings):
+        """RPEConditionalTransformer over a batch of pairs: x rows in stack order [ref_1..ref_B, src_1..src_B],
+        ``cloud_rows`` their 2B row counts (host ints), ``embeddings`` the 2B structure embeddings (device tensors)."""
+        lib = L.lib()
+        nc = len(cloud_rows)
+        rows = (I64 * nc)(*[int(r) for r in cloud_rows])
+        earr = (P * nc)(*[e.data_ptr() for e in embeddings])
+        out = torch.empty_like(x)
+        ws_bytes = lib.geob200_transformer_batched_workspace_bytes(nc // 2, rows, self.hidden, self.heads, self.num_layers)
+        ws = L.workspace(ws_bytes, x.device, 'native_transformer')
+        L.check(lib.geob200_transformer_forward_batched(self.layers, self.num_layers, self.hidden, self.heads, x.data_ptr(), nc // 2, rows,
+                                                        earr, out.data_ptr(), ws.data_ptr(), ws.numel(), L.stream_ptr()),
+                'transformer_forward_batched')
+        return out
 
     def transformer_forward(self, x, n0, emb0, emb1):
         """RPEConditionalTransformer.forward_stacked"""

@@ -81,7 +81,13 @@ def registration_collate_fn_stack_mode(data_dicts, num_stages, voxel_size, searc
     # one H2D per tensor (asynchronous from pinned staging) straight into the stacked device tensors: no host-side
     # torch.cat (a pageable temporary would also make the copy synchronous).  The reference stacks on the host and
     # moves everything later in to_cuda (utils/torch.py:113-123).
-    collated = {k: (v.to(device, non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in collated.items()}
+    def _dev(v):
+        if isinstance(v, torch.Tensor):
+            return v.to(device, non_blocking=True)
+        if isinstance(v, list) and v and all(isinstance(x, torch.Tensor) for x in v):      # batch_size > 1: one entry per pair
+            return [x.to(device, non_blocking=True) for x in v]
+        return v
+    collated = {k: _dev(v) for k, v in collated.items()}
     points, feats = _stack_to_device(points_list, device), _stack_to_device(feats_list, device)
     collated['features'] = feats
     if precompute_data:

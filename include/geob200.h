@@ -106,6 +106,18 @@ int geob200_kpconv_group_norm(const float* s_feats, const float* q_points, const
                               const float* gamma, const float* beta, float eps, int leaky, float slope, float* pre_norm, float* y,
                               void* gn_workspace, size_t gn_workspace_bytes, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Batched forms (several pairs per forward, rows in stack order [ref_1..ref_B, src_1..src_B], cloud_rows_h[2 * n_pairs] host row
+ * counts): the statistics are taken per PAIR (cloud c belongs to pair c % n_pairs), everything else is identical.
+ * Workspace: geob200_group_norm_batched_workspace_bytes, zero-filled once. */
+size_t geob200_group_norm_batched_workspace_bytes(int64_t n_rows, int64_t channels, int64_t groups, int64_t n_pairs);
+int geob200_group_norm_batched(const float* x, int64_t n_rows, int64_t channels, int64_t groups, const float* gamma, const float* beta,
+                               float eps, const float* residual, int leaky, float slope, float* y, void* workspace, size_t workspace_bytes,
+                               void* stream, int64_t n_pairs, const int64_t* cloud_rows_h);
+int geob200_linear_group_norm_batched(const float* x, int64_t ldx, const float* weight, const float* bias, int64_t m, int64_t n, int64_t k,
+                                      int64_t groups, const float* gamma, const float* beta, float eps, const float* residual, int leaky,
+                                      float slope, float* pre_norm, float* y, void* workspace, size_t workspace_bytes, void* stream,
+                                      int64_t n_pairs, const int64_t* cloud_rows_h);
+
 /* maxpool over neighbour rows with a zero shadow row (functional.py:54-67) */
 int geob200_maxpool(const float* x, const int64_t* neighbors, int64_t n_query, int64_t n_support, int64_t n_neighbors,
                     int64_t channels, float* y, void* stream);
@@ -158,6 +170,12 @@ int geob200_gse_embed(const float* d_indices, const float* a_indices, int64_t n,
                       const float* wd_t, const float* wa_t, const float* wd, const float* wa, const float* bd, const float* ba,
                       float* embeddings, int mode, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Same over a flat list of n_rows (anchor, point) index rows -- the (i, j) pairs of several clouds concatenated:
+ * d_indices (n_rows,), a_indices (n_rows, 3) -> embeddings (n_rows, channels).  One launch for a whole batch of clouds. */
+int geob200_gse_embed_pairs(const float* d_indices, const float* a_indices, int64_t n_rows, int64_t channels, const float* div_term,
+                            const float* wd_t, const float* wa_t, const float* wd, const float* wa, const float* bd, const float* ba,
+                            float* embeddings, int mode, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Fused multi-head attention: softmax((q.k + qp.E + qb)/sqrt(d)) v  (rpe_transformer.py:51-70 with proj_p moved onto
  * q; vanilla_transformer.py:50-68 when qp = qb = embed = NULL).  q (n_query,C), k,v (n_key,C), qp (n_query,H,C),
  * qb (n_query,H), embed (n_query,n_key,C).  With a workspace and C = 128 or 256 the streaming path runs (one coalesced
@@ -166,6 +184,13 @@ size_t geob200_attention_workspace_bytes(int64_t n_query, int64_t n_key, int64_t
 int geob200_attention(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv, const float* qp,
                       const float* qb, const float* embed, int64_t n_query, int64_t n_key, int64_t channels, int64_t heads,
                       float* out, int64_t ldo, void* workspace, size_t workspace_bytes, void* stream);
+/* A batch of independent attention problems that share channels, heads and row strides (the clouds / pairs of a batched
+ * forward) in ONE launch pair; all items with embed (self-attention) or all without (cross-attention). */
+typedef struct { const float* q; const float* k; const float* v; const float* qp; const float* qb; const float* embed; float* out;
+                 int64_t n_query, n_key; } geob200_att_item_t;
+size_t geob200_attention_batched_workspace_bytes(const geob200_att_item_t* items_h, int64_t n_items, int64_t heads);
+int geob200_attention_batched(const geob200_att_item_t* items_h, int64_t n_items, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
+                              int64_t channels, int64_t heads, void* workspace, size_t workspace_bytes, void* stream);
 int geob200_head_bias(const float* q, int64_t ldq, const float* bias_p, int64_t n, int64_t channels, int64_t heads, float* qb,
                       void* stream);
 /* y = LayerNorm(a + b) (b may be NULL) */
@@ -240,6 +265,16 @@ int geob200_evaluate(const int64_t* gt_node_corr_indices, const float* gt_node_c
                      int64_t n_src_points, int mode, float rmse_threshold, float rre_threshold, float rte_threshold,
                      float* metrics, void* stream);
 
+/* Same with the three row counts optionally taken from DEVICE memory (int32, produced by geob200_node_correspondences /
+ * geob200_superpoint_matching / geob200_local_global_registration): a non-NULL *_dev pointer overrides the host value
+ * (n_node_corr: the smaller of the two), so a whole forward can be enqueued without a host read-back in between. */
+int geob200_evaluate_counts(const int64_t* gt_node_corr_indices, const float* gt_node_corr_overlaps, int64_t n_gt, const int32_t* n_gt_dev,
+                            float acceptance_overlap, const int64_t* ref_node_corr_indices, const int64_t* src_node_corr_indices,
+                            int64_t n_node_corr, const int32_t* n_node_corr_dev, const float* ref_corr_points, const float* src_corr_points,
+                            int64_t n_corr, const int32_t* n_corr_dev, float acceptance_radius, const float* gt_transform,
+                            const float* est_transform, const float* src_points, int64_t n_src_points, int mode, float rmse_threshold,
+                            float rre_threshold, float rte_threshold, float* metrics, void* stream);
+
 /* Profiling aid (bench.py roofline): while enabled, every tcgen05 GEMM launch (nn.Linear and the KPConv contraction) is
  * bracketed by CUDA events on its stream; _read synchronises them and returns the count, shapes[3i..] = (m, n, k), ms[i]. */
 int geob200_linear_profile_enable(int on);
@@ -285,6 +320,18 @@ int geob200_backbone_forward(const geob200_backbone_t* net, const float* feats, 
                              float* const* out_feats, void* gn_workspace, size_t gn_workspace_bytes, void* workspace,
                              size_t workspace_bytes, void* stream);
 
+/* Batched form (several pairs per forward, stack order [ref_1..ref_B, src_1..src_B] at every level like the reference collate
+ * with batch_size B, utils/data.py:144): identical kernels over the stacked rows; the GroupNorm statistics are taken per pair
+ * (modules/kpconv/modules.py:46-50 normalises over the stacked rows of ONE pair).  cloud_rows_h[level][2 * n_pairs]: host row
+ * counts per cloud.  n_pairs <= 32.  The GroupNorm workspace needs geob200_backbone_gn_workspace_bytes (zero-filled once). */
+size_t geob200_backbone_gn_workspace_bytes(const geob200_backbone_t* net, const int64_t* level_rows, int64_t n_pairs);
+int geob200_backbone_forward_batched(const geob200_backbone_t* net, const float* feats, const float* const* points,
+                                     const int64_t* level_rows, const int64_t* const* neighbors, const int64_t* neighbor_width,
+                                     const int64_t* const* subsampling, const int64_t* subsampling_width,
+                                     const int64_t* const* upsampling, const int64_t* upsampling_width, float* const* out_feats,
+                                     void* gn_workspace, size_t gn_workspace_bytes, void* workspace, size_t workspace_bytes, void* stream,
+                                     int64_t n_pairs, const int64_t* const* cloud_rows_h);
+
 /* one transformer layer ('self' with the structure embedding, or 'cross'); w_qkv = [Wq;Wk;Wv] (3C,C), w_kv = [Wk;Wv], wp_t = Wp^T */
 typedef struct {
     int32_t is_self, reserved;
@@ -298,6 +345,15 @@ size_t geob200_transformer_workspace_bytes(int64_t n0, int64_t n1, int64_t chann
 int geob200_transformer_forward(const geob200_tlayer_t* layers, int64_t num_layers, int64_t channels, int64_t heads, const float* x,
                                 int64_t n0, int64_t n1, const float* emb0, const float* emb1, float* out, void* workspace,
                                 size_t workspace_bytes, void* stream);
+
+/* Batched form: x rows in stack order [ref_1..ref_B, src_1..src_B] (cloud_rows_h[2B], host); embeddings_h[c] = device pointer
+ * of the structure embedding (rows_c, rows_c, C) of cloud c.  Linears / LayerNorms run once over all rows; attention is one
+ * batched launch pair per phase (geob200_attention_batched).  Same arithmetic per pair as geob200_transformer_forward. */
+size_t geob200_transformer_batched_workspace_bytes(int64_t n_pairs, const int64_t* cloud_rows_h, int64_t channels, int64_t heads,
+                                                   int64_t num_layers);
+int geob200_transformer_forward_batched(const geob200_tlayer_t* layers, int64_t num_layers, int64_t channels, int64_t heads,
+                                        const float* x, int64_t n_pairs, const int64_t* cloud_rows_h, const float* const* embeddings_h,
+                                        float* out, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

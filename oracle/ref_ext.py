@@ -32,6 +32,12 @@ def _lib():
         lib.ref_radius_neighbors.argtypes = [
             ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
             ctypes.c_void_p, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p, ctypes.c_int64]
+        lib.ref_radius_neighbors_search.restype = ctypes.c_int64
+        lib.ref_radius_neighbors_search.argtypes = [
+            ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+            ctypes.c_void_p, ctypes.c_int64, ctypes.c_float]
+        lib.ref_radius_neighbors_fetch.restype = ctypes.c_int64
+        lib.ref_radius_neighbors_fetch.argtypes = [ctypes.c_void_p, ctypes.c_int64]
         _LIB = lib
     return _LIB
 
@@ -55,12 +61,13 @@ def radius_neighbors(q_points, s_points, q_lengths, s_lengths, radius):
     _check(q_points, q_lengths)
     _check(s_points, s_lengths)
     nq, ns, b = q_points.shape[0], s_points.shape[0], q_lengths.shape[0]
-    # first call sizes the table, second fills it (the reference allocates after the search).
-    width = _lib().ref_radius_neighbors(q_points.data_ptr(), nq, s_points.data_ptr(), ns, q_lengths.data_ptr(),
-                                        s_lengths.data_ptr(), b, float(radius), None, 0)
-    out = torch.zeros((nq, width), dtype=torch.int64)
-    _lib().ref_radius_neighbors(q_points.data_ptr(), nq, s_points.data_ptr(), ns, q_lengths.data_ptr(),
-                                s_lengths.data_ptr(), b, float(radius), out.data_ptr(), width)
+    # ONE reference search; the table is allocated afterwards and filled from the kept result, as the reference's ATen
+    # wrapper does (radius_neighbors.cpp:47-66)
+    width = _lib().ref_radius_neighbors_search(q_points.data_ptr(), nq, s_points.data_ptr(), ns, q_lengths.data_ptr(),
+                                               s_lengths.data_ptr(), b, float(radius))
+    out = torch.empty((nq, width), dtype=torch.int64)
+    rc = _lib().ref_radius_neighbors_fetch(out.data_ptr(), nq * width)
+    assert rc == 0, 'ref_radius_neighbors_fetch: size mismatch'
     return out
 
 

@@ -55,4 +55,30 @@ int64_t ref_radius_neighbors(const float* q_points, int64_t nq, const float* s_p
   return max_count;
 }
 
+// Single-search form (what the reference does: search, THEN allocate the tensor and copy, radius_neighbors.cpp:47-66):
+// ref_radius_neighbors_search runs the reference search once and keeps the index list; ref_radius_neighbors_fetch copies it
+// out.  Used by oracle/ref_ext.py so that a timed reference search is ONE search.
+static thread_local std::vector<long> g_last_idx;
+
+int64_t ref_radius_neighbors_search(const float* q_points, int64_t nq, const float* s_points, int64_t ns,
+                                    const int64_t* q_lengths, const int64_t* s_lengths, int64_t batch, float radius) {
+  std::vector<PointXYZ> vq(reinterpret_cast<const PointXYZ*>(q_points),
+                           reinterpret_cast<const PointXYZ*>(q_points) + nq);
+  std::vector<PointXYZ> vs(reinterpret_cast<const PointXYZ*>(s_points),
+                           reinterpret_cast<const PointXYZ*>(s_points) + ns);
+  std::vector<long> ql(q_lengths, q_lengths + batch);
+  std::vector<long> sl(s_lengths, s_lengths + batch);
+  g_last_idx.clear();
+  radius_neighbors_cpu(vq, vs, ql, sl, g_last_idx, radius);
+  return nq > 0 ? static_cast<int64_t>(g_last_idx.size()) / nq : 0;
+}
+
+int64_t ref_radius_neighbors_fetch(int64_t* out, int64_t n_values) {
+  if (static_cast<int64_t>(g_last_idx.size()) != n_values) return -1;
+  std::memcpy(out, g_last_idx.data(), sizeof(int64_t) * g_last_idx.size());
+  g_last_idx.clear();
+  g_last_idx.shrink_to_fit();
+  return 0;
+}
+
 }  // extern "C"

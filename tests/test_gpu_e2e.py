@@ -151,16 +151,19 @@ def check_forward(workload, cfg, model, pair, gold, native=False):
     valid = (inl >= 0).nonzero().flatten()
     assert valid.numel() == otaps['patch_transforms'].shape[0]
     dT = (det['patch_transforms'].cpu()[valid] - otaps['patch_transforms']).abs().flatten(1).max(dim=1)[0]
-    assert dT.median() < 1e-4 and (dT < 1e-3).float().mean() > 0.8, f'patch transforms: median {dT.median():.2e}'
+    # absolute tolerances are stated for metre-scale scenes (3DMatch / ModelNet); the translation error of a Kabsch solution
+    # scales with the coordinates (KITTI: tens of metres), so they are scaled by the extent of the patch coordinates
+    scale = max(1.0, float(out['ref_node_corr_knn_points'].abs().max()) / 2.0)
+    assert dT.median() < 1e-4 * scale and (dT < 1e-3 * scale).float().mean() > 0.8, f'patch transforms: median {dT.median():.2e}'
     dcount = (inl[valid].long() - otaps['inlier_counts']).abs()
     assert (dcount <= 2).float().mean() > 0.8, f'inlier counts differ: {dcount.tolist()}'
-    good = (dT < 1e-4)
+    good = (dT < 1e-4 * scale)
     assert int(dcount[good].max()) <= 2
     best = int(det['best'].item())
     o_best = int(valid[int(otaps['best_index'])])
     if best == o_best:
         dT_final = float((o_T - T2.cpu()).abs().max())
-        if dT_final >= 1e-4:
+        if dT_final >= 1e-4 * scale:
             # legitimate only when a residual sits on the hard inlier threshold (within the propagated float noise of the
             # hypothesis transform, ~1e-4 of the cloud scale): the refinement then re-selects a different inlier set
             assert otaps['threshold_margin'] < 2e-4 * cfg.fine_matching.acceptance_radius / 0.1 + 1e-6, \
@@ -171,8 +174,8 @@ def check_forward(workload, cfg, model, pair, gold, native=False):
             # same correspondences and same winning hypothesis as the reference run.  The refinement re-selects inliers
             # with a hard distance threshold, so the fixture is only reproducible when the oracle LGR, fed OUR assignment
             # matrix (which differs from the reference's by ~1e-5), still lands on the fixture itself
-            if float(np.abs(o_T.numpy() - gold['estimated_transform']).max()) < 1e-4 and dT_final < 1e-4:
-                assert np.abs(T - gold['estimated_transform']).max() < 1e-4, f'transform\n{T}\nvs\n{gold["estimated_transform"]}'
+            if float(np.abs(o_T.numpy() - gold['estimated_transform']).max()) < 1e-4 * scale and dT_final < 1e-4 * scale:
+                assert np.abs(T - gold['estimated_transform']).max() < 1e-4 * scale, f'transform\n{T}\nvs\n{gold["estimated_transform"]}'
             else:
                 print(f'{workload}: oracle LGR on our scores leaves the fixture transform (threshold flip in the refinement); '
                       f'compared against the oracle only')
@@ -182,7 +185,7 @@ def check_forward(workload, cfg, model, pair, gold, native=False):
         o_pos = int(otaps['best_index'])
         near_tie = abs(int(inl[best]) - int(inl[o_best])) <= 2
         b_pos = int((valid == best).nonzero()[0])
-        assert near_tie or dT[o_pos] > 1e-3 or dT[b_pos] > 1e-3, \
+        assert near_tie or dT[o_pos] > 1e-3 * scale or dT[b_pos] > 1e-3 * scale, \
             f'best hypothesis {best} ({inl[best]}) vs oracle {o_best} ({inl[o_best]}), dT {dT[o_pos]:.2e} / {dT[b_pos]:.2e}'
         print(f'{workload}: hypotheses {best} / {o_best} (inliers {int(inl[best])} / {int(inl[o_best])}, near tie {near_tie}); '
               f'final transform not compared')
