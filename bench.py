@@ -406,7 +406,8 @@ def main():
     gse_solo_ms = [s.elapsed_time(e) for s, e in events_solo.get('gse_embed', [])]
     n_c = [r['num_superpoints'][0] for r in results] + [r['num_superpoints'][1] for r in results]
     mean_n2 = float(np.mean([n * n for n in n_c])) if n_c else 0.0
-    flops = 2.0 * mean_n2 * 4 * C * C
+    clouds_per_launch = 2 * BATCH if BATCH > 1 else 1          # batch mode: ONE structure-embedding launch covers all clouds of the batch
+    flops = 2.0 * mean_n2 * 4 * C * C * clouds_per_launch
     peak_tf, peak_tf_sustained, peak_hbm, peak_src = load_peaks()
     traffic = load_traffic()
     avg_ms = float(np.mean(gse_solo_ms)) if gse_solo_ms else None
@@ -415,7 +416,7 @@ def main():
     mode_name = {0: 'fp32 CUDA cores', 1: 'tcgen05 3xTF32', 2: 'tcgen05 1xTF32', 3: 'tcgen05 3xFP16 (fp32-accurate split)', 4: 'tcgen05 3xFP16 split, CTA-pair TMA multicast of B'}[GF.GSE_MODE]
     roofline_gse = {'kernel': 'gse_embed (structure-embedding contraction)', 'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf,
                 'unit': 'TFLOP/s', 'frac': (achieved / peak_tf) if achieved else None, 'traffic': traffic.get('gse_embed_bytes_per_launch'),
-                'avg_ms_per_launch': avg_ms, 'launches_timed': len(gse_solo_ms), 'flops_per_launch': flops,
+                'avg_ms_per_launch': avg_ms, 'launches_timed': len(gse_solo_ms), 'flops_per_launch': flops, 'clouds_per_launch': clouds_per_launch,
                 'avg_ms_per_launch_with_other_streams_active': avg_ms_concurrent,
                 'timing': 'CUDA events around the launch, one pair in flight (kernel alone on the GPU), same workload, after the timed regions',
                 'share_of_gpu_time': (sum(gse_ms) / (ms_res * LANES)) if gse_ms else None, 'mode': mode_name,
@@ -428,6 +429,13 @@ def main():
     g_ms = sum(t for _, _, _, t in gemm)
     g_bytes = sum(4.0 * (m * k + n * k + m * n) for m, n, k, _ in gemm)
     big = sorted(gemm, key=lambda r: -r[3])[:3]
+    by_shape = {}
+    for m, n, k, t in gemm:
+        key = (n, k)
+        e = by_shape.setdefault(key, [0, 0.0, 0.0, 0])
+        e[0] += 1; e[1] += t; e[2] += 2.0 * m * n * k; e[3] = max(e[3], m)
+    shape_table = [{'n': n, 'k': k, 'launches': c, 'max_m': mm, 'ms_per_pair': round(t / max(n_solo, 1), 4), 'tflops': round(fl / (t * 1e-3) / 1e12, 1)}
+                   for (n, k), (c, t, fl, mm) in sorted(by_shape.items(), key=lambda kv: -kv[1][1])[:12]]
     roofline = {'kernel': 'linear_tc_kernel (tcgen05 3xTF32 GEMM: all nn.Linear + KPConv contraction)', 'bound': 'tensor',
                 'achieved': (g_flops / (g_ms * 1e-3) / 1e12) if g_ms else None, 'peak': peak_tf, 'unit': 'TFLOP/s',
                 'frac': (g_flops / (g_ms * 1e-3) / 1e12 / peak_tf) if g_ms else None,
@@ -438,7 +446,7 @@ def main():
                 'launches_timed': n_gemm, 'launches_per_pair': n_gemm / max(n_solo, 1), 'ms_per_pair': g_ms / max(n_solo, 1),
                 'flops_per_pair': g_flops / max(n_solo, 1), 'algorithmic_bytes_per_pair': g_bytes / max(n_solo, 1),
                 'achieved_GBps': (g_bytes / (g_ms * 1e-3) / 1e9) if g_ms else None, 'hbm_peak_GBps': peak_hbm,
-                'slowest_launches_m_n_k_ms': [[m, n, k, round(t, 4)] for m, n, k, t in big],
+                'slowest_launches_m_n_k_ms': [[m, n, k, round(t, 4)] for m, n, k, t in big], 'time_by_weight_shape': shape_table,
                 'share_of_gpu_time': (g_ms / max(n_solo, 1)) / (ms_res / (K * S) * LANES) if g_ms else None,
                 'timing': 'CUDA events around every launch, one pair in flight (kernel alone on the GPU), same workload, after the timed regions',
                 'note': 'a family of ~80 small GEMMs per pair: most launches cover <= 27 CTAs and are latency-bound (K-loop of one CTA), '

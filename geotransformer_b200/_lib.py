@@ -91,7 +91,9 @@ _sig('geob200_backbone_forward', c_int, P, P, P, P, P, P, P, P, P, P, P, P, SZ, 
 _sig('geob200_transformer_workspace_bytes', SZ, I64, I64, I64, I64, I64)
 _sig('geob200_transformer_forward', c_int, P, I64, I64, I64, P, I64, I64, P, P, P, P, SZ, P)
 _sig('geob200_backbone_gn_workspace_bytes', SZ, P, P, I64)
-_sig('geob200_backbone_forward_batched', c_int, P, P, P, P, P, P, P, P, P, P, P, P, SZ, P, SZ, P, I64, P)
+_sig('geob200_backbone_forward_batched', c_int, P, P, P, P, P, P, P, P, P, P, P, P, SZ, P, SZ, P, I64, P, P)
+_sig('geob200_cloud_max_count', c_int, P, I64, I64, I64, I64, P, P, P)
+_sig('geob200_maxpool_batched', c_int, P, P, I64, I64, I64, I64, P, I64, P, P, P)
 _sig('geob200_transformer_batched_workspace_bytes', SZ, I64, P, I64, I64, I64)
 _sig('geob200_transformer_forward_batched', c_int, P, I64, I64, I64, P, I64, P, P, P, P, SZ, P)
 _sig('geob200_attention_batched_workspace_bytes', SZ, P, I64, I64)

@@ -109,6 +109,9 @@ int kpconv_group_norm_impl(const float* s_feats, const float* q_points, const fl
                            void* gn_workspace, size_t gn_workspace_bytes, void* workspace, size_t workspace_bytes, void* stream,
                            const GnSeg* seg);
 
+int maxpool_seg(const float* x, const int64_t* neighbors, int64_t n_query, int64_t n_support, int64_t n_neighbors, int64_t channels,
+                float* y, const GnSeg* seg, const int* cloud_max, void* stream);
+
 // Bump allocator over a caller-provided workspace.
 struct Arena {
     char* base;

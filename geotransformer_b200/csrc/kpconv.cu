@@ -592,53 +592,59 @@ __global__ void __launch_bounds__(256) gn_tile_stats_kernel(const float* __restr
     for (int i = threadIdx.x; i < 2 * slots; i += blockDim.x) partial[(long long)blockIdx.x * 2 * slots + i] = sh[i];
 }
 
-// One CTA per pair: folds the tile partials of the tiles lying completely inside one of the pair's clouds and adds the rows of
-// the (at most two per cloud) tiles that straddle a cloud boundary directly from the activations.  mean_rstd [pair][G][2].
-__global__ void __launch_bounds__(1024) gn_seg_finalize_kernel(const double* __restrict__ partial, const float* __restrict__ x, int C,
-                                                               int slots_total, int spg, int G, double eps, GnSeg seg,
-                                                               float* __restrict__ mean_rstd) {
+// One 128-thread CTA per (group, pair): folds the tile partials of the tiles lying completely inside one of the pair's clouds
+// and adds the rows of the (at most two per cloud) tiles that straddle a cloud boundary directly from the activations; the
+// threads stride over the (tile, slot) entries and the edge elements (short dependent chains: the kernel is pure latency).
+// mean_rstd [pair][G][2].
+__global__ void __launch_bounds__(128) gn_seg_finalize_kernel(const double* __restrict__ partial, const float* __restrict__ x, int C,
+                                                              int slots_total, int spg, int G, double eps, GnSeg seg,
+                                                              float* __restrict__ mean_rstd) {
+    __shared__ double red[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int p = blockIdx.x;
+    const int g = blockIdx.x, p = blockIdx.y;
     const int cpg = C / G;
     const double2* part = reinterpret_cast<const double2*>(partial);
-    for (int g = warp; g < G; g += 32) {
-        double sa = 0.0, sb = 0.0;
-        long long rows = 0;
-        for (int c = p; c < seg.n_clouds; c += seg.n_pairs) {
-            const int r0 = seg.start[c], r1 = seg.start[c + 1];
-            rows += r1 - r0;
-            int t0 = (r0 + 127) / 128, t1 = r1 / 128;          // full tiles [t0, t1)
-            if (t1 < t0) t1 = t0;                              // the cloud lies inside one tile: all rows direct
-            for (int sl = 0; sl < spg; ++sl)
-                for (int t = t0 + lane; t < t1; t += 32) {
-                    const double2 v = part[(long long)t * slots_total + (long long)g * spg + sl];
-                    sa += v.x;
-                    sb += v.y;
-                }
-            const int e0 = min(r1, t0 * 128);                  // rows [r0, e0) and [b1, r1) are in straddling tiles
-            const int b1 = min(r1, max(e0, t1 * 128));
-            const int n_edge = (e0 - r0) + (r1 - b1);
-            for (int i = lane; i < n_edge * cpg; i += 32) {
-                const int ri = i / cpg, j = i % cpg;
-                const int r = ri < e0 - r0 ? r0 + ri : b1 + (ri - (e0 - r0));
-                const double v = (double)x[(long long)r * C + g * cpg + j];
-                sa += v;
-                sb += v * v;
-            }
+    double sa = 0.0, sb = 0.0;
+    long long rows = 0;
+    for (int c = p; c < seg.n_clouds; c += seg.n_pairs) {
+        const int r0 = seg.start[c], r1 = seg.start[c + 1];
+        rows += r1 - r0;
+        int t0 = (r0 + 127) / 128, t1 = r1 / 128;          // full tiles [t0, t1)
+        if (t1 < t0) t1 = t0;                              // the cloud lies inside one tile: all rows direct
+        const int n_full = (t1 - t0) * spg;                // (tile, slot-of-group) entries
+        for (int i = threadIdx.x; i < n_full; i += 128) {
+            const int t = t0 + i / spg, sl = i % spg;
+            const double2 v = part[(long long)t * slots_total + (long long)g * spg + sl];
+            sa += v.x;
+            sb += v.y;
         }
+        const int e0 = min(r1, t0 * 128);                  // rows [r0, e0) and [b1, r1) are in straddling tiles
+        const int b1 = min(r1, max(e0, t1 * 128));
+        const int n_edge = (e0 - r0) + (r1 - b1);
+        for (int i = threadIdx.x; i < n_edge * cpg; i += 128) {
+            const int ri = i / cpg, j = i % cpg;
+            const int r = ri < e0 - r0 ? r0 + ri : b1 + (ri - (e0 - r0));
+            const double v = (double)x[(long long)r * C + g * cpg + j];
+            sa += v;
+            sb += v * v;
+        }
+    }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            sa += __shfl_xor_sync(0xffffffffu, sa, o);
-            sb += __shfl_xor_sync(0xffffffffu, sb, o);
-        }
-        if (lane == 0) {
-            const double count = (double)cpg * (double)rows;
-            const double mean = sa / count;
-            double var = sb / count - mean * mean;
-            if (var < 0.0) var = 0.0;
-            mean_rstd[((long long)p * G + g) * 2] = (float)mean;
-            mean_rstd[((long long)p * G + g) * 2 + 1] = (float)(1.0 / sqrt(var + eps));
-        }
+    for (int o = 16; o > 0; o >>= 1) {
+        sa += __shfl_xor_sync(0xffffffffu, sa, o);
+        sb += __shfl_xor_sync(0xffffffffu, sb, o);
+    }
+    if (lane == 0) { red[2 * warp] = sa; red[2 * warp + 1] = sb; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        sa = (red[0] + red[2]) + (red[4] + red[6]);
+        sb = (red[1] + red[3]) + (red[5] + red[7]);
+        const double count = (double)cpg * (double)rows;
+        const double mean = sa / count;
+        double var = sb / count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        mean_rstd[((long long)p * G + g) * 2] = (float)mean;
+        mean_rstd[((long long)p * G + g) * 2 + 1] = (float)(1.0 / sqrt(var + eps));
     }
 }
 
@@ -696,6 +702,69 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
         o[u] = t;
     }
     reinterpret_cast<float4*>(y)[i] = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+// Batched maxpool: the reference cuts a neighbour table to min(limit, max neighbour count OF THE PAIR) columns
+// (radius_search.py:25-26 on the pair's own collate), and a row whose count equals that width has no shadow entry in its max.
+// A batched table is as wide as the widest pair needs, so the columns past a pair's own width must not exist for its rows:
+// cloud_max[c] = max neighbour count over the query rows of cloud c (geob200_cloud_max_count); pair width =
+// min(H, max(cloud_max[p], cloud_max[B + p])).
+__global__ void __launch_bounds__(256) maxpool_seg_kernel(const float* __restrict__ x, const long long* __restrict__ nbr, int H,
+                                                          int Ns, int M, int C, float* __restrict__ y, GnSeg seg,
+                                                          const int* __restrict__ cloud_max) {
+    __shared__ int starts[GEOB_MAX_CLOUDS + 1];
+    __shared__ int width[GEOB_MAX_CLOUDS];
+    for (int i = threadIdx.x; i <= seg.n_clouds; i += blockDim.x) starts[i] = seg.start[i];
+    for (int i = threadIdx.x; i < seg.n_clouds; i += blockDim.x) {
+        const int p = i % seg.n_pairs;
+        int w = 0;
+        for (int c = p; c < seg.n_clouds; c += seg.n_pairs) w = max(w, cloud_max[c]);
+        width[i] = min(H, w);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int m = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (m >= M) return;
+    int lo = 0, hi = seg.n_clouds;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (starts[mid] <= m) lo = mid; else hi = mid;
+    }
+    const int W = width[lo];
+    for (int c = lane; c < C; c += 32) {
+        float best = -INFINITY;
+        for (int h = 0; h < W; ++h) {
+            const long long idx = nbr[(long long)m * H + h];
+            const float v = (idx < Ns) ? x[idx * C + c] : 0.f;
+            best = fmaxf(best, v);
+        }
+        y[(long long)m * C + c] = best;
+    }
+}
+
+// cloud_max[c] = max over the rows of cloud c of the number of real (non-sentinel) entries of a neighbour table row
+__global__ void __launch_bounds__(256) cloud_max_count_kernel(const long long* __restrict__ nbr, int H, int Ns, GnSeg seg,
+                                                              int* __restrict__ cloud_max) {
+    __shared__ int red[8];
+    const int c = blockIdx.x;
+    const int r0 = seg.start[c], r1 = seg.start[c + 1];
+    int best = 0;
+    for (int m = r0 + (int)threadIdx.x; m < r1; m += blockDim.x) {
+        // real indices come first: binary search for the first sentinel of the row
+        int lo = 0, hi = H;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (nbr[(long long)m * H + mid] < Ns) lo = mid + 1; else hi = mid;
+        }
+        best = max(best, lo);
+    }
+    for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) best = max(best, red[w]);
+        cloud_max[c] = best;
+    }
 }
 
 // max over neighbour rows (shadow row = zeros), functional.py:54-67.  One warp per output row.
@@ -891,8 +960,8 @@ static void launch_gn_seg_apply(const float* x, const GnWs& w, const float* gamm
                                 cudaStream_t st) {
     const int cpg = (int)(channels / groups);
     const int slot_width = cpg < 32 ? cpg : 32;
-    gn_seg_finalize_kernel<<<seg.n_pairs, 1024, 0, st>>>(w.partial, x, (int)channels, (int)(channels / slot_width), cpg / slot_width,
-                                                         (int)groups, (double)eps, seg, w.mean_rstd);
+    gn_seg_finalize_kernel<<<dim3((unsigned)groups, (unsigned)seg.n_pairs), 128, 0, st>>>(
+        w.partial, x, (int)channels, (int)(channels / slot_width), cpg / slot_width, (int)groups, (double)eps, seg, w.mean_rstd);
     const long long total4 = n_rows * channels / 4;
     gn_seg_apply_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(x, w.mean_rstd, gamma, beta, residual, y, total4, (int)channels,
                                                                          cpg, (int)groups, leaky, slope, seg);
@@ -1130,4 +1199,36 @@ int geob200_linear_group_norm_batched(const float* x, int64_t ldx, const float* 
                                            workspace, workspace_bytes, stream, &seg);
 }
 
+/* cloud_max[c] (device int32[2 * n_pairs]) = widest row (number of real neighbours) among the query rows of cloud c */
+int geob200_cloud_max_count(const int64_t* neighbors, int64_t n_query, int64_t n_support, int64_t n_neighbors, int64_t n_pairs,
+                            const int64_t* cloud_rows_h, int32_t* cloud_max, void* stream) {
+    geob200::GnSeg seg;
+    if (geob200::make_seg(&seg, n_pairs, cloud_rows_h, n_query)) return -2;
+    geob200::cloud_max_count_kernel<<<seg.n_clouds, 256, 0, (cudaStream_t)stream>>>((const long long*)neighbors, (int)n_neighbors,
+                                                                                   (int)n_support, seg, cloud_max);
+    GEOB_CHECK_LAUNCH();
+    geob200::count_launches(1);
+    return 0;
+}
+
+int geob200_maxpool_batched(const float* x, const int64_t* neighbors, int64_t n_query, int64_t n_support, int64_t n_neighbors,
+                            int64_t channels, float* y, int64_t n_pairs, const int64_t* cloud_rows_h, const int32_t* cloud_max,
+                            void* stream) {
+    geob200::GnSeg seg;
+    if (geob200::make_seg(&seg, n_pairs, cloud_rows_h, n_query)) return -2;
+    return geob200::maxpool_seg(x, neighbors, n_query, n_support, n_neighbors, channels, y, &seg, cloud_max, stream);
+}
+
 }  // extern "C"
+
+namespace geob200 {
+int maxpool_seg(const float* x, const int64_t* neighbors, int64_t n_query, int64_t n_support, int64_t n_neighbors, int64_t channels,
+                float* y, const GnSeg* seg, const int* cloud_max, void* stream) {
+    maxpool_seg_kernel<<<(unsigned)((n_query + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, (const long long*)neighbors, (int)n_neighbors,
+                                                                                      (int)n_support, (int)n_query, (int)channels, y, *seg,
+                                                                                      cloud_max);
+    GEOB_CHECK_LAUNCH();
+    count_launches(1);
+    return 0;
+}
+}  // namespace geob200

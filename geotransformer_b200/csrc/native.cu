@@ -15,6 +15,7 @@
 namespace geob200 {
 
 struct Ctx {
+    const int* const* sub_cloud_max = nullptr;     // batched: per level, widest subsampling row per cloud (device), see maxpool_seg_kernel
     Arena ar;
     void* gn_ws;
     size_t gn_ws_bytes;
@@ -86,7 +87,8 @@ static int run_unary(Ctx& c, const geob200_linear_t& l, const geob200_norm_t& n,
 }
 
 static int run_resblock(Ctx& c, const geob200_resblock_t& b, const float* feats, int64_t ns, const float* q_pts, const float* s_pts,
-                        const int64_t* nbr, int64_t m, int64_t h, float* out, const GnSeg* seg_s, const GnSeg* seg_q) {
+                        const int64_t* nbr, int64_t m, int64_t h, float* out, const GnSeg* seg_s, const GnSeg* seg_q,
+                        const int* cloud_max = nullptr) {
     const float* x = feats;
     if (b.has_unary1) {
         float* u = c.fl(ns, b.unary1.c_out);
@@ -100,7 +102,11 @@ static int run_resblock(Ctx& c, const geob200_resblock_t& b, const float* feats,
     if (b.strided) {
         float* mp = c.fl(m, b.c_in);
         GEOB_REQUIRE(c.ar.ok(), "native: arena too small (maxpool)");
-        TRY(geob200_maxpool(feats, nbr, m, ns, h, b.c_in, mp, c.stream));
+        if (seg_q != nullptr && cloud_max != nullptr) {
+            TRY(maxpool_seg(feats, nbr, m, ns, h, b.c_in, mp, seg_q, cloud_max, c.stream));
+        } else {
+            TRY(geob200_maxpool(feats, nbr, m, ns, h, b.c_in, mp, c.stream));
+        }
         sc = mp;
     }
     if (b.has_shortcut) {
@@ -136,7 +142,7 @@ int geob200_backbone_forward(const geob200_backbone_t* net, const float* feats, 
                              size_t gn_workspace_bytes, void* workspace, size_t workspace_bytes, void* stream) {
     return geob200_backbone_forward_batched(net, feats, points, level_rows, neighbors, neighbor_width, subsampling, subsampling_width,
                                             upsampling, upsampling_width, out_feats, gn_workspace, gn_workspace_bytes, workspace,
-                                            workspace_bytes, stream, 1, nullptr);
+                                            workspace_bytes, stream, 1, nullptr, nullptr);
 }
 
 size_t geob200_backbone_gn_workspace_bytes(const geob200_backbone_t* net, const int64_t* level_rows, int64_t n_pairs) {
@@ -148,7 +154,8 @@ int geob200_backbone_forward_batched(const geob200_backbone_t* net, const float*
                                      const int64_t* const* subsampling, const int64_t* subsampling_width,
                                      const int64_t* const* upsampling, const int64_t* upsampling_width, float* const* out_feats,
                                      void* gn_workspace, size_t gn_workspace_bytes, void* workspace, size_t workspace_bytes, void* stream,
-                                     int64_t n_pairs, const int64_t* const* cloud_rows_h) {
+                                     int64_t n_pairs, const int64_t* const* cloud_rows_h, const int32_t* const* sub_cloud_max) {
+    GEOB_REQUIRE(n_pairs == 1 || sub_cloud_max != nullptr, "backbone: batched execution needs the per-cloud subsampling widths");
     GEOB_REQUIRE(net->num_stages >= 2 && net->num_stages <= GEOB200_MAX_STAGES, "backbone: num_stages out of range");
     GEOB_REQUIRE(n_pairs >= 1 && 2 * n_pairs <= GEOB_MAX_CLOUDS, "backbone: 1 <= pairs per batch <= %d", GEOB_MAX_CLOUDS / 2);
     GEOB_REQUIRE(n_pairs == 1 || cloud_rows_h != nullptr, "backbone: batched execution needs the per-cloud row counts of every level");
@@ -187,7 +194,7 @@ int geob200_backbone_forward_batched(const geob200_backbone_t* net, const float*
         const geob200_resblock_t& b1 = net->blocks[bi++];
         float* o1 = c.fl(m, b1.unary2.c_out);
         TRY(run_resblock(c, b1, enc[lvl - 1], ns, points[lvl], points[lvl - 1], subsampling[lvl - 1], m, subsampling_width[lvl - 1], o1,
-                         sg[lvl - 1], sg[lvl]));
+                         sg[lvl - 1], sg[lvl], sub_cloud_max != nullptr ? sub_cloud_max[lvl - 1] : nullptr));
         const geob200_resblock_t& b2 = net->blocks[bi++];
         float* o2 = c.fl(m, b2.unary2.c_out);
         TRY(run_resblock(c, b2, o1, m, points[lvl], points[lvl], neighbors[lvl], m, neighbor_width[lvl], o2, sg[lvl], sg[lvl]));

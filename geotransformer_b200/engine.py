@@ -103,7 +103,15 @@ class RegistrationEngine:
         stream = self.streams[slot]
         b = self.cfg.backbone
         n = len(chunk)
+        marks = None
+        if self.stage_times is not None:
+            marks = []
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            marks.append(('begin', e))
         data = registration_collate_fn_stack_mode(chunk, b.num_stages, b.init_voxel_size, b.init_radius, self.limits, device=self.device)
+        if marks is not None:
+            data['_stage_events'] = marks
         r_dev, r_host = self.r_dev[slot][:n], self.r_host[slot][:n]
         if n == 1:             # a trailing single pair: the one-pair forward
             out = self.model(data)
@@ -123,6 +131,9 @@ class RegistrationEngine:
         done = torch.cuda.Event()
         done.record(stream)
         done.synchronize()
+        if marks is not None:          # per-stage GPU time of this batch on its main stream (label = the interval ending at that mark)
+            for (_, e0), (label, e1) in zip(marks[:-1], marks[1:]):
+                self.stage_times.setdefault('collate' if label == 'start' else label, []).append(e0.elapsed_time(e1))
         lens_c = data['lengths_host'][-1]
         res = []
         for p in range(n):

@@ -54,6 +54,14 @@ class GeoTransformer(nn.Module):
         native = getattr(self, '_native', None)
         if native is None:
             raise RuntimeError('forward_batch needs the native stage drivers: call enable_native(model) first')
+        marks = data_dict.get('_stage_events')            # profiling hook: list receiving (label, CUDA event) pairs
+
+        def mark(label):
+            if marks is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append((label, e))
+        mark('start')
         B = int(data_dict['batch_size'])
         lens_h = data_dict.get('lengths_host') or [l.tolist() for l in data_dict['lengths']]
         fl, K = self.fine_level, self.num_points_in_patch
@@ -118,6 +126,7 @@ class GeoTransformer(nn.Module):
         # ---- backbone over all pairs (main stream, overlaps the grouping)
         feats_list = native.backbone_forward(data_dict['features'], data_dict)
         feats_c, feats_f = feats_list[-1], feats_list[0]
+        mark('backbone')
 
         # ---- structure embeddings of all clouds in one launch, transformer over all rows
         tr = self.transformer
@@ -139,13 +148,16 @@ class GeoTransformer(nn.Module):
         GF.gse_embed_flat(d_all, a_all, eo[-1], emb_mod.embedding.div_term, emb_mod.proj_d.weight.detach(), emb_mod.proj_a.weight.detach(),
                           emb_mod.proj_d.bias.detach(), emb_mod.proj_a.bias.detach(), wd_t, wa_t, E_all)
         embs = [E_all[eo[c]:eo[c + 1]] for c in range(2 * B)]
+        mark('structure_embedding')
         x = GF.linear(feats_c, tr.in_proj.weight, tr.in_proj.bias)
         x = native.transformer_forward_batched(x, rows_c, embs)
         y = GF.linear(x, tr.out_proj.weight, tr.out_proj.bias)
         y_n = GF.l2_normalize(y)
+        mark('transformer')
 
         # ---- per-pair tail on the side streams
         join()          # grouping results are consumed below on arbitrary side streams
+        mark('join_grouping+gt')
         fork()
         outs = []
         cm, fm = self.coarse_matching, self.fine_matching
@@ -181,6 +193,7 @@ class GeoTransformer(nn.Module):
                                     n_node_corr=corr_count, n_corr=n_corr)
                 outs.append(o)
         join()
+        mark('matching+sinkhorn+lgr+metrics')
         if no_sync:
             return outs if keep_outputs else None
         # trim the capacity tensors to the counts (one host sync for the whole batch)

@@ -160,9 +160,15 @@ class NativeModel:
             lens = data_dict['lengths_host']
             keep = [(I64 * (2 * n_pairs))(*[int(v) for v in lens[l]]) for l in range(S)]
             carr = (P * S)(*[ctypes.cast(k, P).value for k in keep])
+            # widest subsampling row per cloud: the strided blocks' maxpool sees each pair at its own table width
+            cmax = torch.empty((S - 1, 2 * n_pairs), dtype=torch.int32, device=dev)
+            for l in range(S - 1):
+                L.check(lib.geob200_cloud_max_count(sub[l].data_ptr(), sub[l].shape[0], pts[l].shape[0], sub[l].shape[1], n_pairs, keep[l + 1],
+                                                    cmax[l].data_ptr(), L.stream_ptr()), 'cloud_max_count')
+            marr = (P * S)(*([cmax[l].data_ptr() for l in range(S - 1)] + [None]))
             L.check(lib.geob200_backbone_forward_batched(ctypes.byref(self.backbone), feats.data_ptr(), parr, rows, narr, nw, sarr, sw,
                                                          uarr, uw, oarr, gn.data_ptr(), gn.numel(), ws.data_ptr(), ws.numel(),
-                                                         L.stream_ptr(), n_pairs, carr), 'backbone_forward_batched')
+                                                         L.stream_ptr(), n_pairs, carr, marr), 'backbone_forward_batched')
         else:
             L.check(lib.geob200_backbone_forward(ctypes.byref(self.backbone), feats.data_ptr(), parr, rows, narr, nw, sarr, sw, uarr, uw,
                                                  oarr, gn.data_ptr(), gn.numel(), ws.data_ptr(), ws.numel(), L.stream_ptr()),

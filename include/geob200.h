@@ -122,6 +122,14 @@ int geob200_linear_group_norm_batched(const float* x, int64_t ldx, const float* 
 int geob200_maxpool(const float* x, const int64_t* neighbors, int64_t n_query, int64_t n_support, int64_t n_neighbors,
                     int64_t channels, float* y, void* stream);
 
+/* Batched maxpool over a table that is wider than a pair's own (radius_search.py:25-26 cuts to the pair's max count):
+ * columns past min(n_neighbors, max(cloud_max[p], cloud_max[B + p])) are ignored for the rows of pair p. */
+int geob200_cloud_max_count(const int64_t* neighbors, int64_t n_query, int64_t n_support, int64_t n_neighbors, int64_t n_pairs,
+                            const int64_t* cloud_rows_h, int32_t* cloud_max, void* stream);
+int geob200_maxpool_batched(const float* x, const int64_t* neighbors, int64_t n_query, int64_t n_support, int64_t n_neighbors,
+                            int64_t channels, float* y, int64_t n_pairs, const int64_t* cloud_rows_h, const int32_t* cloud_max,
+                            void* stream);
+
 /* y[m] = [ x_pad[up_indices[m*up_stride]] | skip[m] ]: nearest_upsample (functional.py:6-22) fused with the
  * torch.cat of the decoder (backbone.py:75-76).  skip may be NULL (c2 = 0). */
 int geob200_upsample_concat(const float* x, const int64_t* up_indices, int64_t up_stride, int64_t n_support,
@@ -323,14 +331,16 @@ int geob200_backbone_forward(const geob200_backbone_t* net, const float* feats, 
 /* Batched form (several pairs per forward, stack order [ref_1..ref_B, src_1..src_B] at every level like the reference collate
  * with batch_size B, utils/data.py:144): identical kernels over the stacked rows; the GroupNorm statistics are taken per pair
  * (modules/kpconv/modules.py:46-50 normalises over the stacked rows of ONE pair).  cloud_rows_h[level][2 * n_pairs]: host row
- * counts per cloud.  n_pairs <= 32.  The GroupNorm workspace needs geob200_backbone_gn_workspace_bytes (zero-filled once). */
+ * counts per cloud.  n_pairs <= 32.  The GroupNorm workspace needs geob200_backbone_gn_workspace_bytes (zero-filled once).
+ * sub_cloud_max[level][2 * n_pairs] (device int32, geob200_cloud_max_count of the subsampling tables): the strided blocks'
+ * maxpool must see every pair's table at the width the pair's own collate would have cut it to (geob200_maxpool_batched). */
 size_t geob200_backbone_gn_workspace_bytes(const geob200_backbone_t* net, const int64_t* level_rows, int64_t n_pairs);
 int geob200_backbone_forward_batched(const geob200_backbone_t* net, const float* feats, const float* const* points,
                                      const int64_t* level_rows, const int64_t* const* neighbors, const int64_t* neighbor_width,
                                      const int64_t* const* subsampling, const int64_t* subsampling_width,
                                      const int64_t* const* upsampling, const int64_t* upsampling_width, float* const* out_feats,
                                      void* gn_workspace, size_t gn_workspace_bytes, void* workspace, size_t workspace_bytes, void* stream,
-                                     int64_t n_pairs, const int64_t* const* cloud_rows_h);
+                                     int64_t n_pairs, const int64_t* const* cloud_rows_h, const int32_t* const* sub_cloud_max);
 
 /* one transformer layer ('self' with the structure embedding, or 'cross'); w_qkv = [Wq;Wk;Wv] (3C,C), w_kv = [Wk;Wv], wp_t = Wp^T */
 typedef struct {

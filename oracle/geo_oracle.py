@@ -509,6 +509,13 @@ def local_global_registration(cfg, ref_knn_pts, src_knn_pts, ref_masks, src_mask
         margins = [float((res_all[best] - fm.acceptance_radius).abs().min())]
         if taps is not None:
             taps['patch_transforms'], taps['inlier_counts'], taps['best_index'] = Ts, inl.sum(dim=1), best
+            # conditioning of every per-patch Kabsch problem (test diagnostics only): ratio of the two largest singular values
+            # of the weighted, centred source points -- near 0 for (almost) collinear correspondences, whose rotation about
+            # the line is undetermined and differs between SVD implementations by far more than rounding
+            w = bw / (bw.sum(dim=1, keepdim=True) + 1e-5)
+            cen = bs - (bs * w.unsqueeze(2)).sum(dim=1, keepdim=True)
+            sv = torch.linalg.svdvals(cen * w.sqrt().unsqueeze(2))
+            taps['patch_conditioning'] = sv[:, 1] / sv[:, 0].clamp(min=1e-12)
     else:
         T = weighted_procrustes(src_c, ref_c, sc)
         res = torch.linalg.norm(ref_c - apply_transform(src_c, T), dim=1)

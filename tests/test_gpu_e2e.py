@@ -113,6 +113,14 @@ def check_forward(workload, cfg, model, pair, gold, native=False):
     out = model(data)
     ms = out['matching_scores'].reshape(out['matching_scores'].shape[0], -1)[torch.from_numpy(gold['matching_scores_rows']).cuda()].cpu().numpy()
     want = gold['matching_scores_sample']
+    # a sampled patch is comparable element by element only if both of its point lists are the reference's (a patch slot that
+    # flipped between near-tied distances above permutes a row / column of its assignment matrix)
+    same_r = (taps['ref_node_knn_indices'].cpu() == torch.from_numpy(gold['ref_node_knn_indices'].astype(np.int64))).all(dim=1)
+    same_s = (taps['src_node_knn_indices'].cpu() == torch.from_numpy(gold['src_node_knn_indices'].astype(np.int64))).all(dim=1)
+    keep = np.array([bool(same_r[gold['ref_node_corr_indices'][p]]) and bool(same_s[gold['src_node_corr_indices'][p]])
+                     for p in gold['matching_scores_rows']])
+    assert keep.sum() >= len(keep) // 2, 'too many sampled patches have permuted point lists'
+    ms, want = ms[keep], want[keep]
     live = want > -1e11
     assert np.abs(ms[live] - want[live]).max() < 2e-4, f'matching_scores {np.abs(ms[live] - want[live]).max():.2e}'
     # fine correspondences: identical rows in identical order, except entries whose acceptance is decided by a value
@@ -154,7 +162,13 @@ def check_forward(workload, cfg, model, pair, gold, native=False):
     # absolute tolerances are stated for metre-scale scenes (3DMatch / ModelNet); the translation error of a Kabsch solution
     # scales with the coordinates (KITTI: tens of metres), so they are scaled by the extent of the patch coordinates
     scale = max(1.0, float(out['ref_node_corr_knn_points'].abs().max()) / 2.0)
-    assert dT.median() < 1e-4 * scale and (dT < 1e-3 * scale).float().mean() > 0.8, f'patch transforms: median {dT.median():.2e}'
+    # ... and the bulk criterion is applied to the well-conditioned problems only (second singular value of the centred
+    # source points >= 20 % of the first; the oracle reports it): a near-collinear patch leaves the rotation about its line
+    # to the SVD implementation (fp32 LAPACK there, double Jacobi here)
+    well = otaps['patch_conditioning'] > 0.2
+    assert dT.median() < 1e-4 * scale, f'patch transforms: median {dT.median():.2e}'
+    assert (dT[well] < 1e-3 * scale).float().mean() > 0.9, \
+        f'patch transforms: {(dT[well] >= 1e-3 * scale).sum()} of {int(well.sum())} well-conditioned patches differ by more than {1e-3 * scale:.1e}'
     dcount = (inl[valid].long() - otaps['inlier_counts']).abs()
     assert (dcount <= 2).float().mean() > 0.8, f'inlier counts differ: {dcount.tolist()}'
     good = (dT < 1e-4 * scale)
