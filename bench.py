@@ -44,6 +44,7 @@ def parse():
     ap.add_argument('--streams', type=int, default=None,
                     help='forwards in flight per GPU (one CUDA stream + host thread each); default 2 in batch mode, 4 with --batch 1')
     ap.add_argument('--pairs-per-step', type=int, default=None, help='pairs per GPU and step (default 2 x batch x streams)')
+    ap.add_argument('--attention-tma', type=int, default=None, help='1/0: TMA-staged self-attention kernels (default 1)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     return ap.parse_args()
 
@@ -292,6 +293,8 @@ def main():
         GF.GSE_MODE = args.gse_mode
     if args.linear_persistent is not None:
         _lib.lib().geob200_set_linear_persistent(int(args.linear_persistent))
+    if args.attention_tma is not None:
+        _lib.lib().geob200_set_attention_tma(int(args.attention_tma))
     cfg = make_cfg(WORKLOADS[args.workload][0])
     limits = cfg.neighbor_limits or [27, 75, 147, 157, 119][:cfg.backbone.num_stages]
     model = create_model(cfg)

@@ -64,6 +64,7 @@ _sig('geob200_gse_embed', c_int, P, P, I64, I64, P, P, P, P, P, P, P, P, c_int, 
 _sig('geob200_gse_embed_pairs', c_int, P, P, I64, I64, P, P, P, P, P, P, P, P, c_int, P, SZ, P)
 _sig('geob200_attention_workspace_bytes', SZ, I64, I64, I64)
 _sig('geob200_attention', c_int, P, I64, P, I64, P, I64, P, P, P, I64, I64, I64, I64, P, I64, P, SZ, P)
+_sig('geob200_set_attention_tma', c_int, c_int)
 _sig('geob200_head_bias', c_int, P, I64, P, I64, I64, I64, P, P)
 _sig('geob200_add_layernorm', c_int, P, P, P, P, I64, I64, F, P, P)
 _sig('geob200_l2_normalize', c_int, P, I64, I64, P, P)

@@ -9,10 +9,13 @@
 //     q_h . (Wp e + bp)_h  =  (Wp_h^T q_h) . e  +  q_h . bp_h
 // The host computes qp[n,h,:] = Wp_h^T q[n,h,:] (a tiny GEMM) and this kernel streams E once per layer:
 // scores, softmax and P.V never leave the SM.  HBM/L2-bound on the E read (N*M*C*4 bytes per cloud and layer).
+#include "attention.cuh"
 #include "common.cuh"
 #include "geob200.h"
 
 namespace geob200 {
+
+static bool g_att_tma = true;      // self-attention through the TMA-staged kernels of attention_tma.cu (geob200_set_attention_tma)
 
 // R = 2 query rows per CTA (key/value rows fetched once for both).  Keys are spread over LANES: lane <-> key m, so
 // every dot product over channels is a private register accumulation (no shuffles); q / qp are warp-broadcast
@@ -188,13 +191,6 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // them round-robin.  Each warp streams the E rows of its next ATS_DEPTH-1 groups into its private shared-memory ring with
 // cp.async (every lane later reads back exactly the 16-byte pieces it copied, so no barrier is needed): ~8 KB of E in flight
 // per warp without spending registers on it.
-// One launch covers a batch of independent attention problems (the clouds / pairs of a batched forward): the work units of all
-// items form one sequence (gprefix = running number of (query, 4-key group) units) that the persistent CTAs split evenly.
-// The descriptor travels by value in the kernel parameter space (no device allocation, no H2D copy).
-constexpr int ATT_MAX_ITEMS = 32;
-struct AttItem { const float *q, *k, *v, *qp, *qb, *E; float *out, *S; int N, M; };
-struct AttBatch { int n_items; int reserved; long long gprefix[ATT_MAX_ITEMS + 1]; AttItem it[ATT_MAX_ITEMS]; };
-
 template <int H, int J>
 __global__ void __launch_bounds__(128) att_scores_kernel(const __grid_constant__ AttBatch b, int ldq, int ldk, float div) {
     constexpr int C = 128 * J;
@@ -464,6 +460,7 @@ static int attention_streaming_batch(const geob200_att_item_t* items, int64_t n_
     AttBatch b{};
     b.n_items = (int)n_items;
     b.gprefix[0] = 0;
+    b.uprefix[0] = 0;
     size_t need = 0;
     for (int i = 0; i < (int)n_items; ++i) {
         const geob200_att_item_t& it = items[i];
@@ -481,9 +478,14 @@ static int attention_streaming_batch(const geob200_att_item_t* items, int64_t n_
         d.S = (float*)((char*)workspace + need);
         need += align_up((size_t)it.n_query * (size_t)it.n_key * (size_t)heads * sizeof(float), 256);
         b.gprefix[i + 1] = b.gprefix[i] + (long long)it.n_query * ((it.n_key + ATS_G - 1) / ATS_G);
+        b.uprefix[i + 1] = b.uprefix[i] + (long long)it.n_query;
     }
     GEOB_REQUIRE(workspace_bytes >= need, "attention: workspace too small");
     const float div = sqrtf((float)(channels / heads));   // d_model_per_head ** 0.5
+    if (g_att_tma) {
+        const int rt = attention_tma_batch(b, (int)ldq, (int)ldk, (int)ldv, (int)ldo, (int)channels, (int)heads, div, st);
+        if (rt <= 0) return rt;            // done, or a hard error; 1 = not handled there
+    }
     int rc = -2;
 #define LAUNCH_STREAM(HV)                                                                                             \
     rc = (channels == 256) ? launch_streaming<HV, 2>(b, (int)ldq, (int)ldk, (int)ldv, div, (int)ldo, st)              \
@@ -507,6 +509,12 @@ static int attention_check(int64_t channels, int64_t heads, int64_t ldq, int64_t
                  "attention: unsupported channels=%lld heads=%lld", (long long)channels, (long long)heads);
     GEOB_REQUIRE(ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0, "attention: row strides must be multiples of 4 floats");
     GEOB_REQUIRE(heads == 1 || heads == 2 || heads == 4 || heads == 8, "attention: heads must be 1, 2, 4 or 8");
+    return 0;
+}
+
+/* 1 (default): self-attention (with E) runs the TMA-staged kernels; 0: the lanes<->channels cp.async kernels */
+int geob200_set_attention_tma(int on) {
+    g_att_tma = on != 0;
     return 0;
 }
 

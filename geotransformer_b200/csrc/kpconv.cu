@@ -704,6 +704,56 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
     reinterpret_cast<float4*>(y)[i] = make_float4(o[0], o[1], o[2], o[3]);
 }
 
+// One warp pools one output row: the row's neighbour indices are fetched once (lane h holds index h, broadcast by shuffle),
+// channels are walked as float4 (coalesced 512-byte segments of a neighbour row), four neighbour rows in flight.
+__device__ __forceinline__ void maxpool_row(const float* __restrict__ x, const long long* __restrict__ nb, int W, int Ns, int C,
+                                            float* __restrict__ yrow, int lane) {
+    constexpr int NI = 5;                           // rows of up to 160 neighbours keep their indices in registers
+    if ((C & 3) == 0 && W <= 32 * NI) {
+        int idx_l[NI];
+#pragma unroll
+        for (int i = 0; i < NI; ++i) idx_l[i] = (lane + 32 * i < W) ? (int)min(nb[lane + 32 * i], (long long)Ns) : Ns;
+        const int C4 = C >> 2;
+        for (int c0 = 0; c0 < C4; c0 += 32) {       // warp-uniform trip count: every lane takes part in the shuffles
+            const int c4 = c0 + lane;
+            const bool active = c4 < C4;
+            float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            for (int h0 = 0; h0 < W; h0 += 4) {
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int h = h0 + u;
+                    int id = Ns;
+#pragma unroll
+                    for (int i = 0; i < NI; ++i) {
+                        const int t = __shfl_sync(0xffffffffu, idx_l[i], h & 31);
+                        if ((h >> 5) == i) id = t;
+                    }
+                    v[u] = (active && h < W && id < Ns) ? __ldg(reinterpret_cast<const float4*>(x + (long long)id * C) + c4)
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (h >= W) v[u] = best;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    best.x = fmaxf(best.x, v[u].x); best.y = fmaxf(best.y, v[u].y);
+                    best.z = fmaxf(best.z, v[u].z); best.w = fmaxf(best.w, v[u].w);
+                }
+            }
+            if (active) reinterpret_cast<float4*>(yrow)[c4] = best;
+        }
+        return;
+    }
+    for (int c = lane; c < C; c += 32) {
+        float best = -INFINITY;
+        for (int h = 0; h < W; ++h) {
+            const long long idx = nb[h];
+            const float v = (idx < Ns) ? x[idx * C + c] : 0.f;
+            best = fmaxf(best, v);
+        }
+        yrow[c] = best;
+    }
+}
+
 // Batched maxpool: the reference cuts a neighbour table to min(limit, max neighbour count OF THE PAIR) columns
 // (radius_search.py:25-26 on the pair's own collate), and a row whose count equals that width has no shadow entry in its max.
 // A batched table is as wide as the widest pair needs, so the columns past a pair's own width must not exist for its rows:
@@ -731,15 +781,7 @@ __global__ void __launch_bounds__(256) maxpool_seg_kernel(const float* __restric
         if (starts[mid] <= m) lo = mid; else hi = mid;
     }
     const int W = width[lo];
-    for (int c = lane; c < C; c += 32) {
-        float best = -INFINITY;
-        for (int h = 0; h < W; ++h) {
-            const long long idx = nbr[(long long)m * H + h];
-            const float v = (idx < Ns) ? x[idx * C + c] : 0.f;
-            best = fmaxf(best, v);
-        }
-        y[(long long)m * C + c] = best;
-    }
+    maxpool_row(x, nbr + (long long)m * H, W, Ns, C, y + (long long)m * C, lane);
 }
 
 // cloud_max[c] = max over the rows of cloud c of the number of real (non-sentinel) entries of a neighbour table row
@@ -773,6 +815,10 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const float* __restrict__ 
     const int lane = threadIdx.x & 31;
     const int m = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (m >= M) return;
+    if ((C & 3) == 0 && H <= 160) {
+        maxpool_row(x, nbr + (long long)m * H, H, Ns, C, y + (long long)m * C, lane);
+        return;
+    }
     for (int c = lane; c < C; c += 32) {
         float best = -INFINITY;
         for (int h = 0; h < H; ++h) {

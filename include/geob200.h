@@ -199,6 +199,9 @@ typedef struct { const float* q; const float* k; const float* v; const float* qp
 size_t geob200_attention_batched_workspace_bytes(const geob200_att_item_t* items_h, int64_t n_items, int64_t heads);
 int geob200_attention_batched(const geob200_att_item_t* items_h, int64_t n_items, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
                               int64_t channels, int64_t heads, void* workspace, size_t workspace_bytes, void* stream);
+/* self-attention kernels: 1 (default) = TMA-staged E stream (cp.async.bulk ring, q.k and P.v as tiled passes), 0 = the
+ * lanes<->channels cp.async kernels */
+int geob200_set_attention_tma(int on);
 int geob200_head_bias(const float* q, int64_t ldq, const float* bias_p, int64_t n, int64_t channels, int64_t heads, float* qb,
                       void* stream);
 /* y = LayerNorm(a + b) (b may be NULL) */

@@ -474,7 +474,8 @@ def test_transformer_layers(mn, models):
 
 @pytest.mark.parametrize('n,m,c,h,with_e', [(37, 53, 256, 4, True), (130, 130, 256, 4, True), (64, 201, 128, 4, True),
                                             (33, 65, 256, 4, False), (320, 317, 256, 4, False), (5, 3, 128, 2, True),
-                                            (40, 70, 256, 8, True), (19, 23, 64, 4, True), (70, 41, 128, 1, False)])
+                                            (40, 70, 256, 8, True), (19, 23, 64, 4, True), (70, 41, 128, 1, False), (323, 323, 256, 4, True),
+                                            (100, 100, 128, 1, True), (48, 16, 128, 2, True)])
 def test_attention_paths_vs_torch(n, m, c, h, with_e):
     """softmax((q.k + qp.E + qb)/sqrt(d)) v : streaming (lanes <-> channels) and single-kernel paths against fp64 torch;
     q/k/v are column slices of wider buffers like the fused projections"""
@@ -495,10 +496,17 @@ def test_attention_paths_vs_torch(n, m, c, h, with_e):
     cq, ck = qkv_q.cuda(), qkv_k.cuda()
     args = (cq[:, :c], ck[:, c:2 * c], ck[:, 2 * c:], h)
     kw = dict(qp=None if qp is None else qp.cuda(), qb=None if qb is None else qb.cuda(), embed=None if E is None else E.cuda())
-    got_stream = GF.attention(*args, **kw)
+    got_stream = GF.attention(*args, **kw)          # self-attention: TMA-staged E stream (attention_tma.cu); cross: cp.async path
     got_single = GF.attention(*args, streaming=False, **kw)
     close(got_stream, want, 2e-5, 'attention (default path)')
     close(got_single, want, 2e-5, 'attention (single-kernel path)')
+    from geotransformer_b200 import _lib as L
+    L.lib().geob200_set_attention_tma(0)
+    try:
+        got_cpasync = GF.attention(*args, **kw)
+    finally:
+        L.lib().geob200_set_attention_tma(1)
+    close(got_cpasync, want, 2e-5, 'attention (lanes<->channels cp.async streaming path)')
     out = torch.full((n, 2 * c), 7.0, device='cuda')                 # strided output, untouched columns stay
     GF.attention(*args, out=out[:, c:], **kw)
     assert torch.equal(out[:, c:], got_stream) and bool((out[:, :c] == 7.0).all())
