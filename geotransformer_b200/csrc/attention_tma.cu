@@ -271,6 +271,45 @@ __global__ void __launch_bounds__(256) att_pv_kernel(const __grid_constant__ Att
     }
 }
 
+// ---- plain softmax over the keys (cross-attention: no structure term) --------------------------------------------------------
+// one warp per (query, head) row of S: p = softmax(s / div), in place
+template <int H>
+__global__ void __launch_bounds__(256) att_softmax_kernel(const __grid_constant__ AttBatch b, float div) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);          // over all (item, n, h)
+    if (row >= b.uprefix[b.n_items] * H) return;
+    const long long u = row / H;
+    int ci = 0;
+    while (u >= b.uprefix[ci + 1]) ++ci;
+    const AttItem& it = b.it[ci];
+    const int M = it.M;
+    float* s = it.S + ((u - b.uprefix[ci]) * H + (row % H)) * M;
+    float mx = -INFINITY;
+    for (int m = lane; m < M; m += 32) mx = fmaxf(mx, s[m] / div);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int m = lane; m < M; m += 32) {
+        const float e = expf(s[m] / div - mx);
+        s[m] = e;
+        sum += e;
+    }
+    sum = warp_sum(sum);
+    for (int m = lane; m < M; m += 32) s[m] = s[m] / sum;
+}
+
+template <int H>
+static int launch_cross(const AttBatch& b, int ldq, int ldk, int ldv, int ldo, int D, float div, cudaStream_t st) {
+    int max_n = 0, max_m = 0;
+    for (int i = 0; i < b.n_items; ++i) { max_n = b.it[i].N > max_n ? b.it[i].N : max_n; max_m = b.it[i].M > max_m ? b.it[i].M : max_m; }
+    const dim3 qk_grid((unsigned)((max_m + ATQ_T - 1) / ATQ_T), (unsigned)((max_n + ATQ_T - 1) / ATQ_T), (unsigned)(b.n_items * H));
+    att_qk_kernel<H><<<qk_grid, 256, 0, st>>>(b, ldq, ldk, D);
+    const long long rows = b.uprefix[b.n_items] * H;
+    att_softmax_kernel<H><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(b, div);
+    const dim3 pv_grid((unsigned)((max_n + ATQ_T - 1) / ATQ_T), (unsigned)(H * ((D + 63) / 64)), (unsigned)b.n_items);
+    att_pv_kernel<H><<<pv_grid, 256, 0, st>>>(b, ldv, ldo, D);
+    return 0;
+}
+
 template <int H, int J>
 static int launch_tma(const AttBatch& b, int ldq, int ldk, int ldv, int ldo, float div, cudaStream_t st) {
     constexpr int C = 128 * J, D = C / H;
@@ -293,7 +332,20 @@ static int launch_tma(const AttBatch& b, int ldq, int ldk, int ldv, int ldo, flo
 
 // returns 1 when the shape is not handled here (caller falls back to the lanes<->channels kernels of attention.cu)
 int attention_tma_batch(const AttBatch& b, int ldq, int ldk, int ldv, int ldo, int channels, int heads, float div, cudaStream_t st) {
-    if (b.it[0].E == nullptr) return 1;                               // cross-attention has no E stream
+    if (b.it[0].E == nullptr) {                                       // cross-attention: q.k^T -> softmax -> P.v as three tiled passes
+        int rc = -2;
+        switch (heads) {
+            case 1: rc = launch_cross<1>(b, ldq, ldk, ldv, ldo, channels / heads, div, st); break;
+            case 2: rc = launch_cross<2>(b, ldq, ldk, ldv, ldo, channels / heads, div, st); break;
+            case 4: rc = launch_cross<4>(b, ldq, ldk, ldv, ldo, channels / heads, div, st); break;
+            case 8: rc = launch_cross<8>(b, ldq, ldk, ldv, ldo, channels / heads, div, st); break;
+            default: return 1;
+        }
+        if (rc != 0) return rc;
+        GEOB_CHECK_LAUNCH();
+        count_launches(3);
+        return 0;
+    }
     if (!(channels == 128 || channels == 256)) return 1;
     int max_m = 0;
     for (int i = 0; i < b.n_items; ++i) max_m = b.it[i].M > max_m ? b.it[i].M : max_m;

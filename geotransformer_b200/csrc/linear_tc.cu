@@ -86,6 +86,134 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// ---- pieces shared by the one-CTA-per-tile kernel and the persistent kernel ---------------------------------------------------
+// splitter: in-place hi = tf32_rn(x), lo = x - hi into the second buffer of each operand (element-wise, so the swizzled
+// positions are irrelevant: same offset in the hi and lo buffers).  Two 16-byte vectors per thread and iteration: their
+// shared-memory round trips overlap.  t = thread index among the NSPLIT_WARPS * 32 splitter threads.
+__device__ __forceinline__ void split_stage(unsigned char* st, int BN, int t) {
+    constexpr int NT = NSPLIT_WARPS * 32;
+    const int nvec_a = TILE_A / 16, nvec_b = BN * 128 / 16;
+    const int nvec = nvec_a + nvec_b;            // multiple of NT (BN is a multiple of 16)
+    for (int v0 = t; v0 < nvec; v0 += 2 * NT) {
+        const int v1 = v0 + NT;
+        unsigned char* p0 = (v0 < nvec_a) ? (st + v0 * 16) : (st + 2 * TILE_A + (v0 - nvec_a) * 16);
+        unsigned char* l0 = p0 + ((v0 < nvec_a) ? TILE_A : TILE_B);
+        const bool two = v1 < nvec;
+        unsigned char* p1 = !two ? p0 : (v1 < nvec_a) ? (st + v1 * 16) : (st + 2 * TILE_A + (v1 - nvec_a) * 16);
+        unsigned char* l1 = p1 + ((v1 < nvec_a) ? TILE_A : TILE_B);
+        const float4 x0 = *reinterpret_cast<float4*>(p0);
+        const float4 x1 = *reinterpret_cast<float4*>(p1);
+        float4 h0, q0, h1, q1;
+        h0.x = tf32_rn(x0.x); q0.x = x0.x - h0.x;     // round-to-nearest split: |lo| <= 2^-12 |x|, unbiased
+        h0.y = tf32_rn(x0.y); q0.y = x0.y - h0.y;
+        h0.z = tf32_rn(x0.z); q0.z = x0.z - h0.z;
+        h0.w = tf32_rn(x0.w); q0.w = x0.w - h0.w;
+        h1.x = tf32_rn(x1.x); q1.x = x1.x - h1.x;
+        h1.y = tf32_rn(x1.y); q1.y = x1.y - h1.y;
+        h1.z = tf32_rn(x1.z); q1.z = x1.z - h1.z;
+        h1.w = tf32_rn(x1.w); q1.w = x1.w - h1.w;
+        *reinterpret_cast<float4*>(p0) = h0;
+        *reinterpret_cast<float4*>(l0) = q0;
+        if (two) {
+            *reinterpret_cast<float4*>(p1) = h1;
+            *reinterpret_cast<float4*>(l1) = q1;
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// the 12 MMAs of one 32-float K chunk: main products and the (2^-11 smaller) correction products go to separate accumulators
+// (columns [acc, acc+128) and [acc+128, acc+256)): the fp32 accumulation in the tensor core truncates, so keeping the number of
+// additions into the main accumulator at K/8 instead of 3K/8 cuts the systematic error by 3x
+__device__ __forceinline__ void issue_chunk_mmas(uint32_t st, uint32_t acc, uint32_t idesc, bool first_chunk) {
+    const uint64_t a_hi = make_desc(st), a_lo = make_desc(st + TILE_A);
+    const uint64_t b_hi = make_desc(st + 2 * TILE_A), b_lo = make_desc(st + 2 * TILE_A + TILE_B);
+#pragma unroll
+    for (int kk = 0; kk < KC / 8; ++kk) {
+        const uint64_t adv = (uint64_t)(kk * 2);
+        const uint32_t first = (first_chunk && kk == 0) ? 0u : 1u;
+        umma_tf32(acc, a_hi + adv, b_hi + adv, idesc, first);
+        umma_tf32(acc + 128, a_hi + adv, b_lo + adv, idesc, first);
+        umma_tf32(acc + 128, a_lo + adv, b_hi + adv, idesc, 1u);
+    }
+}
+
+// 32 columns of both accumulators (main, corrections) of this thread's row
+__device__ __forceinline__ void tmem_ld_pair(uint32_t taddr, uint32_t (&v)[32], uint32_t (&w2)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(w2[0]), "=r"(w2[1]), "=r"(w2[2]), "=r"(w2[3]), "=r"(w2[4]), "=r"(w2[5]), "=r"(w2[6]), "=r"(w2[7]), "=r"(w2[8]),
+          "=r"(w2[9]), "=r"(w2[10]), "=r"(w2[11]), "=r"(w2[12]), "=r"(w2[13]), "=r"(w2[14]), "=r"(w2[15]), "=r"(w2[16]),
+          "=r"(w2[17]), "=r"(w2[18]), "=r"(w2[19]), "=r"(w2[20]), "=r"(w2[21]), "=r"(w2[22]), "=r"(w2[23]), "=r"(w2[24]),
+          "=r"(w2[25]), "=r"(w2[26]), "=r"(w2[27]), "=r"(w2[28]), "=r"(w2[29]), "=r"(w2[30]), "=r"(w2[31])
+        : "r"(taddr + 128));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// epilogue of one 32-column chunk of this thread's row: (main + corrections) * row scale + bias (+ ReLU), direct row-segment
+// store, and the GroupNorm column sums over the warp's 32 rows (rows past M and columns past N contribute nothing) through the
+// transposing butterfly into gn_sm[q][slot]
+__device__ __forceinline__ void finish_chunk(const uint32_t (&v)[32], const uint32_t (&w2)[32], float rs, const float* bias_s, int cc,
+                                             int relu, bool row_ok, float* yr, int nvalid, const GnFuse& gn, float2* gn_sm, int q,
+                                             int lane) {
+    float o[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+        float t = (__uint_as_float(v[c]) + __uint_as_float(w2[c])) * rs + bias_s[cc + c];
+        if (relu) t = fmaxf(t, 0.f);
+        o[c] = t;
+    }
+    if (row_ok) {
+        if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(yr) & 15) == 0)) {
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) *reinterpret_cast<float4*>(yr + c) = make_float4(o[c], o[c + 1], o[c + 2], o[c + 3]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+                if (c < nvalid) yr[c] = o[c];
+        }
+    }
+    if (gn.groups > 0) {
+        float s1[32], s2[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            const float t = (row_ok && c < nvalid) ? o[c] : 0.f;
+            s1[c] = t;
+            s2[c] = t * t;
+        }
+        float a = warp_butterfly(s1, lane), b2 = warp_butterfly(s2, lane);
+        for (int off = 1; off < gn.slot_width; off <<= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, off);
+            b2 += __shfl_xor_sync(0xffffffffu, b2, off);
+        }
+        if ((lane & (gn.slot_width - 1)) == 0) gn_sm[q * 128 + (cc + lane) / gn.slot_width] = make_float2(a, b2);
+    }
+}
+
+// 4 epilogue warps -> per-tile partial in a fixed order; gn_finalize / gn_seg_finalize (kpconv.cu) fold the tiles afterwards
+// (no fence / ticket here: the CTA must not wait for its output stores to drain).  et = thread index among the 128 epilogue threads.
+__device__ __forceinline__ void write_gn_partials(const GnFuse& gn, const float2* gn_sm, int et, int BN, int N, int n0, int tile_row) {
+    const int slots_tile = BN / gn.slot_width, slots_total = N / gn.slot_width;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (et < slots_tile) {
+        const float2 p0 = gn_sm[et], p1 = gn_sm[128 + et], p2 = gn_sm[256 + et], p3 = gn_sm[384 + et];
+        double* dst = gn.partial + ((long long)tile_row * slots_total + n0 / gn.slot_width + et) * 2;
+        dst[0] = ((double)p0.x + (double)p1.x) + ((double)p2.x + (double)p3.x);
+        dst[1] = ((double)p0.y + (double)p1.y) + ((double)p2.y + (double)p3.y);
+    }
+}
+
 __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const __grid_constant__ CUtensorMap map_x,
                                                                 const __grid_constant__ CUtensorMap map_w,
                                                                 const float* __restrict__ bias, const float* __restrict__ row_scale,
@@ -137,43 +265,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const __grid_con
             }
         }
     } else if (warp <= NSPLIT_WARPS) {
-        constexpr int NT = NSPLIT_WARPS * 32;
-        const int t = threadIdx.x - 32;              // 0..NT-1
+        const int t = threadIdx.x - 32;              // 0..NSPLIT_WARPS*32-1
         int s = 0;
         uint32_t ph = 0;
-        const int nvec_a = TILE_A / 16, nvec_b = BN * 128 / 16;
-        const int nvec = nvec_a + nvec_b;            // multiple of NT (BN is a multiple of 16)
         for (int kc = kc0; kc < kc1; ++kc) {
             mbar_wait(&raw_full[s], ph);
-            unsigned char* st = smem + s * STAGE;
-            // element-wise, so the swizzled positions are irrelevant: same offset in the hi and lo buffers.
-            // Two 16-byte vectors per thread and iteration: their shared-memory round trips overlap.
-            for (int v0 = t; v0 < nvec; v0 += 2 * NT) {
-                const int v1 = v0 + NT;
-                unsigned char* p0 = (v0 < nvec_a) ? (st + v0 * 16) : (st + 2 * TILE_A + (v0 - nvec_a) * 16);
-                unsigned char* l0 = p0 + ((v0 < nvec_a) ? TILE_A : TILE_B);
-                const bool two = v1 < nvec;
-                unsigned char* p1 = !two ? p0 : (v1 < nvec_a) ? (st + v1 * 16) : (st + 2 * TILE_A + (v1 - nvec_a) * 16);
-                unsigned char* l1 = p1 + ((v1 < nvec_a) ? TILE_A : TILE_B);
-                const float4 x0 = *reinterpret_cast<float4*>(p0);
-                const float4 x1 = *reinterpret_cast<float4*>(p1);
-                float4 h0, q0, h1, q1;
-                h0.x = tf32_rn(x0.x); q0.x = x0.x - h0.x;     // round-to-nearest split: |lo| <= 2^-12 |x|, unbiased
-                h0.y = tf32_rn(x0.y); q0.y = x0.y - h0.y;
-                h0.z = tf32_rn(x0.z); q0.z = x0.z - h0.z;
-                h0.w = tf32_rn(x0.w); q0.w = x0.w - h0.w;
-                h1.x = tf32_rn(x1.x); q1.x = x1.x - h1.x;
-                h1.y = tf32_rn(x1.y); q1.y = x1.y - h1.y;
-                h1.z = tf32_rn(x1.z); q1.z = x1.z - h1.z;
-                h1.w = tf32_rn(x1.w); q1.w = x1.w - h1.w;
-                *reinterpret_cast<float4*>(p0) = h0;
-                *reinterpret_cast<float4*>(l0) = q0;
-                if (two) {
-                    *reinterpret_cast<float4*>(p1) = h1;
-                    *reinterpret_cast<float4*>(l1) = q1;
-                }
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            split_stage(smem + s * STAGE, BN, t);
             __syncwarp();
             if (lane == 0) mbar_arrive(&split_full[s]);
             if (++s == NSTAGE) { s = 0; ph ^= 1u; }
@@ -186,20 +283,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const __grid_con
             for (int kc = kc0; kc < kc1; ++kc) {
                 mbar_wait(&split_full[s], ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t st = smem_u32(smem + s * STAGE);
-                const uint64_t a_hi = make_desc(st), a_lo = make_desc(st + TILE_A);
-                const uint64_t b_hi = make_desc(st + 2 * TILE_A), b_lo = make_desc(st + 2 * TILE_A + TILE_B);
-#pragma unroll
-                for (int kk = 0; kk < KC / 8; ++kk) {
-                    const uint64_t adv = (uint64_t)(kk * 2);
-                    // main products and the (2^-11 smaller) correction products go to separate accumulators (columns
-                    // [0,128) and [128,256)): the fp32 accumulation in the tensor core truncates, so keeping the number of
-                    // additions into the main accumulator at K/8 instead of 3K/8 cuts the systematic error by 3x
-                    const uint32_t first = (kc == kc0 && kk == 0) ? 0u : 1u;
-                    umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, first);
-                    umma_tf32(tmem_base + 128, a_hi + adv, b_lo + adv, idesc, first);
-                    umma_tf32(tmem_base + 128, a_lo + adv, b_hi + adv, idesc, 1u);
-                }
+                issue_chunk_mmas(smem_u32(smem + s * STAGE), tmem_base, idesc, kc == kc0);
                 umma_commit(&empty[s]);
                 if (++s == NSTAGE) { s = 0; ph ^= 1u; }
             }
@@ -217,29 +301,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const __grid_con
         mbar_wait(acc_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int m = m0 + q * 32 + lane;
+        const float rs = (row_scale != nullptr && m < M) ? row_scale[m] : 1.0f;   // KPConv: 1 / neighbour count
         for (int cc = 0; cc < BN; cc += 32) {
-            uint32_t v[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-                  "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-                  "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-                  "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                : "r"(taddr));
-            uint32_t w2[32];
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(w2[0]), "=r"(w2[1]), "=r"(w2[2]), "=r"(w2[3]), "=r"(w2[4]), "=r"(w2[5]), "=r"(w2[6]), "=r"(w2[7]), "=r"(w2[8]),
-                  "=r"(w2[9]), "=r"(w2[10]), "=r"(w2[11]), "=r"(w2[12]), "=r"(w2[13]), "=r"(w2[14]), "=r"(w2[15]), "=r"(w2[16]),
-                  "=r"(w2[17]), "=r"(w2[18]), "=r"(w2[19]), "=r"(w2[20]), "=r"(w2[21]), "=r"(w2[22]), "=r"(w2[23]), "=r"(w2[24]),
-                  "=r"(w2[25]), "=r"(w2[26]), "=r"(w2[27]), "=r"(w2[28]), "=r"(w2[29]), "=r"(w2[30]), "=r"(w2[31])
-                : "r"(taddr + 128));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            uint32_t v[32], w2[32];
+            tmem_ld_pair(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, v, w2);
             const int nvalid = min(32, N - (n0 + cc));
             if (splitk_out != nullptr) {              // raw partial sums of this K-slice (N is a multiple of 16: float4-aligned)
                 if (m < M) {
@@ -253,56 +318,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const __grid_con
                 }
                 continue;
             }
-            const float rs = (row_scale != nullptr && m < M) ? row_scale[m] : 1.0f;   // KPConv: 1 / neighbour count
-            float o[32];
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                float t = (__uint_as_float(v[c]) + __uint_as_float(w2[c])) * rs + bias_s[cc + c];
-                if (relu) t = fmaxf(t, 0.f);
-                o[c] = t;
-            }
-            if (m < M) {
-                float* yr = Y + (long long)m * ldy + n0 + cc;
-                if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(yr) & 15) == 0)) {
-#pragma unroll
-                    for (int c = 0; c < 32; c += 4) *reinterpret_cast<float4*>(yr + c) = make_float4(o[c], o[c + 1], o[c + 2], o[c + 3]);
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 32; ++c)
-                        if (c < nvalid) yr[c] = o[c];
-                }
-            }
-            if (gn.groups > 0) {
-                // column sums over this warp's 32 rows (rows past M and columns past N contribute nothing)
-                float s1[32], s2[32];
-                const bool rv = m < M;
-#pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const float t = (rv && c < nvalid) ? o[c] : 0.f;
-                    s1[c] = t;
-                    s2[c] = t * t;
-                }
-                float a = warp_butterfly(s1, lane), b2 = warp_butterfly(s2, lane);
-                for (int off = 1; off < gn.slot_width; off <<= 1) {
-                    a += __shfl_xor_sync(0xffffffffu, a, off);
-                    b2 += __shfl_xor_sync(0xffffffffu, b2, off);
-                }
-                if ((lane & (gn.slot_width - 1)) == 0) gn_sm[q * 128 + (cc + lane) / gn.slot_width] = make_float2(a, b2);
-            }
+            finish_chunk(v, w2, rs, bias_s, cc, relu, m < M, Y + (long long)m * ldy + n0 + cc, nvalid, gn, gn_sm, q, lane);
         }
-        if (gn.groups > 0 && splitk_out == nullptr) {
-            // 4 epilogue warps -> per-tile partial in a fixed order; gn_finalize_kernel (kpconv.cu) folds the tiles afterwards
-            // (no fence / ticket here: the CTA must not wait for its output stores to drain)
-            const int et = threadIdx.x - EPI_WARP0 * 32;
-            const int slots_tile = BN / gn.slot_width, slots_total = N / gn.slot_width;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (et < slots_tile) {
-                const float2 p0 = gn_sm[et], p1 = gn_sm[128 + et], p2 = gn_sm[256 + et], p3 = gn_sm[384 + et];
-                double* dst = gn.partial + ((long long)blockIdx.y * slots_total + n0 / gn.slot_width + et) * 2;
-                dst[0] = ((double)p0.x + (double)p1.x) + ((double)p2.x + (double)p3.x);
-                dst[1] = ((double)p0.y + (double)p1.y) + ((double)p2.y + (double)p3.y);
-            }
-        }
+        if (gn.groups > 0 && splitk_out == nullptr) write_gn_partials(gn, gn_sm, threadIdx.x - EPI_WARP0 * 32, BN, N, n0, blockIdx.y);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -372,42 +390,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_persistent_kernel(const
             }
         }
     } else if (warp <= NSPLIT_WARPS) {
-        constexpr int NT = NSPLIT_WARPS * 32;
         const int tt = threadIdx.x - 32;
         int s = 0;
         uint32_t ph = 0;
-        const int nvec_a = TILE_A / 16, nvec_b = BN * 128 / 16;
-        const int nvec = nvec_a + nvec_b;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             for (int kc = 0; kc < nk; ++kc) {
                 mbar_wait(&raw_full[s], ph);
-                unsigned char* st = smem + s * STAGE;
-                for (int v0 = tt; v0 < nvec; v0 += 2 * NT) {
-                    const int v1 = v0 + NT;
-                    unsigned char* p0 = (v0 < nvec_a) ? (st + v0 * 16) : (st + 2 * TILE_A + (v0 - nvec_a) * 16);
-                    unsigned char* l0 = p0 + ((v0 < nvec_a) ? TILE_A : TILE_B);
-                    const bool two = v1 < nvec;
-                    unsigned char* p1 = !two ? p0 : (v1 < nvec_a) ? (st + v1 * 16) : (st + 2 * TILE_A + (v1 - nvec_a) * 16);
-                    unsigned char* l1 = p1 + ((v1 < nvec_a) ? TILE_A : TILE_B);
-                    const float4 x0 = *reinterpret_cast<float4*>(p0);
-                    const float4 x1 = *reinterpret_cast<float4*>(p1);
-                    float4 h0, q0, h1, q1;
-                    h0.x = tf32_rn(x0.x); q0.x = x0.x - h0.x;
-                    h0.y = tf32_rn(x0.y); q0.y = x0.y - h0.y;
-                    h0.z = tf32_rn(x0.z); q0.z = x0.z - h0.z;
-                    h0.w = tf32_rn(x0.w); q0.w = x0.w - h0.w;
-                    h1.x = tf32_rn(x1.x); q1.x = x1.x - h1.x;
-                    h1.y = tf32_rn(x1.y); q1.y = x1.y - h1.y;
-                    h1.z = tf32_rn(x1.z); q1.z = x1.z - h1.z;
-                    h1.w = tf32_rn(x1.w); q1.w = x1.w - h1.w;
-                    *reinterpret_cast<float4*>(p0) = h0;
-                    *reinterpret_cast<float4*>(l0) = q0;
-                    if (two) {
-                        *reinterpret_cast<float4*>(p1) = h1;
-                        *reinterpret_cast<float4*>(l1) = q1;
-                    }
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                split_stage(smem + s * STAGE, BN, tt);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&split_full[s]);
                 if (++s == NSTAGE) { s = 0; ph ^= 1u; }
@@ -427,17 +416,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_persistent_kernel(const
                 for (int kc = 0; kc < nk; ++kc) {
                     mbar_wait(&split_full[s], ph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t st = smem_u32(smem + s * STAGE);
-                    const uint64_t a_hi = make_desc(st), a_lo = make_desc(st + TILE_A);
-                    const uint64_t b_hi = make_desc(st + 2 * TILE_A), b_lo = make_desc(st + 2 * TILE_A + TILE_B);
-#pragma unroll
-                    for (int kk = 0; kk < KC / 8; ++kk) {
-                        const uint64_t adv = (uint64_t)(kk * 2);
-                        const uint32_t first = (kc == 0 && kk == 0) ? 0u : 1u;
-                        umma_tf32(acc, a_hi + adv, b_hi + adv, idesc, first);
-                        umma_tf32(acc + 128, a_hi + adv, b_lo + adv, idesc, first);
-                        umma_tf32(acc + 128, a_lo + adv, b_hi + adv, idesc, 1u);
-                    }
+                    issue_chunk_mmas(smem_u32(smem + s * STAGE), acc, idesc, kc == 0);
                     umma_commit(&empty[s]);
                     if (++s == NSTAGE) { s = 0; ph ^= 1u; }
                 }
@@ -460,79 +439,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_persistent_kernel(const
             const int m = m0 + q * 32 + lane;
             const float rs = (row_scale != nullptr && m < M) ? row_scale[m] : 1.0f;
             for (int cc = 0; cc < BN; cc += 32) {
-                uint32_t v[32];
-                const uint32_t taddr = tmem_base + (uint32_t)(set * 256) + ((uint32_t)(q * 32) << 16) + (uint32_t)cc;
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-                      "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-                      "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-                      "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                    : "r"(taddr));
-                uint32_t w2[32];
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(w2[0]), "=r"(w2[1]), "=r"(w2[2]), "=r"(w2[3]), "=r"(w2[4]), "=r"(w2[5]), "=r"(w2[6]), "=r"(w2[7]), "=r"(w2[8]),
-                      "=r"(w2[9]), "=r"(w2[10]), "=r"(w2[11]), "=r"(w2[12]), "=r"(w2[13]), "=r"(w2[14]), "=r"(w2[15]), "=r"(w2[16]),
-                      "=r"(w2[17]), "=r"(w2[18]), "=r"(w2[19]), "=r"(w2[20]), "=r"(w2[21]), "=r"(w2[22]), "=r"(w2[23]), "=r"(w2[24]),
-                      "=r"(w2[25]), "=r"(w2[26]), "=r"(w2[27]), "=r"(w2[28]), "=r"(w2[29]), "=r"(w2[30]), "=r"(w2[31])
-                    : "r"(taddr + 128));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                uint32_t v[32], w2[32];
+                tmem_ld_pair(tmem_base + (uint32_t)(set * 256) + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, v, w2);
                 if (cc + 32 >= BN) {        // last chunk read: hand the accumulator set back before the stores and statistics
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&acc_empty[set]);
                 }
-                const int nvalid = min(32, N - (n0 + cc));
-                float o[32];
-#pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    float x = (__uint_as_float(v[c]) + __uint_as_float(w2[c])) * rs + bias_s[cc + c];
-                    if (relu) x = fmaxf(x, 0.f);
-                    o[c] = x;
-                }
-                if (m < M) {
-                    float* yr = Y + (long long)m * ldy + n0 + cc;
-                    if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(yr) & 15) == 0)) {
-#pragma unroll
-                        for (int c = 0; c < 32; c += 4) *reinterpret_cast<float4*>(yr + c) = make_float4(o[c], o[c + 1], o[c + 2], o[c + 3]);
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < 32; ++c)
-                            if (c < nvalid) yr[c] = o[c];
-                    }
-                }
-                if (gn.groups > 0) {
-                    float s1[32], s2[32];
-                    const bool rv = m < M;
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        const float x = (rv && c < nvalid) ? o[c] : 0.f;
-                        s1[c] = x;
-                        s2[c] = x * x;
-                    }
-                    float a = warp_butterfly(s1, lane), b2 = warp_butterfly(s2, lane);
-                    for (int off = 1; off < gn.slot_width; off <<= 1) {
-                        a += __shfl_xor_sync(0xffffffffu, a, off);
-                        b2 += __shfl_xor_sync(0xffffffffu, b2, off);
-                    }
-                    if ((lane & (gn.slot_width - 1)) == 0) gn_sm[q * 128 + (cc + lane) / gn.slot_width] = make_float2(a, b2);
-                }
+                finish_chunk(v, w2, rs, bias_s, cc, relu, m < M, Y + (long long)m * ldy + n0 + cc, min(32, N - (n0 + cc)), gn, gn_sm, q, lane);
             }
-            if (gn.groups > 0) {
-                const int slots_tile = BN / gn.slot_width, slots_total = N / gn.slot_width;
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (et < slots_tile) {
-                    const float2 p0 = gn_sm[et], p1 = gn_sm[128 + et], p2 = gn_sm[256 + et], p3 = gn_sm[384 + et];
-                    double* dst = gn.partial + ((long long)ty * slots_total + n0 / gn.slot_width + et) * 2;
-                    dst[0] = ((double)p0.x + (double)p1.x) + ((double)p2.x + (double)p3.x);
-                    dst[1] = ((double)p0.y + (double)p1.y) + ((double)p2.y + (double)p3.y);
-                }
-            }
+            if (gn.groups > 0) write_gn_partials(gn, gn_sm, et, BN, N, n0, ty);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -67,6 +67,32 @@ def test_ops_fail_loudly_on_cpu_tensors():
         GF.l2_normalize(x)
     with pytest.raises(RuntimeError):
         GF.point_to_node_partition(torch.rand(10, 3), torch.rand(2, 3), 4)
+    from geotransformer_b200.modules import ops
+    for call in (lambda: ops.knn_partition(torch.rand(10, 3), torch.rand(2, 3), 4),
+                 lambda: ops.pairwise_distance(torch.rand(10, 3), torch.rand(2, 3)),
+                 lambda: ops.get_point_to_node_indices(torch.rand(10, 3), torch.rand(2, 3)),
+                 lambda: ops.ball_query_partition(torch.rand(10, 3), torch.rand(2, 3), 0.5, 4),
+                 lambda: ops.apply_transform(torch.rand(10, 3), torch.eye(4)),
+                 lambda: GF.group_norm_batched(torch.rand(8, 32), torch.ones(32), torch.zeros(32), 32, (2, 2, 2, 2))):
+        with pytest.raises(RuntimeError):
+            call()
+
+
+def test_boundary_2_op_surface_is_complete():
+    """every name geotransformer/modules/ops/__init__.py:1-21 exports on the registration path exists here"""
+    from geotransformer_b200.modules import ops
+    for name in ('grid_subsample', 'radius_search', 'index_select', 'pairwise_distance', 'get_point_to_node_indices',
+                 'point_to_node_partition', 'knn_partition', 'ball_query_partition', 'apply_transform'):
+        assert callable(getattr(ops, name)), name
+
+
+def test_forward_batch_needs_the_native_drivers(models):
+    """the batched forward has no per-op fallback: it fails loudly instead of silently running something else"""
+    cfg, sd, model = models('3dmatch')
+    if hasattr(model, '_native'):
+        del model._native
+    with pytest.raises(RuntimeError, match='native'):
+        model.forward_batch({'batch_size': 2})
 
 
 def test_unsupported_module_options_are_rejected():
