@@ -4,14 +4,18 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload 3dmatch20k]
 
 A step = one pass of the hot path (stack-mode collate -> KPConv-FPN -> geometric transformer -> superpoint matching ->
-Sinkhorn -> local-to-global registration) over a batch of --streams synthetic pairs per rank, processed concurrently by
-geotransformer_b200.engine.RegistrationEngine (weak scaling: pair i of rank r is synth.make_pair(workload, r + i*W)).  Prints ONE JSON line (see the task contract):
-  value     pairs/s with the raw pair already resident in HBM when the timed region starts
-  e2e       pairs/s through the public API with HOST (pinned) inputs: H2D + collate + forward + D2H of the transform
-  roofline  the dominant kernel by GPU-time share (tcgen05 GEMM family), algorithmic FLOPs / CUDA-event time; the
-            structure-embedding contraction (largest single launch) is reported beside it as roofline_gse_embed
-  cpu_baseline  the reference's CPU path on this box's host cores, bounded sample (N=1 only)
---impl reference times that CPU path alone (oracle port of the forward + the reference's own C++ collate ops).
+Sinkhorn -> local-to-global registration -> Evaluator) over --pairs-per-step (64) synthetic pairs per rank, registered by
+geotransformer_b200.engine.RegistrationEngine: --batch (8) pairs per forward, --streams (2) forwards in flight (weak scaling:
+pair i of rank r is synth.make_pair(workload, r + i*W); at 8 GPUs two steps are BASELINE config 5's 1024 pairs).
+Prints ONE JSON line (see the task contract):
+  value     pairs/s with the raw pairs already resident in HBM when the timed region starts
+  e2e       pairs/s through the public API with HOST (pinned) inputs: H2D + collate + forward + D2H of transform + metrics
+  roofline  the dominant kernel family by GPU-time share (tcgen05 3xTF32 GEMMs), algorithmic FLOPs / CUDA-event time, with the
+            measured TF32 dense peak and the committed ncu DRAM traffic; the structure-embedding contraction (largest single
+            launch) is reported beside it as roofline_gse_embed
+  cpu_baseline    the reference's CPU path on this box's host cores, bounded sample (N=1 only): 16-thread and 1-thread numbers
+  gpu_eager_port  host collate + the pinned torch restatement executed as eager ops on this GPU (what a drop-in user sees today)
+--impl reference times the CPU path alone (the reference's own C++ collate ops + the oracle port of the forward).
 """
 import argparse
 import json
@@ -424,7 +428,7 @@ def main():
                 'avg_ms_per_launch': avg_ms, 'launches_timed': len(gse_solo_ms), 'flops_per_launch': flops, 'clouds_per_launch': clouds_per_launch,
                 'avg_ms_per_launch_with_other_streams_active': avg_ms_concurrent,
                 'timing': 'CUDA events around the launch, one pair in flight (kernel alone on the GPU), same workload, after the timed regions',
-                'share_of_gpu_time': (sum(gse_ms) / (ms_res * LANES)) if gse_ms else None, 'mode': mode_name,
+                'share_of_gpu_time': (avg_ms / clouds_per_launch * 2.0) / (ms_res / (K * S)) if avg_ms else None, 'mode': mode_name,
                 'peak_source': f'{peak_src} bf16 dense BURST (MEASURED_PEAKS.json; the kernel is timed alone)'}
 
     # dominant kernel by share of the step's GPU time: linear_tc_kernel (every nn.Linear and the KPConv contraction; ~80 launches
@@ -452,10 +456,12 @@ def main():
                 'flops_per_pair': g_flops / max(n_solo, 1), 'algorithmic_bytes_per_pair': g_bytes / max(n_solo, 1),
                 'achieved_GBps': (g_bytes / (g_ms * 1e-3) / 1e9) if g_ms else None, 'hbm_peak_GBps': peak_hbm,
                 'slowest_launches_m_n_k_ms': [[m, n, k, round(t, 4)] for m, n, k, t in big], 'time_by_weight_shape': shape_table,
-                'share_of_gpu_time': (g_ms / max(n_solo, 1)) / (ms_res / (K * S) * LANES) if g_ms else None,
+                'share_of_gpu_time': (g_ms / max(n_solo, 1)) / (ms_res / (K * S)) if g_ms else None,
                 'timing': 'CUDA events around every launch, one pair in flight (kernel alone on the GPU), same workload, after the timed regions',
-                'note': 'a family of ~80 small GEMMs per pair: most launches cover <= 27 CTAs and are latency-bound (K-loop of one CTA), '
-                        'see DESIGN.md section 5; share_of_gpu_time = its time per pair (kernel alone) / stream-time per pair (streams x wall)',
+                'note': 'the ~80 GEMMs of one forward (every nn.Linear + the KPConv contractions), each over the stacked rows of all pairs of the '
+                        'batch; the wide / deep shapes run at 125-133 TFLOP/s (shared-memory-bandwidth ceiling of the 3xTF32 formulation, DESIGN.md 5a), '
+                        'the narrow (N = 32, 64) and the M = 5 100 transformer shapes pull the family average down: see time_by_weight_shape; '
+                        'share_of_gpu_time = its time per pair (kernel alone) / wall time per pair of the timed region',
                 'peak_source': f'{peak_src} bf16 dense BURST (MEASURED_PEAKS.json; launches timed alone); tf32_dense_peak_measured = torch.matmul fp32 '
                                f'8192^3 with allow_tf32, best of 10, this run; the kernel executes 3 TF32 MMAs per product term'}
 

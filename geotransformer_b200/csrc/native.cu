@@ -15,7 +15,6 @@
 namespace geob200 {
 
 struct Ctx {
-    const int* const* sub_cloud_max = nullptr;     // batched: per level, widest subsampling row per cloud (device), see maxpool_seg_kernel
     Arena ar;
     void* gn_ws;
     size_t gn_ws_bytes;
