@@ -281,7 +281,8 @@ int geob200_gse_embed_pairs(const float* d_indices, const float* a_indices, int6
         int rc = geob200_gse_embed_tc(d_indices, a_indices, n_pairs, (int)channels, div_term, wd, wa, bd, ba, embeddings, mode,
                                       workspace, workspace_bytes, st);
         if (rc <= 0) return rc;
-        GEOB_REQUIRE(false, "gse_embed: tensor-core mode %d does not support C=%lld", mode, (long long)channels);
+        GEOB_REQUIRE(false, "gse_embed: tensor-core mode %d does not support C=%lld (C = 256: modes 1-4, C = 128: mode 3)", mode,
+                     (long long)channels);
     }
     if (channels == GSE_C) {
         const size_t smem = sizeof(float) * (4 * GSE_PAIRS * GSE_AST + 2 * GSE_BK * GSE_C);

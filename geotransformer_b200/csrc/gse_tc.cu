@@ -375,19 +375,20 @@ constexpr int KC16 = 64;                  // halves per 128-byte row
 constexpr int NCHUNK16 = KTOT / KC16;     // 8
 constexpr uint32_t kIdescF16 = (1u << 4) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);   // A = B = F16 (0), D = F32
 
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate, uint32_t idesc = kIdescF16) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(kIdescF16), "r"(accumulate)
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 
 // scale[0] = 2^-e with max|W| = m 2^e, m in [0.5,1)  ; scale[1] = 2^e
+template <int CC>
 __global__ void __launch_bounds__(1024) gse_absmax_kernel(const float* __restrict__ Wd, const float* __restrict__ Wa, float* __restrict__ scale) {
     __shared__ float red[32];
     float m = 0.f;
-    for (int i = threadIdx.x; i < C * 256; i += blockDim.x) m = fmaxf(m, fmaxf(fabsf(Wd[i]), fabsf(Wa[i])));
+    for (int i = threadIdx.x; i < CC * CC; i += blockDim.x) m = fmaxf(m, fmaxf(fabsf(Wd[i]), fabsf(Wa[i])));
     m = warp_max(m);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
     __syncthreads();
@@ -400,18 +401,20 @@ __global__ void __launch_bounds__(1024) gse_absmax_kernel(const float* __restric
     }
 }
 
+// CC = hidden dim (256: 3DMatch / ModelNet, 128: KITTI); B = [Wa | Wd] is (CC rows) x (2 CC halves)
+template <int CC>
 __global__ void __launch_bounds__(256) gse_pack_b_f16_kernel(const float* __restrict__ Wd, const float* __restrict__ Wa,
                                                              const float* __restrict__ bd, const float* __restrict__ ba,
                                                              const float* __restrict__ scale, __half* __restrict__ img_hi,
                                                              __half* __restrict__ img_lo, float* __restrict__ bias_sum) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < C) bias_sum[t] = ba[t] + bd[t];
-    if (t >= C * KTOT) return;
-    const int n = t / KTOT, k = t % KTOT;
-    const float w = ((k < 256) ? Wa[n * 256 + k] : Wd[n * 256 + (k - 256)]) * scale[0];
+    if (t < CC) bias_sum[t] = ba[t] + bd[t];
+    if (t >= CC * 2 * CC) return;
+    const int n = t / (2 * CC), k = t % (2 * CC);
+    const float w = ((k < CC) ? Wa[n * CC + k] : Wd[n * CC + (k - CC)]) * scale[0];
     const __half hi = __float2half_rn(w);
     const int kc = k / KC16, e = k % KC16;
-    const int dst = kc * (C * KC16) + (n >> 3) * 512 + (n & 7) * 64 + (((e >> 3) ^ (n & 7)) << 3) + (e & 7);
+    const int dst = kc * (CC * KC16) + (n >> 3) * 512 + (n & 7) * 64 + (((e >> 3) ^ (n & 7)) << 3) + (e & 7);
     img_hi[dst] = hi;
     img_lo[dst] = __float2half_rn(w - __half2float(hi));
 }
@@ -420,15 +423,21 @@ constexpr int F16_STAGE_BYTES = 2 * (A_BYTES + B_BYTES);      // hi + lo of both
 constexpr int F16_NSTAGE = 2;
 constexpr int F16_SMEM = F16_NSTAGE * F16_STAGE_BYTES + ROWS * STAGE_LD * 4 + 1024 + 256;
 
+template <int CC>
 __global__ void __launch_bounds__(NTHREADS, 1) gse_embed_f16_kernel(const float* __restrict__ d_idx, const float* __restrict__ a_idx,
                                                                     long long n_pairs, const float* __restrict__ div_term,
                                                                     const __half* __restrict__ img_hi, const __half* __restrict__ img_lo,
                                                                     const float* __restrict__ bias_sum, const float* __restrict__ scale,
                                                                     float* __restrict__ E) {
     constexpr int NSTAGE = F16_NSTAGE;
+    constexpr int CP = CC / KC16;                         // chunks per part (angle, distance)
+    constexpr int NCH = 2 * CP;                           // K chunks per tile
+    constexpr int BB = CC * 128;                          // bytes of one B chunk (CC rows x 64 halves)
+    constexpr int STB = 2 * (A_BYTES + BB);               // stage: hi + lo of both operands
+    constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(CC >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    float* xstage = (float*)(smem + NSTAGE * F16_STAGE_BYTES);
+    float* xstage = (float*)(smem + NSTAGE * STB);
     uint64_t* bars = (uint64_t*)(xstage + ROWS * STAGE_LD);
     uint64_t* full = bars;
     uint64_t* empty = bars + NSTAGE;
@@ -444,7 +453,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gse_embed_f16_kernel(const float*
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == NGEN_WARPS + 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(2 * CC) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -456,7 +465,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gse_embed_f16_kernel(const float*
         {   // zero the two padding rows (126, 127) of every A buffer once
             for (int e = threadIdx.x; e < NSTAGE * 2 * 64; e += NGEN_WARPS * 32) {
                 const int sidx = e / 128, rem = e % 128, part = rem / 64, w = rem % 64;
-                float* base = (float*)(smem + sidx * F16_STAGE_BYTES + part * A_BYTES + 15 * 1024 + 6 * 128);
+                float* base = (float*)(smem + sidx * STB + part * A_BYTES + 15 * 1024 + 6 * 128);
                 base[w] = 0.f;
             }
             asm volatile("bar.sync 2, %0;" ::"n"(NGEN_WARPS * 32) : "memory");
@@ -465,11 +474,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gse_embed_f16_kernel(const float*
         uint32_t ph = 0;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const long long p0 = tile * PAIRS;
-            for (int kc = 0; kc < NCHUNK16; ++kc) {
+            for (int kc = 0; kc < NCH; ++kc) {
                 mbar_wait(&empty[s], ph ^ 1u);
-                unsigned char* st = smem + s * F16_STAGE_BYTES;
-                const int f0 = (kc & 3) * 32;               // 32 frequencies (64 halves) per chunk
-                const bool angle = kc < 4;
+                unsigned char* st = smem + s * STB;
+                const int f0 = (kc % CP) * 32;               // 32 frequencies (64 halves) per chunk
+                const bool angle = kc < CP;
                 const int n_items = (angle ? 3 * PAIRS : PAIRS) * 8;
                 for (int it = threadIdx.x; it < n_items; it += NGEN_WARPS * 32) {
                     const int c = it & 7, rr = it >> 3;     // 16-byte chunk c = frequencies f0+4c .. f0+4c+3
@@ -510,12 +519,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gse_embed_f16_kernel(const float*
             int s = 0;
             uint32_t ph = 0;
             for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                for (int kc = 0; kc < NCHUNK16; ++kc) {
+                for (int kc = 0; kc < NCH; ++kc) {
                     mbar_wait(&empty[s], ph ^ 1u);
-                    unsigned char* st = smem + s * F16_STAGE_BYTES;
-                    mbar_arrive_expect_tx(&full[s], 2 * B_BYTES);
-                    bulk_g2s(st + 2 * A_BYTES, img_hi + (size_t)kc * (C * KC16), B_BYTES, &full[s]);
-                    bulk_g2s(st + 2 * A_BYTES + B_BYTES, img_lo + (size_t)kc * (C * KC16), B_BYTES, &full[s]);
+                    unsigned char* st = smem + s * STB;
+                    mbar_arrive_expect_tx(&full[s], 2 * BB);
+                    bulk_g2s(st + 2 * A_BYTES, img_hi + (size_t)kc * (CC * KC16), BB, &full[s]);
+                    bulk_g2s(st + 2 * A_BYTES + BB, img_lo + (size_t)kc * (CC * KC16), BB, &full[s]);
                     if (++s == NSTAGE) { s = 0; ph ^= 1u; }
                 }
             }
@@ -529,19 +538,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) gse_embed_f16_kernel(const float*
             for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 mbar_wait(&tempty[acc], acc_ph[acc] ^ 1u);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * C);
-                for (int kc = 0; kc < NCHUNK16; ++kc) {
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * CC);
+                for (int kc = 0; kc < NCH; ++kc) {
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
-                    const uint32_t st = smem_u32(smem + s * F16_STAGE_BYTES);
+                    const uint32_t st = smem_u32(smem + s * STB);
                     const uint64_t da_hi = make_desc(st), da_lo = make_desc(st + A_BYTES);
-                    const uint64_t db_hi = make_desc(st + 2 * A_BYTES), db_lo = make_desc(st + 2 * A_BYTES + B_BYTES);
+                    const uint64_t db_hi = make_desc(st + 2 * A_BYTES), db_lo = make_desc(st + 2 * A_BYTES + BB);
 #pragma unroll
                     for (int kk = 0; kk < KC16 / 16; ++kk) {        // 4 MMAs of K = 16 (32 bytes) per operand pair
                         const uint64_t adv = (uint64_t)(kk * 2);
-                        umma_f16(d_tmem, da_hi + adv, db_hi + adv, (kc == 0 && kk == 0) ? 0u : 1u);
-                        umma_f16(d_tmem, da_hi + adv, db_lo + adv, 1u);
-                        umma_f16(d_tmem, da_lo + adv, db_hi + adv, 1u);
+                        umma_f16(d_tmem, da_hi + adv, db_hi + adv, (kc == 0 && kk == 0) ? 0u : 1u, IDESC);
+                        umma_f16(d_tmem, da_hi + adv, db_lo + adv, 1u, IDESC);
+                        umma_f16(d_tmem, da_lo + adv, db_hi + adv, 1u, IDESC);
                     }
                     umma_commit(&empty[s]);
                     if (++s == NSTAGE) { s = 0; ph ^= 1u; }
@@ -561,9 +570,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gse_embed_f16_kernel(const float*
             mbar_wait(&tfull[acc], acc_ph[acc]);
             tc_fence_after();
             const long long p0 = tile * PAIRS;
-            for (int cc = 0; cc < C / 32; ++cc) {
+            for (int cc = 0; cc < CC / 32; ++cc) {
                 uint32_t v[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C + cc * 32);
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * CC + cc * 32);
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -584,7 +593,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gse_embed_f16_kernel(const float*
                     if (p < n_pairs) {
                         const float m = fmaxf(fmaxf(xstage[jj * STAGE_LD + c], xstage[(PAIRS + jj) * STAGE_LD + c]),
                                               xstage[(2 * PAIRS + jj) * STAGE_LD + c]);
-                        E[p * C + cc * 32 + c] = fmaf(m, inv_scale, __ldg(bias_sum + cc * 32 + c));
+                        E[p * CC + cc * 32 + c] = fmaf(m, inv_scale, __ldg(bias_sum + cc * 32 + c));
                     }
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -600,7 +609,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gse_embed_f16_kernel(const float*
     __syncthreads();
     if (warp == NGEN_WARPS + 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * CC) : "memory");
     }
 }
 
@@ -820,8 +829,28 @@ using namespace geob200;
 int geob200_gse_embed_tc(const float* d_idx, const float* a_idx, long long n_pairs, int C, const float* div_term,
                          const float* Wd, const float* Wa, const float* bd, const float* ba, float* E, int mode,
                          void* workspace, size_t workspace_bytes, cudaStream_t st) {
-    if (C != tc::C) return 1;
     if (mode != 1 && mode != 2 && mode != 3 && mode != 4) return 1;
+    if (C == 128 && mode == 3) {
+        // hidden 128 (KITTI): the 3xFP16 kernel instantiated for N = 128, K = 2 x 128 (two angle + two distance chunks per tile)
+        constexpr int CC = 128;
+        const size_t img_halves = (size_t)CC * 2 * CC;
+        const size_t need = 2 * img_halves * sizeof(__half) + (CC + 2) * sizeof(float) + 1024;
+        GEOB_REQUIRE(workspace_bytes >= need, "gse_embed_tc: workspace too small (%zu < %zu)", workspace_bytes, need);
+        __half* h_hi = (__half*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+        __half* h_lo = h_hi + img_halves;
+        float* bsum = (float*)(h_lo + img_halves);
+        float* scale = bsum + CC;
+        const long long n_tiles = (n_pairs + tc::PAIRS - 1) / tc::PAIRS;
+        const int grid = (int)(n_tiles < (long long)num_sms() ? n_tiles : (long long)num_sms());
+        tc::gse_absmax_kernel<CC><<<1, 1024, 0, st>>>(Wd, Wa, scale);
+        tc::gse_pack_b_f16_kernel<CC><<<(unsigned)((img_halves + 255) / 256), 256, 0, st>>>(Wd, Wa, bd, ba, scale, h_hi, h_lo, bsum);
+        if (ensure_max_smem((const void*)tc::gse_embed_f16_kernel<CC>)) return -1;
+        tc::gse_embed_f16_kernel<CC><<<grid, tc::NTHREADS, tc::F16_SMEM, st>>>(d_idx, a_idx, n_pairs, div_term, h_hi, h_lo, bsum, scale, E);
+        GEOB_CHECK_LAUNCH();
+        count_launches(3);
+        return 0;
+    }
+    if (C != tc::C) return 1;
     const size_t img_floats = (size_t)tc::C * tc::KTOT;
     const size_t need = sizeof(float) * (2 * img_floats + tc::C) + 1024;
     GEOB_REQUIRE(workspace_bytes >= need, "gse_embed_tc: workspace too small (%zu < %zu)", workspace_bytes, need);
@@ -835,15 +864,15 @@ int geob200_gse_embed_tc(const float* d_idx, const float* a_idx, long long n_pai
         __half* h_lo = h_hi + img_floats;
         float* bsum = (float*)(h_lo + img_floats);
         float* scale = bsum + tc::C;
-        tc::gse_absmax_kernel<<<1, 1024, 0, st>>>(Wd, Wa, scale);
-        tc::gse_pack_b_f16_kernel<<<(unsigned)((img_floats + 255) / 256), 256, 0, st>>>(Wd, Wa, bd, ba, scale, h_hi, h_lo, bsum);
-        if (ensure_max_smem((const void*)tc::gse_embed_f16_kernel) || ensure_max_smem((const void*)tc::gse_embed_f16_cluster_kernel)) return -1;
+        tc::gse_absmax_kernel<tc::C><<<1, 1024, 0, st>>>(Wd, Wa, scale);
+        tc::gse_pack_b_f16_kernel<tc::C><<<(unsigned)((img_floats + 255) / 256), 256, 0, st>>>(Wd, Wa, bd, ba, scale, h_hi, h_lo, bsum);
+        if (ensure_max_smem((const void*)tc::gse_embed_f16_kernel<tc::C>) || ensure_max_smem((const void*)tc::gse_embed_f16_cluster_kernel)) return -1;
         if (mode == 4) {
             // CTA pairs (cluster of 2) share every B chunk through TMA multicast; grid = even number of CTAs, one per SM
             int g2 = (int)((n_tiles + 1) / 2 < (long long)(num_sms() / 2) ? (n_tiles + 1) / 2 : (long long)(num_sms() / 2)) * 2;
             tc::gse_embed_f16_cluster_kernel<<<g2, tc::NTHREADS, tc::F16_SMEM, st>>>(d_idx, a_idx, n_pairs, div_term, h_hi, h_lo, bsum, scale, E);
         } else
-            tc::gse_embed_f16_kernel<<<grid, tc::NTHREADS, tc::F16_SMEM, st>>>(d_idx, a_idx, n_pairs, div_term, h_hi, h_lo, bsum, scale, E);
+            tc::gse_embed_f16_kernel<tc::C><<<grid, tc::NTHREADS, tc::F16_SMEM, st>>>(d_idx, a_idx, n_pairs, div_term, h_hi, h_lo, bsum, scale, E);
         GEOB_CHECK_LAUNCH();
         count_launches(3);
         return 0;

@@ -373,8 +373,10 @@ def gse_embed_flat(d_indices, a_indices, n_rows, div_term, wd, wa, bd, ba, wd_t,
     concatenated (d (n_rows,), a (n_rows, k)) -> out (n_rows, C): one launch for a whole batch of clouds."""
     c = wd.shape[0]
     mode = GSE_MODE if mode is None else mode
-    if c != 256:
-        mode = 0                     # the tcgen05 contraction is specialised for hidden_dim 256 (3DMatch / ModelNet)
+    if c == 128 and mode != 0:
+        mode = 3                     # hidden_dim 128 (KITTI): the 3xFP16 tcgen05 kernel has an N = 128 instantiation
+    elif c != 256:
+        mode = 0                     # other widths: fp32 CUDA-core kernel
     lib = L.lib()
     ws = L.workspace(lib.geob200_gse_embed_workspace_bytes(1, c), d_indices.device, 'gse')
     with _timed('gse_embed'):
@@ -389,8 +391,10 @@ def gse_embed(d_indices, a_indices, div_term, wd, wa, bd, ba, wd_t, wa_t, mode=N
     n = d_indices.shape[0]
     c = wd.shape[0]
     mode = GSE_MODE if mode is None else mode
-    if c != 256:
-        mode = 0                     # the tcgen05 contraction is specialised for hidden_dim 256 (3DMatch / ModelNet)
+    if c == 128 and mode != 0:
+        mode = 3                     # hidden_dim 128 (KITTI): the 3xFP16 tcgen05 kernel has an N = 128 instantiation
+    elif c != 256:
+        mode = 0                     # other widths: fp32 CUDA-core kernel
     lib = L.lib()
     ws = L.workspace(lib.geob200_gse_embed_workspace_bytes(n, c), d_indices.device, 'gse')
     emb = torch.empty((n, n, c), dtype=_f32, device=d_indices.device) if out is None else out

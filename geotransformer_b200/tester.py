@@ -26,9 +26,11 @@ def _np(x):
 
 
 class RegistrationTester:
-    def __init__(self, cfg, model, neighbor_limits, output_dir=None, num_streams=4, chunk=16, device=None):
-        self.cfg, self.output_dir, self.chunk = cfg, output_dir, max(1, int(chunk))
-        self.engine = RegistrationEngine(model, cfg, neighbor_limits, num_streams=num_streams, device=device, evaluator=Evaluator(cfg))
+    def __init__(self, cfg, model, neighbor_limits, output_dir=None, num_streams=4, chunk=16, device=None, batch_size=1):
+        """batch_size > 1: that many pairs per forward (GeoTransformer.forward_batch) on each of the num_streams lanes"""
+        self.cfg, self.output_dir, self.chunk = cfg, output_dir, max(1, int(chunk), int(batch_size) * int(num_streams))
+        self.engine = RegistrationEngine(model, cfg, neighbor_limits, num_streams=num_streams, device=device, evaluator=Evaluator(cfg),
+                                         batch_size=batch_size)
 
     def after_test_step(self, data_dict, output_dict):
         """experiments/*/test.py:65-92"""

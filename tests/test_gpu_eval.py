@@ -173,8 +173,10 @@ def test_engine_streams_and_metrics(models):
     assert len({tuple(x['estimated_transform'].flatten().tolist()) for x in a}) == 5        # five different pairs
 
 
-def test_tester_loop_writes_reference_npz(models, tmp_path):
-    """SingleTester-style loop: one <scene>/<ref>_<src>.npz per pair with the arrays test.py:73-92 writes, metrics summary"""
+@pytest.mark.parametrize('batch_size', [1, 2])
+def test_tester_loop_writes_reference_npz(models, tmp_path, batch_size):
+    """SingleTester-style loop: one <scene>/<ref>_<src>.npz per pair with the arrays test.py:73-92 writes, metrics summary;
+    batch_size 2 = two pairs per forward (3 pairs: one full batch + a trailing single pair)"""
     from geotransformer_b200.tester import RegistrationTester, NPZ_OUTPUT_KEYS
     cfg, sd, model = models('3dmatch')
     model = model.cuda().eval()
@@ -185,7 +187,8 @@ def test_tester_loop_writes_reference_npz(models, tmp_path):
         d.update(scene_name='synthetic_scene', ref_frame=2 * i, src_frame=2 * i + 1, overlap=0.5)
         dataset.append(d)
     lines = []
-    tester = RegistrationTester(cfg, model, [38, 36, 36, 38], output_dir=str(tmp_path), num_streams=2, chunk=2)
+    tester = RegistrationTester(cfg, model, [38, 36, 36, 38], output_dir=str(tmp_path), num_streams=2 if batch_size == 1 else 1, chunk=2,
+                                batch_size=batch_size)
     summary, per_pair = tester.run(dataset, log=lines.append)
     tester.close()
     assert len(per_pair) == 3 and len(lines) == 3 and set(summary) == {'PIR', 'IR', 'RRE', 'RTE', 'RMSE', 'RR'}
