@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256) row_positive_kernel(const float* __restri
 // CPL = channels per lane: 2 when Cin is a multiple of 64 (every broadcast read of an influence row then feeds 30 FMAs instead
 // of 15; with 15 the kernel is bound by the shared-memory pipe, 4 LDS.128 per 15 FMAs)
 template <int CPL>
-__global__ void __launch_bounds__(256) kpconv_gather_kernel(const float* __restrict__ feats, const unsigned char* __restrict__ pos,
+__global__ void __launch_bounds__(256, 4) kpconv_gather_kernel(const float* __restrict__ feats, const unsigned char* __restrict__ pos,
                                                             const float* __restrict__ q_pts, const float* __restrict__ s_pts,
                                                             const long long* __restrict__ nbr, int H, const float* __restrict__ kp,
                                                             float sigma, int Ns, int M, int Cin, float* __restrict__ wf,
