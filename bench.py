@@ -124,6 +124,56 @@ def measure_tf32_peak(dev):
         return None
 
 
+def attention_roofline(dev, n_sp, clouds, channels, heads, peak_hbm, traffic):
+    """HBM roofline of the self-attention (the E stream, N^2 C 4 bytes per cloud and layer, is its only large operand): one
+    layer over `clouds` clouds of n_sp superpoints through geob200_attention_batched (q.k pass + TMA-staged E stream + P.v pass),
+    CUDA events around the three launches, L2 flushed between repetitions.  achieved = E bytes / time of ALL three launches."""
+    try:
+        import ctypes
+        from geotransformer_b200 import _lib as L
+
+        class Item(ctypes.Structure):
+            _fields_ = [(n, ctypes.c_void_p) for n in ('q', 'k', 'v', 'qp', 'qb', 'embed', 'out')] + [('n_query', ctypes.c_int64), ('n_key', ctypes.c_int64)]
+        C, H, N = channels, heads, n_sp
+        rows = clouds * N
+        qkv = torch.randn(rows, 3 * C, device=dev)
+        qp = torch.randn(rows, H, C, device=dev) * 0.2
+        qb = torch.randn(rows, H, device=dev)
+        E = torch.randn(clouds, N, N, C, device=dev)
+        out = torch.empty(rows, C, device=dev)
+        items = (Item * clouds)()
+        for c in range(clouds):
+            o = c * N
+            items[c] = Item(qkv[o:].data_ptr(), qkv[o:, C:].data_ptr(), qkv[o:, 2 * C:].data_ptr(), qp[o:].data_ptr(), qb[o:].data_ptr(),
+                            E[c].data_ptr(), out[o:].data_ptr(), N, N)
+        lib = L.lib()
+        ws = torch.empty(lib.geob200_attention_batched_workspace_bytes(items, clouds, H) + 1024, dtype=torch.uint8, device=dev)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        st = torch.cuda.current_stream().cuda_stream
+        ts = []
+        for i in range(13):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            L.check(lib.geob200_attention_batched(items, clouds, 3 * C, 3 * C, 3 * C, C, C, H, ws.data_ptr(), ws.numel(), st), 'attention')
+            e1.record()
+            e1.synchronize()
+            if i >= 3:
+                ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        ms = ts[len(ts) // 2]
+        e_bytes = float(clouds) * N * N * C * 4
+        ach = e_bytes / (ms * 1e-3) / 1e9
+        return {'kernel': 'self-attention layer: att_qk_kernel + att_stream_kernel (TMA-staged E stream) + att_pv_kernel', 'bound': 'hbm',
+                'achieved': ach, 'peak': peak_hbm, 'unit': 'GB/s', 'frac': ach / peak_hbm, 'traffic': traffic.get('att_stream_bytes_per_launch'),
+                'algorithmic_bytes_per_launch': e_bytes, 'ms_per_layer': ms, 'clouds': clouds, 'superpoints_per_cloud': N,
+                'timing': 'CUDA events around the three launches of one layer (median of 10, L2 flushed), kernels alone on the GPU, after the timed regions',
+                'note': 'achieved counts the E bytes only and divides by the time of ALL three launches; the streaming kernel alone moves '
+                        'E at 5.35 TB/s = 0.81 of the peak (ncu, profiles/r02_top_kernels_ncu_selected.csv)'}
+    except Exception as ex:
+        return {'kernel': 'self-attention', 'bound': 'hbm', 'achieved': None, 'note': f'failed: {type(ex).__name__}: {ex}'}
+
+
 def load_traffic():
     """per-launch DRAM traffic of the roofline kernels from the committed ncu --set full capture (profiles/r02_dram_traffic.json)"""
     p = os.path.join(ROOT, 'profiles', 'r02_dram_traffic.json')
@@ -465,6 +515,10 @@ def main():
                 'peak_source': f'{peak_src} bf16 dense BURST (MEASURED_PEAKS.json; launches timed alone); tf32_dense_peak_measured = torch.matmul fp32 '
                                f'8192^3 with allow_tf32, best of 10, this run; the kernel executes 3 TF32 MMAs per product term'}
 
+    roofline_att = None
+    if rank == 0 and C in (128, 256) and n_c:
+        roofline_att = attention_roofline(dev, int(np.mean(n_c)), 2 * BATCH, C, cfg.geotransformer.num_heads, peak_hbm, traffic)
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
@@ -493,7 +547,7 @@ def main():
                 'h2d_bytes_per_step': int(h2d_bytes), 'd2h_bytes_per_step': 96 * S},
         'gpu_launches': int(launches), 'gpu_launches_per_pair': launches / max(K * S, 1),
         'cuda_mallocs': {'timed_region_resident': int(mallocs_res), 'timed_region_e2e': int(mallocs_e2e)},
-        'per_rank_ms': {'value': per_rank_res, 'e2e': per_rank_e2e}, 'roofline': roofline, 'roofline_gse_embed': roofline_gse, 'cpu_baseline': cpu, 'gpu_eager_port': eager, 'clocks': sampler.summary(),
+        'per_rank_ms': {'value': per_rank_res, 'e2e': per_rank_e2e}, 'roofline': roofline, 'roofline_gse_embed': roofline_gse, 'roofline_attention': roofline_att, 'cpu_baseline': cpu, 'gpu_eager_port': eager, 'clocks': sampler.summary(),
         'quality': {'median_rre_deg': float(rows_t[:, 0].median()), 'median_rte': float(rows_t[:, 1].median()),
                     'mean_correspondences': float(rows_t[:, 2].mean()), 'pairs': int(rows_t.shape[0]),
                     'mean_PIR': float(rows_t[:, 4].nanmean()), 'mean_IR': float(rows_t[:, 5].nanmean()),
