@@ -33,50 +33,61 @@ __device__ __forceinline__ void influence15(const float* __restrict__ kp_s, floa
 
 // First layer of every backbone: Cin == 1 (features are all-ones columns, model input_dim = 1).
 // out[m][c'] = (sum_k (sum_h w[h][k] f[h]) W[k][0][c']) / max(#{h: f[h] > 0}, 1) + bias
+// Half a warp per query point (16 queries per CTA): with H = 27..38 neighbours a full warp spends its second pass over the
+// neighbour list almost idle; 16 lanes take 2-3 passes at 80-100 % occupancy and the 15 reductions need 4 shuffle steps.
 __global__ void __launch_bounds__(256) kpconv_c1_kernel(const float* __restrict__ feats, const float* __restrict__ q_pts,
                                                         const float* __restrict__ s_pts, const long long* __restrict__ nbr,
                                                         int H, const float* __restrict__ kp, const float* __restrict__ W,
                                                         const float* __restrict__ bias, float sigma, int Ns, int M, int Cout,
                                                         float* __restrict__ out) {
     __shared__ float kp_s[KP * 3];
-    __shared__ float wk_s[8][KP_PAD];
-    __shared__ float np_s[8];
+    __shared__ float wk_s[16][KP_PAD];
+    __shared__ float np_s[16];
     if (threadIdx.x < KP * 3) kp_s[threadIdx.x] = kp[threadIdx.x];
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int m = blockIdx.x * 8 + warp;
-    if (m >= M) return;
-    const float qx = q_pts[3ll * m], qy = q_pts[3ll * m + 1], qz = q_pts[3ll * m + 2];
+    const int sub = lane >> 4, sl = lane & 15;
+    const int slot = warp * 2 + sub;
+    const int m = blockIdx.x * 16 + slot;
+    const bool live = m < M;
     float acc[KP];
 #pragma unroll
     for (int k = 0; k < KP; ++k) acc[k] = 0.f;
     int npos = 0;
-    for (int h = lane; h < H; h += 32) {
-        const long long idx = nbr[(long long)m * H + h];
-        if (idx < Ns) {
-            float w[KP];
-            influence15(kp_s, s_pts[3 * idx] - qx, s_pts[3 * idx + 1] - qy, s_pts[3 * idx + 2] - qz, 0.f, sigma, w);
-            const float f = feats[idx];
-            npos += (f > 0.f);
+    if (live) {
+        const float qx = q_pts[3ll * m], qy = q_pts[3ll * m + 1], qz = q_pts[3ll * m + 2];
+        for (int h = sl; h < H; h += 16) {
+            const long long idx = nbr[(long long)m * H + h];
+            if (idx < Ns) {
+                float w[KP];
+                influence15(kp_s, s_pts[3 * idx] - qx, s_pts[3 * idx + 1] - qy, s_pts[3 * idx + 2] - qz, 0.f, sigma, w);
+                const float f = feats[idx];
+                npos += (f > 0.f);
 #pragma unroll
-            for (int k = 0; k < KP; ++k) acc[k] = fmaf(w[k], f, acc[k]);
+                for (int k = 0; k < KP; ++k) acc[k] = fmaf(w[k], f, acc[k]);
+            }
         }
     }
+    // reductions over the 16 lanes of the half warp (xor offsets < 16 stay inside it); every lane of the warp takes part
 #pragma unroll
-    for (int k = 0; k < KP; ++k) acc[k] = warp_sum(acc[k]);
+    for (int k = 0; k < KP; ++k) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) npos += __shfl_xor_sync(0xffffffffu, npos, o);
-    if (lane == 0) {
+        for (int o = 8; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+    }
 #pragma unroll
-        for (int k = 0; k < KP; ++k) wk_s[warp][k] = acc[k];
-        np_s[warp] = (float)max(npos, 1);
+    for (int o = 8; o > 0; o >>= 1) npos += __shfl_xor_sync(0xffffffffu, npos, o);
+    if (sl == 0) {
+#pragma unroll
+        for (int k = 0; k < KP; ++k) wk_s[slot][k] = acc[k];
+        np_s[slot] = (float)max(npos, 1);
     }
     __syncwarp();
-    for (int c = lane; c < Cout; c += 32) {
+    if (!live) return;
+    for (int c = sl; c < Cout; c += 16) {
         float o = 0.f;
 #pragma unroll
-        for (int k = 0; k < KP; ++k) o = fmaf(wk_s[warp][k], W[k * Cout + c], o);
-        o = o / np_s[warp];
+        for (int k = 0; k < KP; ++k) o = fmaf(wk_s[slot][k], W[k * Cout + c], o);
+        o = o / np_s[slot];
         if (bias != nullptr) o += bias[c];
         out[(long long)m * Cout + c] = o;
     }
@@ -648,37 +659,71 @@ __global__ void __launch_bounds__(128) gn_seg_finalize_kernel(const double* __re
     }
 }
 
+// y = leaky((x - mean) * rstd * gamma + beta + residual) with the statistics of the row's pair.  One CTA normalises GN_RPB
+// consecutive rows: they lie in at most two clouds unless a cloud is shorter than GN_RPB rows, so the per-channel scale / shift
+// of the first two clouds of the block are tabulated once in shared memory (mean and rstd expanded per channel: no group
+// arithmetic and no statistics loads per element, same expression as gn_apply_kernel); rows of a third cloud (tiny clouds
+// only) take the per-element path.
+constexpr int GN_RPB = 32;
 __global__ void __launch_bounds__(256) gn_seg_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean_rstd,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                           const float* __restrict__ residual, float* __restrict__ y, long long total4,
+                                                           const float* __restrict__ residual, float* __restrict__ y, int n_rows,
                                                            int C, int cpg, int G, int leaky, float slope, GnSeg seg) {
+    extern __shared__ float gn_tab[];             // [2 clouds][mean | rstd][C]
     __shared__ int starts[GEOB_MAX_CLOUDS + 1];
     for (int i = threadIdx.x; i <= seg.n_clouds; i += blockDim.x) starts[i] = seg.start[i];
     __syncthreads();
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total4) return;
-    const int row = (int)((i * 4) / C);
-    int lo = 0, hi = seg.n_clouds;                             // cloud with starts[lo] <= row < starts[lo + 1]
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (starts[mid] <= row) lo = mid; else hi = mid;
+    const int r0 = blockIdx.x * GN_RPB, r1 = min(n_rows, r0 + GN_RPB);
+    int c0 = 0, hi = seg.n_clouds;                // cloud of the block's first row
+    while (hi - c0 > 1) {
+        const int mid = (c0 + hi) >> 1;
+        if (starts[mid] <= r0) c0 = mid; else hi = mid;
     }
-    const float* mr = mean_rstd + (long long)(lo % seg.n_pairs) * 2 * G;
-    const float4 v = reinterpret_cast<const float4*>(x)[i];
-    const int c = (int)((i * 4) % C);
-    float in[4] = {v.x, v.y, v.z, v.w}, o[4];
-    float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (residual != nullptr) rv = reinterpret_cast<const float4*>(residual)[i];
-    const float rs[4] = {rv.x, rv.y, rv.z, rv.w};
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+        const int t = i / C, c = i % C;
+        const int cl = min(c0 + t, seg.n_clouds - 1);
+        const float* mr = mean_rstd + (long long)(cl % seg.n_pairs) * 2 * G + 2 * (c / cpg);
+        gn_tab[(2 * t) * C + c] = mr[0];
+        gn_tab[(2 * t + 1) * C + c] = mr[1];
+    }
+    __syncthreads();
+    const int b0 = starts[c0 + 1];                                        // rows < b0 use table 0
+    const int b1 = (c0 + 2 <= seg.n_clouds) ? starts[c0 + 2] : n_rows;    // rows in [b0, b1) use table 1
+    const int C4 = C >> 2;
+    const long long base4 = (long long)r0 * C4;
+    const int total4 = (r1 - r0) * C4;
+    for (int i = threadIdx.x; i < total4; i += blockDim.x) {
+        const int row = r0 + i / C4, c = (i % C4) * 4;
+        const float4 v = reinterpret_cast<const float4*>(x)[base4 + i];
+        float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (residual != nullptr) rv = reinterpret_cast<const float4*>(residual)[base4 + i];
+        float in[4] = {v.x, v.y, v.z, v.w}, o[4];
+        const float rs[4] = {rv.x, rv.y, rv.z, rv.w};
+        if (row < b1) {
+            const float* ta = gn_tab + (row < b0 ? 0 : 2 * C) + c;
+            const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + c)), bt = __ldg(reinterpret_cast<const float4*>(beta + c));
+            const float ga[4] = {gm.x, gm.y, gm.z, gm.w}, ba[4] = {bt.x, bt.y, bt.z, bt.w};
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        const int g = (c + u) / cpg;
-        float t = (in[u] - mr[2 * g]) * mr[2 * g + 1] * gamma[c + u] + beta[c + u];
-        t += rs[u];
-        if (leaky) t = t > 0.f ? t : t * slope;
-        o[u] = t;
+            for (int u = 0; u < 4; ++u) o[u] = (in[u] - ta[u]) * ta[C + u] * ga[u] + ba[u] + rs[u];
+        } else {                                   // third cloud inside one block: clouds shorter than GN_RPB rows
+            int lo = c0, hh = seg.n_clouds;
+            while (hh - lo > 1) {
+                const int mid = (lo + hh) >> 1;
+                if (starts[mid] <= row) lo = mid; else hh = mid;
+            }
+            const float* mr = mean_rstd + (long long)(lo % seg.n_pairs) * 2 * G;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int g = (c + u) / cpg;
+                o[u] = (in[u] - mr[2 * g]) * mr[2 * g + 1] * gamma[c + u] + beta[c + u] + rs[u];
+            }
+        }
+        if (leaky) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) o[u] = o[u] > 0.f ? o[u] : o[u] * slope;
+        }
+        reinterpret_cast<float4*>(y)[base4 + i] = make_float4(o[0], o[1], o[2], o[3]);
     }
-    reinterpret_cast<float4*>(y)[i] = make_float4(o[0], o[1], o[2], o[3]);
 }
 
 __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean_rstd,
@@ -898,7 +943,7 @@ int geob200_kpconv(const float* s_feats, const float* q_points, const float* s_p
     GEOB_REQUIRE(n_kernel == KP, "kpconv: kernel_size %lld unsupported (all shipped models use 15)", (long long)n_kernel);
     GEOB_REQUIRE(n_query > 0 && n_support > 0 && n_neighbors > 0, "kpconv: empty input");
     if (c_in == 1) {
-        kpconv_c1_kernel<<<(unsigned)((n_query + 7) / 8), 256, 0, st>>>(s_feats, q_points, s_points, (const long long*)neighbors,
+        kpconv_c1_kernel<<<(unsigned)((n_query + 15) / 16), 256, 0, st>>>(s_feats, q_points, s_points, (const long long*)neighbors,
                                                                        (int)n_neighbors, kernel_points, weights, bias, sigma,
                                                                        (int)n_support, (int)n_query, (int)c_out, out);
         GEOB_CHECK_LAUNCH();
@@ -1008,9 +1053,8 @@ static void launch_gn_seg_apply(const float* x, const GnWs& w, const float* gamm
     const int slot_width = cpg < 32 ? cpg : 32;
     gn_seg_finalize_kernel<<<dim3((unsigned)groups, (unsigned)seg.n_pairs), 128, 0, st>>>(
         w.partial, x, (int)channels, (int)(channels / slot_width), cpg / slot_width, (int)groups, (double)eps, seg, w.mean_rstd);
-    const long long total4 = n_rows * channels / 4;
-    gn_seg_apply_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(x, w.mean_rstd, gamma, beta, residual, y, total4, (int)channels,
-                                                                         cpg, (int)groups, leaky, slope, seg);
+    gn_seg_apply_kernel<<<(unsigned)((n_rows + GN_RPB - 1) / GN_RPB), 256, sizeof(float) * 4 * channels, st>>>(
+        x, w.mean_rstd, gamma, beta, residual, y, (int)n_rows, (int)channels, cpg, (int)groups, leaky, slope, seg);
     count_launches(2);
 }
 static void launch_gn_tile_stats(const float* x, const GnWs& w, int64_t n_rows, int64_t channels, int64_t groups, cudaStream_t st) {
