@@ -14,7 +14,7 @@ _f32, _i64, _u8, _i32 = torch.float32, torch.int64, torch.uint8, torch.int32
 
 # tensor-core mode of the structure-embedding contraction (see geob200_gse_embed): 0 fp32 CUDA cores, 1 3xTF32, 2 1xTF32,
 # 3 3xFP16 (fp32-accurate like 3xTF32 at half the tensor-pipe time; default)
-GSE_MODE = 3
+GSE_MODE = int(__import__('os').environ.get('GEOB200_GSE_MODE', '3'))
 
 # Optional per-op CUDA-event timing on the launching stream (bench.py sets EVENTS = {} to collect
 # {op name: [(start_event, end_event), ...]}; None = off, zero overhead).
