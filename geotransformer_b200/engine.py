@@ -59,6 +59,8 @@ class RegistrationEngine:
         self.pool = ThreadPoolExecutor(max_workers=num_streams)
         # per slot: [estimated_transform (16) | metrics (8)] on the device and pinned on the host
         self.batch_size = max(1, int(batch_size))
+        if self.batch_size > 32:
+            raise ValueError('RegistrationEngine: at most 32 pairs per forward (the kernels carry the 2 x batch cloud offsets by value)')
         bs = self.batch_size
         self.r_dev = [torch.zeros((24,) if bs == 1 else (bs, 24), dtype=torch.float32, device=self.device) for _ in range(num_streams)]
         self.r_host = [torch.zeros((24,) if bs == 1 else (bs, 24), dtype=torch.float32).pin_memory() for _ in range(num_streams)]
