@@ -59,6 +59,7 @@ _sig('geob200_pairwise_distance', c_int, P, I64, P, I64, I64, c_int, P, P)
 _sig('geob200_point_to_node_indices', c_int, P, I64, P, I64, P, P, P)
 _sig('geob200_apply_transform', c_int, P, I64, P, P, P)
 _sig('geob200_gse_indices', c_int, P, I64, F, F, I64, P, P, P)
+_sig('geob200_gse_indices_batched', c_int, P, I64, P, F, F, I64, P, P, P)
 _sig('geob200_gse_embed_workspace_bytes', SZ, I64, I64)
 _sig('geob200_gse_embed', c_int, P, P, I64, I64, P, P, P, P, P, P, P, P, c_int, P, SZ, P)
 _sig('geob200_gse_embed_pairs', c_int, P, P, I64, I64, P, P, P, P, P, P, P, P, c_int, P, SZ, P)

@@ -24,10 +24,25 @@ __device__ __forceinline__ float dist_mm(float ax, float ay, float az, float a2,
 
 // One warp per anchor point i: distances to every j, the (k+1) nearest (the first is dropped, geotransformer.py:42),
 // then the k triplet angles for every j.  d_idx (N,N), a_idx (N,N,KA).
+// Clouds of a batch (blockIdx.y = cloud): stacked points, d / a outputs concatenated cloud after cloud (cloud c at pair_start[c]).
+struct GseClouds {
+    int n_clouds;
+    int row_start[GEOB_MAX_CLOUDS + 1];
+    long long pair_start[GEOB_MAX_CLOUDS + 1];
+};
+
 template <int KA>
-__global__ void __launch_bounds__(256) gse_indices_kernel(const float* __restrict__ pts, int N, float sigma_d, float factor_a,
-                                                          float* __restrict__ d_idx, float* __restrict__ a_idx) {
+__global__ void __launch_bounds__(256) gse_indices_kernel(const float* __restrict__ pts_all, int N_single, float sigma_d, float factor_a,
+                                                          float* __restrict__ d_all, float* __restrict__ a_all,
+                                                          const __grid_constant__ GseClouds cl) {
     extern __shared__ float4 ps[];     // (x,y,z,|p|^2)
+    // single cloud (n_clouds == 0): the arguments describe it; batch: cloud blockIdx.y of the descriptor
+    const int cloud = blockIdx.y;
+    const int N = cl.n_clouds > 0 ? cl.row_start[cloud + 1] - cl.row_start[cloud] : N_single;
+    const float* __restrict__ pts = cl.n_clouds > 0 ? pts_all + 3ll * cl.row_start[cloud] : pts_all;
+    float* __restrict__ d_idx = cl.n_clouds > 0 ? d_all + cl.pair_start[cloud] : d_all;
+    float* __restrict__ a_idx = cl.n_clouds > 0 ? a_all + cl.pair_start[cloud] * KA : a_all;
+    if ((int)(blockIdx.x * (blockDim.x >> 5)) >= N) return;          // grid.x covers the largest cloud
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
         const float x = pts[3 * n], y = pts[3 * n + 1], z = pts[3 * n + 2];
         ps[n] = make_float4(x, y, z, sqnorm3g(x, y, z));
@@ -250,7 +265,33 @@ int geob200_gse_indices(const float* points, int64_t n, float sigma_d, float fac
     GEOB_REQUIRE(n * 16 <= 200 * 1024, "gse_indices: too many superpoints (%lld)", (long long)n);
     const size_t smem = sizeof(float4) * n;
     if (smem > 48 * 1024 && ensure_max_smem((const void*)gse_indices_kernel<3>)) return -1;
-    gse_indices_kernel<3><<<(unsigned)((n + 7) / 8), 256, smem, st>>>(points, (int)n, sigma_d, factor_a, d_indices, a_indices);
+    GseClouds none{};
+    gse_indices_kernel<3><<<(unsigned)((n + 7) / 8), 256, smem, st>>>(points, (int)n, sigma_d, factor_a, d_indices, a_indices, none);
+    GEOB_CHECK_LAUNCH();
+    count_launches(1);
+    return 0;
+}
+
+int geob200_gse_indices_batched(const float* points, int64_t n_clouds, const int64_t* cloud_rows_h, float sigma_d, float factor_a,
+                                int64_t angle_k, float* d_indices, float* a_indices, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    GEOB_REQUIRE(n_clouds >= 1 && n_clouds <= GEOB_MAX_CLOUDS, "gse_indices: 1..%d clouds per launch", GEOB_MAX_CLOUDS);
+    GEOB_REQUIRE(angle_k == 3, "gse_indices: angle_k=%lld unsupported (all shipped models use 3)", (long long)angle_k);
+    GseClouds cl{};
+    cl.n_clouds = (int)n_clouds;
+    int64_t max_n = 0;
+    for (int64_t c = 0; c < n_clouds; ++c) {
+        const int64_t n = cloud_rows_h[c];
+        GEOB_REQUIRE(n > 0, "gse_indices: empty cloud");
+        cl.row_start[c + 1] = cl.row_start[c] + (int)n;
+        cl.pair_start[c + 1] = cl.pair_start[c] + n * n;
+        max_n = n > max_n ? n : max_n;
+    }
+    GEOB_REQUIRE(max_n * 16 <= 200 * 1024, "gse_indices: too many superpoints (%lld)", (long long)max_n);
+    const size_t smem = sizeof(float4) * max_n;
+    if (smem > 48 * 1024 && ensure_max_smem((const void*)gse_indices_kernel<3>)) return -1;
+    const dim3 grid((unsigned)((max_n + 7) / 8), (unsigned)n_clouds);
+    gse_indices_kernel<3><<<grid, 256, smem, st>>>(points, 0, sigma_d, factor_a, d_indices, a_indices, cl);
     GEOB_CHECK_LAUNCH();
     count_launches(1);
     return 0;

@@ -338,6 +338,16 @@ def gse_indices(points, sigma_d, sigma_a, angle_k, out=None):
     return d, a
 
 
+def gse_indices_batched(points, cloud_rows, sigma_d, sigma_a, angle_k, d_out, a_out):
+    """get_embedding_indices of several stacked clouds in ONE launch; d_out (sum n^2,), a_out (sum n^2, angle_k) receive the
+    clouds' index arrays one after the other (the layout ``gse_embed_flat`` consumes)"""
+    _f(points, 'points')
+    factor_a = 180.0 / (sigma_a * math.pi)
+    L.check(L.lib().geob200_gse_indices_batched(points.data_ptr(), len(cloud_rows), _cloud_rows(cloud_rows), float(sigma_d), float(factor_a),
+                                                angle_k, d_out.data_ptr(), a_out.data_ptr(), L.stream_ptr()), 'gse_indices_batched')
+    return d_out, a_out
+
+
 def scratch(shape, device, tag):
     """View of a grow-only per-(device, stream, tag) float buffer: for big intermediates whose size changes from pair to
     pair (the N x N x C structure embedding), so that the caching allocator never has to cudaMalloc inside the timed loop.

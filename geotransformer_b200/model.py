@@ -140,9 +140,7 @@ class GeoTransformer(nn.Module):
         d_all = GF.scratch((eo[-1],), dev, 'gse_d_all')
         a_all = GF.scratch((eo[-1], emb_mod.angle_k), dev, 'gse_a_all')
         E_all = GF.scratch((eo[-1], C), dev, 'gse_E_all')
-        for c in range(2 * B):
-            GF.gse_indices(cloud(points_c, oc, c).contiguous(), emb_mod.sigma_d, emb_mod.sigma_a, emb_mod.angle_k,
-                           out=(d_all[eo[c]:eo[c + 1]], a_all[eo[c]:eo[c + 1]]))
+        GF.gse_indices_batched(points_c, rows_c, emb_mod.sigma_d, emb_mod.sigma_a, emb_mod.angle_k, d_all, a_all)
         wd_t = emb_mod._cache.get('wd_t', emb_mod.proj_d.weight, lambda w: w.t().contiguous())
         wa_t = emb_mod._cache.get('wa_t', emb_mod.proj_a.weight, lambda w: w.t().contiguous())
         GF.gse_embed_flat(d_all, a_all, eo[-1], emb_mod.embedding.div_term, emb_mod.proj_d.weight.detach(), emb_mod.proj_a.weight.detach(),

@@ -170,6 +170,11 @@ int geob200_gather_rows(const float* table, int64_t n_rows, int64_t channels, co
 int geob200_gse_indices(const float* points, int64_t n, float sigma_d, float factor_a, int64_t angle_k, float* d_indices,
                         float* a_indices, void* stream);
 
+/* The same for n_clouds stacked clouds in ONE launch (cloud_rows_h: host row counts): points (sum rows, 3); the outputs are
+ * concatenated cloud after cloud: d_indices (sum n_c^2), a_indices (sum n_c^2, 3) -- the layout geob200_gse_embed_pairs takes. */
+int geob200_gse_indices_batched(const float* points, int64_t n_clouds, const int64_t* cloud_rows_h, float sigma_d, float factor_a,
+                                int64_t angle_k, float* d_indices, float* a_indices, void* stream);
+
 /* GeometricStructureEmbedding.forward (geotransformer.py:57-72) given the indices: sinusoid -> proj_d / proj_a ->
  * max over k -> sum, fused.  wd/wa are the nn.Linear weights (out,in); wd_t/wa_t their transposes (in,out).
  * mode 0: fp32 CUDA cores; 1: tcgen05 3xTF32; 2: tcgen05 1xTF32; 3: tcgen05 3xFP16 split (fp32-accurate, fastest). */

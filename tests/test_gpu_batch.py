@@ -103,6 +103,22 @@ def test_batched_collate_equals_per_pair(workload, cfg_name, ids, models):
                     assert bool((got[:, w:] == n_s_total).all())
 
 
+def test_structure_embedding_indices_of_a_batch_in_one_launch():
+    """geob200_gse_indices_batched == the per-cloud launches, bit for bit, clouds of different sizes"""
+    from geotransformer_b200 import functional as GF
+    g = torch.Generator().manual_seed(4)
+    rows = (57, 130, 7, 321, 64, 200)
+    pts = torch.rand(sum(rows), 3, generator=g).cuda() * 3.0
+    tot = sum(r * r for r in rows)
+    d_all, a_all = torch.empty(tot, device='cuda'), torch.empty(tot, 3, device='cuda')
+    GF.gse_indices_batched(pts, rows, 0.2, 15, 3, d_all, a_all)
+    o, e = 0, 0
+    for r in rows:
+        d, a = GF.gse_indices(pts[o:o + r].contiguous(), 0.2, 15, 3)
+        assert torch.equal(d_all[e:e + r * r].view(r, r), d) and torch.equal(a_all[e:e + r * r].view(r, r, 3), a)
+        o, e = o + r, e + r * r
+
+
 @pytest.mark.parametrize('workload,cfg_name,ids', [('demo2k', '3dmatch', (0, 1, 2)), ('modelnet717', 'modelnet', (0, 1, 2, 3)),
                                                    ('kitti4k', 'kitti', (0, 1)), ('3dmatch20k', '3dmatch', (0, 1))])
 def test_forward_batch_equals_single_pair_forward(workload, cfg_name, ids, models):
