@@ -335,6 +335,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_kernel(const __grid_con
 // tile boundaries and there are TWO accumulator sets in TMEM (2 x (main 128 + corrections 128) = 512 columns): while the four
 // epilogue warps drain, normalise and store tile i, the producer / splitters / MMA issuer are already deep in the K loop of
 // tile i + 1, so the per-tile fixed cost (first TMA round trip, TMEM drain, stores) is hidden instead of paid per CTA.
+// 202.5 KB: 6 KB over the 196 KB carve-out the per-tile kernel stays under, i.e. this kernel runs in the 228 KB shared-memory
+// configuration.  Accepted: it is only chosen for GEMMs of more than one wave of tiles (>= 0.1 ms each in batch mode), where a
+// carve-out switch against a neighbouring kernel (~8 us, measured in round 1) is noise, and the GroupNorm / bias staging must
+// survive across the tile loop next to the three operand stages.
 constexpr int SMEM_PERSIST = SMEM + 4 * 128 * 8 + 512;      // + GroupNorm column sums [4][128] float2 + the bias row
 
 __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x,
