@@ -472,14 +472,32 @@ def main():
     avg_ms = float(np.mean(gse_solo_ms)) if gse_solo_ms else None
     achieved = flops / (avg_ms * 1e-3) / 1e12 if avg_ms else None
     avg_ms_concurrent = float(np.mean(gse_ms)) if gse_ms else None
-    mode_name = {0: 'fp32 CUDA cores', 1: 'tcgen05 3xTF32', 2: 'tcgen05 1xTF32', 3: 'tcgen05 3xFP16 (fp32-accurate split)', 4: 'tcgen05 3xFP16 split, CTA-pair TMA multicast of B'}[GF.GSE_MODE]
-    roofline_gse = {'kernel': 'gse_embed (structure-embedding contraction)', 'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf,
-                'unit': 'TFLOP/s', 'frac': (achieved / peak_tf) if achieved else None, 'traffic': traffic.get('gse_embed_bytes_per_launch'),
-                'avg_ms_per_launch': avg_ms, 'launches_timed': len(gse_solo_ms), 'flops_per_launch': flops, 'clouds_per_launch': clouds_per_launch,
-                'avg_ms_per_launch_with_other_streams_active': avg_ms_concurrent,
-                'timing': 'CUDA events around the launch, one pair in flight (kernel alone on the GPU), same workload, after the timed regions',
-                'share_of_gpu_time': (avg_ms / clouds_per_launch * 2.0) / (ms_res / (K * S)) if avg_ms else None, 'mode': mode_name,
-                'peak_source': f'{peak_src} bf16 dense BURST (MEASURED_PEAKS.json; the kernel is timed alone)'}
+    mode_name = {0: 'fp32 CUDA cores', 1: 'tcgen05 3xTF32', 2: 'tcgen05 1xTF32', 3: 'tcgen05 3xFP16 (fp32-accurate split)',
+                 4: 'tcgen05 3xFP16 split, CTA-pair TMA multicast of B',
+                 5: 'tabulated projections (4 lookups + 3 max + 1 add per row and channel; no contraction)'}[GF.GSE_MODE]
+    common = {'avg_ms_per_launch': avg_ms, 'launches_timed': len(gse_solo_ms), 'clouds_per_launch': clouds_per_launch,
+              'avg_ms_per_launch_with_other_streams_active': avg_ms_concurrent,
+              'timing': 'CUDA events around the launch, one pair in flight (kernel alone on the GPU), same workload, after the timed regions',
+              'share_of_gpu_time': (avg_ms / clouds_per_launch * 2.0) / (ms_res / (K * S)) if avg_ms else None, 'mode': mode_name}
+    if GF.GSE_MODE == 5:
+        # no contraction left: the kernel writes E once (rows x C fp32) and reads 16 B of indices per row from HBM; the node
+        # reads (4 lookups x 6 B per channel and row) are served by L2 (hot part of the table: ~15 MB)
+        rows = mean_n2 * clouds_per_launch
+        e_bytes = rows * (C * 4 + 16)
+        gbps = e_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms else None
+        roofline_gse = {'kernel': 'table_embed_kernel (structure embedding through tabulated projections, csrc/gse_table.cu)', 'bound': 'hbm',
+                        'achieved': gbps, 'peak': peak_hbm, 'unit': 'GB/s', 'frac': (gbps / peak_hbm) if gbps else None, 'traffic': None,
+                        'algorithmic_bytes_per_launch': e_bytes, 'l2_node_bytes_per_launch': rows * 4 * C * 6,
+                        'l2_node_read_GBps': (rows * 4 * C * 6 / (avg_ms * 1e-3) / 1e9) if avg_ms else None,
+                        'contraction_flops_replaced_per_launch': flops,
+                        'peak_source': f'{peak_src} HBM copy bandwidth (MEASURED_PEAKS.json)',
+                        'note': 'HBM roofline = the compulsory write of E; the kernel is bound by the L2 reads of the table nodes '
+                                '(6 x the E bytes), see l2_node_read_GBps', **common}
+    else:
+        roofline_gse = {'kernel': 'gse_embed (structure-embedding contraction)', 'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf,
+                        'unit': 'TFLOP/s', 'frac': (achieved / peak_tf) if achieved else None, 'traffic': traffic.get('gse_embed_bytes_per_launch'),
+                        'flops_per_launch': flops, 'peak_source': f'{peak_src} bf16 dense BURST (MEASURED_PEAKS.json; the kernel is timed alone)',
+                        **common}
 
     # dominant kernel by share of the step's GPU time: linear_tc_kernel (every nn.Linear and the KPConv contraction; ~80 launches
     # per pair, shapes M=40 000..320, K=32..3840, N=32..1024).  ALGORITHMIC flops = 2*M*N*K of the fp32 product the reference

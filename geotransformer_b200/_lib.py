@@ -61,6 +61,9 @@ _sig('geob200_apply_transform', c_int, P, I64, P, P, P)
 _sig('geob200_gse_indices', c_int, P, I64, F, F, I64, P, P, P)
 _sig('geob200_gse_indices_batched', c_int, P, I64, P, F, F, I64, P, P, P)
 _sig('geob200_gse_embed_workspace_bytes', SZ, I64, I64)
+_sig('geob200_gse_table_bytes', SZ, I64, I64, F, F)
+_sig('geob200_gse_table_build', c_int, P, P, P, P, P, I64, I64, F, F, P, SZ, P)
+_sig('geob200_gse_embed_table', c_int, P, P, I64, I64, P, SZ, I64, F, F, P, P, P, P, P, P, P)
 _sig('geob200_gse_embed', c_int, P, P, I64, I64, P, P, P, P, P, P, P, P, c_int, P, SZ, P)
 _sig('geob200_gse_embed_pairs', c_int, P, P, I64, I64, P, P, P, P, P, P, P, P, c_int, P, SZ, P)
 _sig('geob200_attention_workspace_bytes', SZ, I64, I64, I64)

@@ -12,9 +12,14 @@ from . import _lib as L
 
 _f32, _i64, _u8, _i32 = torch.float32, torch.int64, torch.uint8, torch.int32
 
-# tensor-core mode of the structure-embedding contraction (see geob200_gse_embed): 0 fp32 CUDA cores, 1 3xTF32, 2 1xTF32,
-# 3 3xFP16 (fp32-accurate like 3xTF32 at half the tensor-pipe time; default)
+# mode of the structure-embedding contraction (see geob200_gse_embed): 0 fp32 CUDA cores, 1 tcgen05 3xTF32, 2 1xTF32,
+# 3 3xFP16 (fp32-accurate like 3xTF32 at half the tensor-pipe time; default), 4 3xFP16 on CTA pairs,
+# 5 tabulated projections (geob200_gse_embed_table: no contraction at all; needs a ``table`` from ``gse_table``)
 GSE_MODE = int(__import__('os').environ.get('GEOB200_GSE_MODE', '3'))
+# tabulation grid of mode 5: step 1 / GSE_TABLE_INV_STEP index units (power of two), distance indices up to GSE_TABLE_D_MAX
+# (larger ones are evaluated directly inside the kernel: correct, slow)
+GSE_TABLE_INV_STEP = int(__import__('os').environ.get('GEOB200_GSE_TABLE_INV_STEP', '256'))
+GSE_TABLE_D_MAX = float(__import__('os').environ.get('GEOB200_GSE_TABLE_D_MAX', '96'))
 
 # Optional per-op CUDA-event timing on the launching stream (bench.py sets EVENTS = {} to collect
 # {op name: [(start_event, end_event), ...]}; None = off, zero overhead).
@@ -378,11 +383,55 @@ def scratch_arange(n, device, tag='arange'):
     return buf[:n]
 
 
-def gse_embed_flat(d_indices, a_indices, n_rows, div_term, wd, wa, bd, ba, wd_t, wa_t, out, mode=None):
+class GseTable:
+    """Tabulated proj_d(sinusoid(x)) / proj_a(sinusoid(x)) (``geob200_gse_table_build``): the device blob and the grid it was
+    built on."""
+    __slots__ = ('blob', 'channels', 'inv_step', 'd_max', 'a_max')
+
+    def __init__(self, blob, channels, inv_step, d_max, a_max):
+        self.blob, self.channels, self.inv_step, self.d_max, self.a_max = blob, channels, inv_step, d_max, a_max
+
+
+def gse_table(div_term, wd_t, wa_t, bd, ba, sigma_a, inv_step=None, d_max=None):
+    """Tabulate the two projections of GeometricStructureEmbedding for the given weights (wd_t / wa_t: transposed nn.Linear
+    weights (in, out)).  Angle indices lie in [0, 180 / sigma_a]; distance indices above ``d_max`` fall back to the direct
+    evaluation inside ``gse_embed*``.  Returns after the build has COMPLETED, so any stream may use the table."""
+    for t, name in ((div_term, 'div_term'), (wd_t, 'wd_t'), (wa_t, 'wa_t'), (bd, 'bd'), (ba, 'ba')):
+        L.require_cuda(t, name, _f32)
+    c = int(wd_t.shape[0])
+    inv_step = GSE_TABLE_INV_STEP if inv_step is None else int(inv_step)
+    d_max = GSE_TABLE_D_MAX if d_max is None else float(d_max)
+    a_max = 180.0 / float(sigma_a) + 0.25
+    lib = L.lib()
+    nbytes = lib.geob200_gse_table_bytes(c, inv_step, d_max, a_max)
+    if nbytes == 0:
+        raise RuntimeError(f'gse_table: bad grid (channels {c}, inv_step {inv_step}, d_max {d_max}, a_max {a_max})')
+    blob = torch.empty(nbytes, dtype=_u8, device=wd_t.device)
+    L.check(lib.geob200_gse_table_build(div_term.data_ptr(), wd_t.data_ptr(), wa_t.data_ptr(), bd.data_ptr(), ba.data_ptr(), c,
+                                        inv_step, d_max, a_max, blob.data_ptr(), nbytes, L.stream_ptr()), 'gse_table_build')
+    torch.cuda.current_stream(wd_t.device).synchronize()
+    return GseTable(blob, c, inv_step, d_max, a_max)
+
+
+def _gse_embed_table(d_indices, a_indices, n_rows, div_term, wd, wa, bd, ba, table, out):
+    c = wd.shape[0]
+    if table is None or table.channels != c:
+        raise RuntimeError('gse_embed mode 5 (tabulated projections) needs the GseTable of these weights (functional.gse_table)')
+    with _timed('gse_embed'):
+        L.check(L.lib().geob200_gse_embed_table(d_indices.data_ptr(), a_indices.data_ptr(), int(n_rows), c, table.blob.data_ptr(),
+                                                table.blob.numel(), table.inv_step, table.d_max, table.a_max, div_term.data_ptr(),
+                                                wd.data_ptr(), wa.data_ptr(), bd.data_ptr(), ba.data_ptr(), out.data_ptr(),
+                                                L.stream_ptr()), 'gse_embed_table')
+    return out
+
+
+def gse_embed_flat(d_indices, a_indices, n_rows, div_term, wd, wa, bd, ba, wd_t, wa_t, out, mode=None, table=None):
     """structure embedding of ``n_rows`` (anchor, point) pairs given as flat index arrays -- the (i, j) pairs of SEVERAL clouds
     concatenated (d (n_rows,), a (n_rows, k)) -> out (n_rows, C): one launch for a whole batch of clouds."""
     c = wd.shape[0]
     mode = GSE_MODE if mode is None else mode
+    if mode == 5 and c in (128, 256):
+        return _gse_embed_table(d_indices, a_indices, n_rows, div_term, wd, wa, bd, ba, table, out)
     if c == 128 and mode != 0:
         mode = 3                     # hidden_dim 128 (KITTI): the 3xFP16 tcgen05 kernel has an N = 128 instantiation
     elif c != 256:
@@ -397,17 +446,19 @@ def gse_embed_flat(d_indices, a_indices, n_rows, div_term, wd, wa, bd, ba, wd_t,
     return out
 
 
-def gse_embed(d_indices, a_indices, div_term, wd, wa, bd, ba, wd_t, wa_t, mode=None, out=None):
+def gse_embed(d_indices, a_indices, div_term, wd, wa, bd, ba, wd_t, wa_t, mode=None, out=None, table=None):
     n = d_indices.shape[0]
     c = wd.shape[0]
     mode = GSE_MODE if mode is None else mode
+    emb = torch.empty((n, n, c), dtype=_f32, device=d_indices.device) if out is None else out
+    if mode == 5 and c in (128, 256):
+        return _gse_embed_table(d_indices, a_indices, n * n, div_term, wd, wa, bd, ba, table, emb)
     if c == 128 and mode != 0:
         mode = 3                     # hidden_dim 128 (KITTI): the 3xFP16 tcgen05 kernel has an N = 128 instantiation
     elif c != 256:
         mode = 0                     # other widths: fp32 CUDA-core kernel
     lib = L.lib()
     ws = L.workspace(lib.geob200_gse_embed_workspace_bytes(n, c), d_indices.device, 'gse')
-    emb = torch.empty((n, n, c), dtype=_f32, device=d_indices.device) if out is None else out
     with _timed('gse_embed'):
         L.check(lib.geob200_gse_embed(d_indices.data_ptr(), a_indices.data_ptr(), n, c, div_term.data_ptr(),
                                       wd_t.data_ptr(), wa_t.data_ptr(), wd.data_ptr(), wa.data_ptr(), bd.data_ptr(),

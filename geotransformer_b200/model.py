@@ -144,7 +144,7 @@ class GeoTransformer(nn.Module):
         wd_t = emb_mod._cache.get('wd_t', emb_mod.proj_d.weight, lambda w: w.t().contiguous())
         wa_t = emb_mod._cache.get('wa_t', emb_mod.proj_a.weight, lambda w: w.t().contiguous())
         GF.gse_embed_flat(d_all, a_all, eo[-1], emb_mod.embedding.div_term, emb_mod.proj_d.weight.detach(), emb_mod.proj_a.weight.detach(),
-                          emb_mod.proj_d.bias.detach(), emb_mod.proj_a.bias.detach(), wd_t, wa_t, E_all)
+                          emb_mod.proj_d.bias.detach(), emb_mod.proj_a.bias.detach(), wd_t, wa_t, E_all, table=emb_mod.table())
         embs = [E_all[eo[c]:eo[c + 1]] for c in range(2 * B)]
         mark('structure_embedding')
         x = GF.linear(feats_c, tr.in_proj.weight, tr.in_proj.bias)

@@ -1,11 +1,16 @@
 """``geotransformer.modules.geotransformer`` on the B200 path: same class names, constructor/forward signatures and
 ``state_dict`` keys as the reference (``geotransformer/modules/geotransformer/{geotransformer.py:9-155,
 superpoint_matching.py:7-50, local_global_registration.py:11-235}``)."""
+import threading
+
 import torch
 import torch.nn as nn
 
 from ... import functional as GF
 from ..transformer.modules import SinusoidalPositionalEmbedding, RPEConditionalTransformer, _WeightCache
+
+
+_TABLE_LOCK = threading.Lock()     # module-level: a lock inside the nn.Module would break deepcopy / pickling of the model
 
 
 class GeometricStructureEmbedding(nn.Module):
@@ -20,6 +25,29 @@ class GeometricStructureEmbedding(nn.Module):
         self.proj_d = nn.Linear(hidden_dim, hidden_dim)
         self.proj_a = nn.Linear(hidden_dim, hidden_dim)
         self._cache = _WeightCache()
+        self._table = None
+
+    def table(self):
+        """``functional.GseTable`` of the current projection weights when the tabulated mode (``GF.GSE_MODE == 5``) is on, else
+        None.  Rebuilt when any of the four parameters changes (version counters) or the grid settings do; built once and
+        complete before it is returned, so the engine's lanes (host thread + stream each) can share it."""
+        c = self.proj_d.out_features
+        if GF.GSE_MODE != 5 or c not in (128, 256):
+            return None
+        params = (self.proj_d.weight, self.proj_d.bias, self.proj_a.weight, self.proj_a.bias)
+        key = tuple((p.data_ptr(), p._version) for p in params) + (GF.GSE_TABLE_INV_STEP, GF.GSE_TABLE_D_MAX, float(self.sigma_a))
+        hit = self._table
+        if hit is None or hit[0] != key:
+            with _TABLE_LOCK:
+                hit = self._table
+                if hit is None or hit[0] != key:
+                    wd_t = self.proj_d.weight.detach().t().contiguous()
+                    wa_t = self.proj_a.weight.detach().t().contiguous()
+                    tab = GF.gse_table(self.embedding.div_term, wd_t, wa_t, self.proj_d.bias.detach().contiguous(),
+                                       self.proj_a.bias.detach().contiguous(), self.sigma_a)
+                    hit = (key, tab)
+                    self._table = hit
+        return hit[1]
 
     @torch.no_grad()
     def get_embedding_indices(self, points):
@@ -42,7 +70,7 @@ class GeometricStructureEmbedding(nn.Module):
         n, c = pts.shape[0], self.proj_d.out_features
         out = GF.scratch((n, n, c), pts.device, scratch_tag) if scratch_tag is not None else None
         emb = GF.gse_embed(d, a, self.embedding.div_term, self.proj_d.weight.detach(), self.proj_a.weight.detach(),
-                           self.proj_d.bias.detach(), self.proj_a.bias.detach(), wd_t, wa_t, out=out)
+                           self.proj_d.bias.detach(), self.proj_a.bias.detach(), wd_t, wa_t, out=out, table=self.table())
         return emb.unsqueeze(0) if squeeze else emb
 
 

@@ -189,6 +189,22 @@ int geob200_gse_embed_pairs(const float* d_indices, const float* a_indices, int6
                             const float* wd_t, const float* wa_t, const float* wd, const float* wa, const float* bd, const float* ba,
                             float* embeddings, int mode, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same embedding through TABULATED projections (csrc/gse_table.cu).  proj_d(sinusoid(x)) and proj_a(sinusoid(x)) are
+ * functions of one scalar, band-limited to 1 rad per index unit: geob200_gse_table_build tabulates both once per set of weights
+ * on a uniform grid of step 1/inv_step (power of two) over [0, d_max] / [0, a_max] (fp64 accumulation; node = fp32 values + fp16
+ * forward differences), geob200_gse_embed_table then needs 4 lookups + 3 max + 1 add per (row, channel) instead of the
+ * 2 * (1 + 3) * C^2 flop contraction.  Linear-interpolation error <= max|g''| / (8 inv_step^2) (< 1e-6 at inv_step 256 for
+ * unit-scale weights).  Index values outside the tabulated range are evaluated directly (sincosf + dot products with wd / wa),
+ * so results never depend on d_max / a_max -- only the speed does.  channels: 128 or 256.  The same (channels, inv_step, d_max,
+ * a_max) must be passed to both calls; table: geob200_gse_table_bytes(...) bytes of device memory, 16-byte aligned. */
+size_t geob200_gse_table_bytes(int64_t channels, int64_t inv_step, float d_max, float a_max);
+int geob200_gse_table_build(const float* div_term, const float* wd_t, const float* wa_t, const float* bd, const float* ba,
+                            int64_t channels, int64_t inv_step, float d_max, float a_max, void* table, size_t table_bytes,
+                            void* stream);
+int geob200_gse_embed_table(const float* d_indices, const float* a_indices, int64_t n_rows, int64_t channels, const void* table,
+                            size_t table_bytes, int64_t inv_step, float d_max, float a_max, const float* div_term, const float* wd,
+                            const float* wa, const float* bd, const float* ba, float* embeddings, void* stream);
+
 /* Fused multi-head attention: softmax((q.k + qp.E + qb)/sqrt(d)) v  (rpe_transformer.py:51-70 with proj_p moved onto
  * q; vanilla_transformer.py:50-68 when qp = qb = embed = NULL).  q (n_query,C), k,v (n_key,C), qp (n_query,H,C),
  * qb (n_query,H), embed (n_query,n_key,C).  With a workspace and C = 128 or 256 the streaming path runs (one coalesced

@@ -427,6 +427,76 @@ def test_gse_embedding_fp16_split_is_scale_invariant():
         assert err < 2e-5, f'weight scale {wscale}: relative error {err:.2e}'
 
 
+def _gse_case(c, n, extent, seed):
+    g = torch.Generator().manual_seed(seed)
+    pts = torch.rand(n, 3, generator=g) * extent
+    sd = {'e.embedding.div_term': torch.exp(torch.arange(0, c, 2).float() * (-np.log(10000.0) / c)),
+          'e.proj_d.weight': torch.randn(c, c, generator=g) / math.sqrt(c), 'e.proj_d.bias': torch.randn(c, generator=g) * 0.1,
+          'e.proj_a.weight': torch.randn(c, c, generator=g) / math.sqrt(c), 'e.proj_a.bias': torch.randn(c, generator=g) * 0.1}
+    cu = {k: v.cuda() for k, v in sd.items()}
+    return pts, sd, cu
+
+
+def _gse_table(cu, **kw):
+    return GF.gse_table(cu['e.embedding.div_term'], cu['e.proj_d.weight'].t().contiguous(), cu['e.proj_a.weight'].t().contiguous(),
+                        cu['e.proj_d.bias'], cu['e.proj_a.bias'], 15, **kw)
+
+
+@pytest.mark.parametrize('c,n,sigma_d,extent', [(256, 7, 0.2, 2.0), (256, 100, 0.2, 2.0), (256, 271, 0.2, 3.0), (128, 40, 4.8, 20.0),
+                                                (128, 173, 4.8, 60.0)])
+def test_gse_embedding_tabulated_projections(c, n, sigma_d, extent):
+    """mode 5 (csrc/gse_table.cu): proj_d / proj_a tabulated over the scalar index, 4 lookups per (i, j) -- vs the oracle.  Also
+    with a table that covers only half of the distance range (the rest takes the direct evaluation inside the kernel) and with a
+    4x coarser grid (error grows with step^2, still inside the tolerance)."""
+    pts, sd, cu = _gse_case(c, n, extent, 100 + n)
+    want = G.structure_embedding(sd, 'e.', pts, sigma_d, 15, 3)
+    d, a = GF.gse_indices(pts.cuda(), sigma_d, 15, 3)
+    args = (d, a, cu['e.embedding.div_term'], cu['e.proj_d.weight'], cu['e.proj_a.weight'], cu['e.proj_d.bias'], cu['e.proj_a.bias'],
+            cu['e.proj_d.weight'].t().contiguous(), cu['e.proj_a.weight'].t().contiguous())
+    close(GF.gse_embed(*args, mode=5, table=_gse_table(cu)), want, 1e-5, 'structure embedding, tabulated projections')
+    close(GF.gse_embed(*args, mode=5, table=_gse_table(cu, d_max=float(d.max()) * 0.5)), want, 2e-5,
+          'structure embedding, table covering half of the distance range')
+    close(GF.gse_embed(*args, mode=5, table=_gse_table(cu, inv_step=64)), want, 3e-5, 'structure embedding, table step 1/64')
+    with pytest.raises(RuntimeError):
+        GF.gse_embed(*args, mode=5)                      # no table given
+
+
+def test_gse_embedding_tabulated_is_scale_invariant():
+    """one power-of-two scale per table keeps the fp16 differences in range: tiny and huge weights keep fp32-level accuracy"""
+    for wscale in (1e-4, 1.0, 300.0):
+        pts, sd, cu = _gse_case(256, 60, 1.0, 5)
+        for k in list(sd):
+            if 'proj' in k:
+                sd[k] = sd[k] * wscale
+        cu = {k: v.cuda() for k, v in sd.items()}
+        want = G.structure_embedding(sd, 'e.', pts, 0.2, 15, 3)
+        d, a = GF.gse_indices(pts.cuda(), 0.2, 15, 3)
+        got = GF.gse_embed(d, a, cu['e.embedding.div_term'], cu['e.proj_d.weight'], cu['e.proj_a.weight'], cu['e.proj_d.bias'],
+                           cu['e.proj_a.bias'], None, None, mode=5, table=_gse_table(cu))
+        err = (got.cpu() - want).abs().max().item() / want.abs().max().item()
+        assert err < 1e-5, f'weight scale {wscale}: relative error {err:.2e}'
+
+
+def test_gse_table_follows_the_weights():
+    """GeometricStructureEmbedding.table(): rebuilt when a projection parameter changes in place (load_state_dict)"""
+    from geotransformer_b200.modules.geotransformer import GeometricStructureEmbedding
+    prev = GF.GSE_MODE
+    GF.GSE_MODE = 5
+    try:
+        torch.manual_seed(3)
+        emb = GeometricStructureEmbedding(256, 0.2, 15, 3).cuda()
+        pts = torch.rand(50, 3).cuda()
+        t1 = emb.table()
+        e1 = emb(pts).clone()
+        assert emb.table() is t1
+        with torch.no_grad():
+            emb.proj_a.bias.add_(1.0)
+        assert emb.table() is not t1
+        close(emb(pts), e1 + 1.0, 2e-6, 'embedding after an in-place bias update')
+    finally:
+        GF.GSE_MODE = prev
+
+
 def test_gse_embedding_generic_channels():
     """hidden_dim 128 (KITTI) goes through the generic contraction"""
     g = torch.Generator().manual_seed(9)
