@@ -13,9 +13,11 @@ from . import _lib as L
 _f32, _i64, _u8, _i32 = torch.float32, torch.int64, torch.uint8, torch.int32
 
 # mode of the structure-embedding contraction (see geob200_gse_embed): 0 fp32 CUDA cores, 1 tcgen05 3xTF32, 2 1xTF32,
-# 3 3xFP16 (fp32-accurate like 3xTF32 at half the tensor-pipe time; default), 4 3xFP16 on CTA pairs,
-# 5 tabulated projections (geob200_gse_embed_table: no contraction at all; needs a ``table`` from ``gse_table``)
-GSE_MODE = int(__import__('os').environ.get('GEOB200_GSE_MODE', '3'))
+# 3 3xFP16 (fp32-accurate like 3xTF32 at half the tensor-pipe time), 4 3xFP16 on CTA pairs,
+# 5 tabulated projections (geob200_gse_embed_table: no contraction at all; default -- 6.4x faster than mode 3 and 3x closer to
+# the oracle, profiles/r02_gse_table_check.txt).  Mode 5 needs the ``table`` of the weights (``gse_table``; the modules build and
+# cache it); the functional ops called WITHOUT a table and without an explicit mode run the tcgen05 contraction (mode 3).
+GSE_MODE = int(__import__('os').environ.get('GEOB200_GSE_MODE', '5'))
 # tabulation grid of mode 5: step 1 / GSE_TABLE_INV_STEP index units (power of two), distance indices up to GSE_TABLE_D_MAX
 # (larger ones are evaluated directly inside the kernel: correct, slow)
 GSE_TABLE_INV_STEP = int(__import__('os').environ.get('GEOB200_GSE_TABLE_INV_STEP', '256'))
@@ -425,11 +427,19 @@ def _gse_embed_table(d_indices, a_indices, n_rows, div_term, wd, wa, bd, ba, tab
     return out
 
 
+def _gse_mode(mode, table):
+    """explicit mode wins (mode 5 without a table is an error, raised by ``_gse_embed_table``); the default is GSE_MODE, except
+    that the tabulated mode without a table means the caller has none: tensor-core contraction"""
+    if mode is not None:
+        return mode
+    return 3 if (GSE_MODE == 5 and table is None) else GSE_MODE
+
+
 def gse_embed_flat(d_indices, a_indices, n_rows, div_term, wd, wa, bd, ba, wd_t, wa_t, out, mode=None, table=None):
     """structure embedding of ``n_rows`` (anchor, point) pairs given as flat index arrays -- the (i, j) pairs of SEVERAL clouds
     concatenated (d (n_rows,), a (n_rows, k)) -> out (n_rows, C): one launch for a whole batch of clouds."""
     c = wd.shape[0]
-    mode = GSE_MODE if mode is None else mode
+    mode = _gse_mode(mode, table)
     if mode == 5 and c in (128, 256):
         return _gse_embed_table(d_indices, a_indices, n_rows, div_term, wd, wa, bd, ba, table, out)
     if c == 128 and mode != 0:
@@ -449,7 +459,7 @@ def gse_embed_flat(d_indices, a_indices, n_rows, div_term, wd, wa, bd, ba, wd_t,
 def gse_embed(d_indices, a_indices, div_term, wd, wa, bd, ba, wd_t, wa_t, mode=None, out=None, table=None):
     n = d_indices.shape[0]
     c = wd.shape[0]
-    mode = GSE_MODE if mode is None else mode
+    mode = _gse_mode(mode, table)
     emb = torch.empty((n, n, c), dtype=_f32, device=d_indices.device) if out is None else out
     if mode == 5 and c in (128, 256):
         return _gse_embed_table(d_indices, a_indices, n * n, div_term, wd, wa, bd, ba, table, emb)

@@ -44,6 +44,24 @@ def test_pure_host_queries_work_without_gpu():
     assert lib.geob200_launch_count() == 0
 
 
+def test_structure_embedding_table_size_and_argument_checks():
+    """geob200_gse_table_bytes is pure host arithmetic (header + (nodes_d + nodes_a) x channels x 6 B); the build / embed entry
+    points reject bad grids BEFORE any launch (so this runs without a GPU) and leave a message in geob200_last_error()"""
+    lib = L.lib()
+    nodes = (96 * 256 + 1) + (int(12.25 * 256) + 1)
+    assert lib.geob200_gse_table_bytes(256, 256, 96.0, 12.25) == 256 + nodes * 256 * 6
+    assert lib.geob200_gse_table_bytes(128, 256, 96.0, 12.25) == 256 + nodes * 128 * 6
+    assert lib.geob200_gse_table_bytes(256, 0, 96.0, 12.25) == 0 and lib.geob200_gse_table_bytes(256, 256, -1.0, 12.25) == 0
+    buf = ctypes.create_string_buffer(4096)
+    bad = [(192, 256, 96.0, 'channels'), (256, 100, 96.0, 'power of two'), (256, 256, 96.0, 'too small')]
+    for channels, inv_step, d_max, word in bad:
+        rc = lib.geob200_gse_table_build(None, None, None, None, None, channels, inv_step, d_max, 12.25, ctypes.addressof(buf), 4096, None)
+        assert rc != 0 and word in lib.geob200_last_error().decode(), (channels, inv_step, lib.geob200_last_error())
+    rc = lib.geob200_gse_embed_table(None, None, 10, 256, ctypes.addressof(buf), 4096, 256, 96.0, 12.25, None, None, None, None, None, None, None)
+    assert rc != 0 and 'table buffer smaller' in lib.geob200_last_error().decode()
+    assert lib.geob200_launch_count() == 0
+
+
 def test_product_does_not_import_the_oracle():
     """the oracle is test infrastructure: nothing under geotransformer_b200/ may reference it"""
     pkg = os.path.join(ROOT, 'geotransformer_b200')

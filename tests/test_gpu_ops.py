@@ -511,13 +511,13 @@ def test_gse_embedding_generic_channels():
     got = GF.gse_embed(d, a, cu['e.embedding.div_term'], cu['e.proj_d.weight'], cu['e.proj_a.weight'], cu['e.proj_d.bias'],
                        cu['e.proj_a.bias'], cu['e.proj_d.weight'].t().contiguous(), cu['e.proj_a.weight'].t().contiguous(), mode=0)
     close(got, want, 2e-5, 'structure embedding C=128')
-    # default path for hidden 128: the 3xFP16 tcgen05 kernel instantiated for N = 128 (two angle + two distance chunks per tile)
+    # tensor-core path for hidden 128: the 3xFP16 tcgen05 kernel instantiated for N = 128 (two angle + two distance chunks per tile)
     for nn in (40, 173):
         pts = torch.rand(nn, 3, generator=g) * 20
         want = G.structure_embedding(sd, 'e.', pts, 4.8, 15, 3)
         d, a = GF.gse_indices(pts.cuda(), 4.8, 15, 3)
         got = GF.gse_embed(d, a, cu['e.embedding.div_term'], cu['e.proj_d.weight'], cu['e.proj_a.weight'], cu['e.proj_d.bias'],
-                           cu['e.proj_a.bias'], cu['e.proj_d.weight'].t().contiguous(), cu['e.proj_a.weight'].t().contiguous())
+                           cu['e.proj_a.bias'], cu['e.proj_d.weight'].t().contiguous(), cu['e.proj_a.weight'].t().contiguous(), mode=3)
         close(got, want, 3e-5, f'structure embedding C=128, tcgen05 3xFP16 (n={nn})')
 
 
