@@ -4,7 +4,7 @@
 set -x
 mkdir -p gpurun_out
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_launches_final.csv python tools/ncu_target.py 8 3 > gpurun_out/r02_ncu_a.log 2>&1
-TOP='linear_tc_persistent_kernel|gse_embed_f16_kernel|att_stream_kernel|kpconv_gather_kernel|rs_query_kernel|att_qk_kernel|att_pv_kernel'
+TOP='linear_tc_persistent_kernel|gse_embed_f16_kernel|table_embed_kernel|att_stream_kernel|kpconv_gather_kernel|rs_query_kernel|att_qk_kernel|att_pv_kernel'
 timeout 700 ncu --set full --clock-control none --kernel-name regex:"$TOP" --launch-skip 70 --launch-count 60 -f -o /tmp/r02_top_full python tools/ncu_target.py 4 2 > gpurun_out/r02_ncu_b.log 2>&1
 ncu -i /tmp/r02_top_full.ncu-rep --page raw --csv > gpurun_out/r02_top_full_raw.csv 2>/dev/null
 timeout 300 ncu --set full --clock-control none --import-source on --kernel-name regex:"linear_tc_persistent_kernel|gse_embed_f16_kernel|att_stream_kernel" --launch-skip 50 --launch-count 3 -f -o gpurun_out/r02_tc_source python tools/ncu_target.py 4 2 > gpurun_out/r02_ncu_c.log 2>&1
