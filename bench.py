@@ -11,11 +11,13 @@ Prints ONE JSON line (see the task contract):
   value     pairs/s with the raw pairs already resident in HBM when the timed region starts
   e2e       pairs/s through the public API with HOST (pinned) inputs: H2D + collate + forward + D2H of transform + metrics
   roofline  the dominant kernel family by GPU-time share (tcgen05 3xTF32 GEMMs), algorithmic FLOPs / CUDA-event time, with the
-            measured TF32 dense peak and the committed ncu DRAM traffic; the structure-embedding contraction (largest single
-            launch) is reported beside it as roofline_gse_embed
+            measured TF32 dense peak and the committed ncu DRAM traffic; beside it roofline_gse_embed (the structure embedding:
+            an HBM row with the default tabulated projections, a tensor row with --gse-mode 3) and roofline_attention (HBM)
+  config    the STATIC workload description, identical in both arms; run_info = what was measured during the run
   cpu_baseline    the reference's CPU path on this box's host cores, bounded sample (N=1 only): 16-thread and 1-thread numbers
   gpu_eager_port  host collate + the pinned torch restatement executed as eager ops on this GPU (what a drop-in user sees today)
---impl reference times the CPU path alone (the reference's own C++ collate ops + the oracle port of the forward).
+--impl reference times the CPU path alone (the reference's own C++ collate ops + the oracle port of the forward) on the same
+config, each of its steps a bounded sample (one pair) of the configured step.
 """
 import argparse
 import json
@@ -285,6 +287,28 @@ def cpu_reference_pairs_per_s(workload, n_pairs, threads, return_times=False):
     return n_pairs / total, total, desc
 
 
+def step_shape(args):
+    """(pairs per forward, forwards in flight, pairs per GPU and step) of the GPU arm for these flags"""
+    batch = max(1, args.batch)
+    lanes = max(1, args.streams if args.streams is not None else (2 if batch > 1 else 4))
+    per_step = max(1, args.pairs_per_step if args.pairs_per_step is not None else (4 * batch * lanes if batch > 1 else lanes))
+    return batch, lanes, per_step
+
+
+def workload_config(args, world):
+    """The STATIC description of the workload: identical in the GPU arm and in the --impl reference arm (which times a bounded
+    sample of it per step, see its ``step_sample``); everything measured during the run goes into ``run_info`` instead."""
+    from geotransformer_b200.config import make_cfg
+    from geotransformer_b200.synth import WORKLOADS
+    cfg_name, _, kw, _ = WORKLOADS[args.workload]
+    batch, lanes, per_step = step_shape(args)
+    return {'workload': args.workload, 'pairs_per_step_per_gpu': per_step, 'pairs_per_forward': batch, 'forwards_in_flight': lanes,
+            'points_per_cloud': int(kw['n']), 'sinkhorn_iterations': make_cfg(cfg_name).model.num_sinkhorn_iterations,
+            'parallelism': f'pairs sharded over {world} GPU(s), one all_gather of metric rows',
+            'l2': 'a different pair every step; per-pair working set (~0.5 GB incl. 2x75 MB embeddings) exceeds the 126 MB L2',
+            'weights': 'random init (synthetic_state_dict seed 7351)'}
+
+
 def main():
     args = parse()
     rank, world, local = dist_env()
@@ -304,8 +328,10 @@ def main():
         line = {'metric': METRIC, 'value': v, 'unit': 'pairs/s', 'n_gpus': args.gpus, 'steps': steps, 'warmup': warm,
                 'ms_per_step': 1000.0 * secs / steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                 'dtype': 'f32', 'data': 'synthetic', 'impl': 'reference',
-                'config': {'workload': args.workload, 'pairs_per_step': 1,
-                           'note': f'CPU path, rank 0 only; --steps {args.steps} --warmup {args.warmup} bounded to {steps} / {warm} pairs'},
+                'config': workload_config(args, args.gpus),
+                'step_sample': f'each step of this arm is a BOUNDED SAMPLE of the configured step: 1 pair of the workload on the host cores '
+                               f'(CPU path, rank 0 only; --steps {args.steps} --warmup {args.warmup} bounded to {steps} / {warm} pairs); the unit '
+                               f'(pairs/s) is the same',
                 'cpu_baseline': {'value': v, 'unit': 'pairs/s', 'cores': threads, 'kind': kind, 'sample': desc,
                                  'seconds_per_pair': _stats(per_pair),
                                  'one_thread': {'value': v1, 'unit': 'pairs/s', 'cores': 1, 'sample': desc1},
@@ -358,10 +384,8 @@ def main():
     enable_native(model)
 
     from geotransformer_b200.engine import RegistrationEngine
-    BATCH = max(1, args.batch)
-    LANES = max(1, args.streams if args.streams is not None else (2 if BATCH > 1 else 4))
+    BATCH, LANES, S = step_shape(args)          # pairs per forward, forwards in flight, pairs per GPU and step
     W, K = args.warmup, args.steps
-    S = max(1, args.pairs_per_step if args.pairs_per_step is not None else (4 * BATCH * LANES if BATCH > 1 else LANES))   # pairs per GPU and step
     pairs = make_inputs(args.workload, (W + K) * S, rank, world)
     # host staging (pinned) and device-resident copies: one pinned slab and one device slab per key, the pairs are views
     slab_h = {k: torch.from_numpy(np.stack([p[k] for p in pairs])).pin_memory() for k in pairs[0]}
@@ -555,12 +579,9 @@ def main():
         'metric': METRIC, 'value': total_pairs / (ms_res * 1e-3), 'unit': 'pairs/s', 'n_gpus': world, 'steps': K, 'warmup': W,
         'ms_per_step': ms_res / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic',
-        'config': {'workload': args.workload, 'pairs_per_step_per_gpu': S, 'pairs_per_forward': BATCH, 'forwards_in_flight': LANES, 'points_per_cloud': int(pairs[0]['ref_points'].shape[0]),
-                   'superpoints_per_cloud': int(np.mean(n_c)) if n_c else None, 'sinkhorn_iterations': cfg.model.num_sinkhorn_iterations,
-                   'parallelism': f'pairs sharded over {world} GPU(s), one all_gather of metric rows',
-                   'host_threads_pinned_to_gpu_numa_node': bool(engine.pinned_cpu),
-                   'l2': 'a different pair every step; per-pair working set (~0.5 GB incl. 2x75 MB embeddings) exceeds the 126 MB L2',
-                   'weights': 'random init (synthetic_state_dict seed 7351)'},
+        'config': workload_config(args, world),
+        'run_info': {'superpoints_per_cloud': int(np.mean(n_c)) if n_c else None,
+                     'host_threads_pinned_to_gpu_numa_node': bool(engine.pinned_cpu)},
         'e2e': {'value': total_pairs / (ms_e2e * 1e-3), 'unit': 'pairs/s', 'ms_per_step': ms_e2e / K,
                 'h2d_bytes_per_step': int(h2d_bytes), 'd2h_bytes_per_step': 96 * S},
         'gpu_launches': int(launches), 'gpu_launches_per_pair': launches / max(K * S, 1),
