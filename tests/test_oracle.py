@@ -145,3 +145,38 @@ def test_tabulated_structure_embedding_model_vs_oracle(c, n, sigma_d, extent):
     assert float((got - want).abs().max()) < 1e-5
     coarse = structure_embedding_tabulated(sd, 'e.', pts, sigma_d, 15, 3, inv_step=64)
     assert float((coarse - want).abs().max()) < 5e-5
+
+
+@pytest.mark.skipif(not ref_ext.available(), reason='oracle/_ref not built')
+def test_c_restatement_matches_reference_build_on_adversarial_small_inputs():
+    """hypothesis: several ragged clouds per batch, coordinates quantised to a coarse lattice (many points per voxel, exact-distance
+    ties, duplicated points), negative coordinates, 1-point clouds.  grid_subsampling: values AND unordered_map order bit for bit;
+    radius_neighbors: identical rows up to the order inside exact-distance tie groups (std::sort is unstable in both)."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None, derandomize=True)
+    @given(st.lists(st.integers(1, 40), min_size=1, max_size=4), st.integers(0, 2 ** 31 - 1), st.sampled_from([0.0, 0.05, 0.25]),
+           st.sampled_from([0.3, 0.5, 1.0]))
+    def check(lengths, seed, lattice, voxel):
+        g = torch.Generator().manual_seed(seed)
+        n = sum(lengths)
+        pts = (torch.rand(n, 3, generator=g) - 0.5) * 4.0
+        if lattice > 0:
+            pts = torch.round(pts / lattice) * lattice
+        pts = pts.contiguous()
+        lens = torch.tensor(lengths)
+        a, al = ref_ext.grid_subsampling(pts, lens, voxel)
+        b, bl = co.grid_subsampling(pts, lens, voxel)
+        assert torch.equal(al, bl) and torch.equal(a, b)
+        r = voxel * 1.5
+        na = ref_ext.radius_neighbors(pts, pts, lens, lens, r)
+        nb = co.radius_neighbors(pts, pts, lens, lens, r)
+        assert na.shape == nb.shape
+        assert torch.equal(G.canonical_neighbors(pts, pts, na), G.canonical_neighbors(pts, pts, nb))
+        # sub-sampled queries against the full support (the 'subsampling' tables of the collate)
+        nq = ref_ext.radius_neighbors(a, pts, al, lens, r)
+        nr = co.radius_neighbors(a, pts, al, lens, r)
+        assert nq.shape == nr.shape
+        assert torch.equal(G.canonical_neighbors(a, pts, nq), G.canonical_neighbors(a, pts, nr))
+
+    check()
