@@ -176,6 +176,49 @@ def attention_roofline(dev, n_sp, clouds, channels, heads, peak_hbm, traffic):
         return {'kernel': 'self-attention', 'bound': 'hbm', 'achieved': None, 'note': f'failed: {type(ex).__name__}: {ex}'}
 
 
+def gse_contraction_roofline(dev, emb_mod, n_sp, clouds, peak_tf, peak_src, traffic):
+    """Tensor roofline of the structure embedding IN ITS CONTRACTION FORM (tcgen05 3xFP16 kernel, GSE mode 3 -- the dense
+    contraction north_star names), timed alone on a batch-sized problem after the timed regions: the default path does not run it
+    any more (tabulated projections, roofline_gse_embed), the number stays in the line for comparison.  Same call sequence as
+    tools/gse_table_check.py."""
+    try:
+        from geotransformer_b200 import functional as GF
+        C = emb_mod.proj_d.out_features
+        if C not in (128, 256):
+            return None
+        g = torch.Generator().manual_seed(11)
+        pts = (torch.rand(clouds * n_sp, 3, generator=g) * 3.0).to(dev)
+        rows = clouds * n_sp * n_sp
+        d_all, a_all = torch.empty(rows, device=dev), torch.empty(rows, 3, device=dev)
+        E = torch.empty(rows, C, device=dev)
+        GF.gse_indices_batched(pts, [n_sp] * clouds, emb_mod.sigma_d, emb_mod.sigma_a, emb_mod.angle_k, d_all, a_all)
+        wd, wa = emb_mod.proj_d.weight.detach(), emb_mod.proj_a.weight.detach()
+        rest = (emb_mod.embedding.div_term, wd, wa, emb_mod.proj_d.bias.detach(), emb_mod.proj_a.bias.detach(), wd.t().contiguous(),
+                wa.t().contiguous(), E)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        ts = []
+        for i in range(6):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            GF.gse_embed_flat(d_all, a_all, rows, *rest, mode=3)
+            e1.record()
+            e1.synchronize()
+            if i:
+                ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        ms = ts[len(ts) // 2]
+        flops = 2.0 * rows * 4 * C * C
+        ach = flops / (ms * 1e-3) / 1e12
+        return {'kernel': f'gse_embed_f16_kernel<{C}> (structure embedding as a tcgen05 3xFP16 contraction; NOT on the default path)', 'bound': 'tensor',
+                'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf, 'traffic': traffic.get('gse_embed_bytes_per_launch'),
+                'ms_per_launch': ms, 'flops_per_launch': flops, 'clouds': clouds, 'superpoints_per_cloud': n_sp,
+                'timing': 'CUDA events around the launch (median of 5, L2 flushed), kernel alone on the GPU, after the timed regions',
+                'peak_source': f'{peak_src} bf16 dense BURST (MEASURED_PEAKS.json; the kernel is timed alone)'}
+    except Exception as ex:
+        return {'kernel': 'gse_embed_f16_kernel', 'bound': 'tensor', 'achieved': None, 'note': f'failed: {type(ex).__name__}: {ex}'}
+
+
 def load_traffic():
     """per-launch DRAM traffic of the roofline kernels from the committed ncu --set full capture (profiles/r02_dram_traffic.json)"""
     p = os.path.join(ROOT, 'profiles', 'r02_dram_traffic.json')
@@ -558,8 +601,11 @@ def main():
                                f'8192^3 with allow_tf32, best of 10, this run; the kernel executes 3 TF32 MMAs per product term'}
 
     roofline_att = None
+    roofline_gse_tc = None
     if rank == 0 and C in (128, 256) and n_c:
         roofline_att = attention_roofline(dev, int(np.mean(n_c)), 2 * BATCH, C, cfg.geotransformer.num_heads, peak_hbm, traffic)
+        if GF.GSE_MODE == 5:
+            roofline_gse_tc = gse_contraction_roofline(dev, model.transformer.embedding, int(np.mean(n_c)), 2 * BATCH, peak_tf, peak_src, traffic)
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -586,7 +632,7 @@ def main():
                 'h2d_bytes_per_step': int(h2d_bytes), 'd2h_bytes_per_step': 96 * S},
         'gpu_launches': int(launches), 'gpu_launches_per_pair': launches / max(K * S, 1),
         'cuda_mallocs': {'timed_region_resident': int(mallocs_res), 'timed_region_e2e': int(mallocs_e2e)},
-        'per_rank_ms': {'value': per_rank_res, 'e2e': per_rank_e2e}, 'roofline': roofline, 'roofline_gse_embed': roofline_gse, 'roofline_attention': roofline_att, 'cpu_baseline': cpu, 'gpu_eager_port': eager, 'clocks': sampler.summary(),
+        'per_rank_ms': {'value': per_rank_res, 'e2e': per_rank_e2e}, 'roofline': roofline, 'roofline_gse_embed': roofline_gse, 'roofline_gse_contraction_tcgen05': roofline_gse_tc, 'roofline_attention': roofline_att, 'cpu_baseline': cpu, 'gpu_eager_port': eager, 'clocks': sampler.summary(),
         'quality': {'median_rre_deg': float(rows_t[:, 0].median()), 'median_rte': float(rows_t[:, 1].median()),
                     'mean_correspondences': float(rows_t[:, 2].mean()), 'pairs': int(rows_t.shape[0]),
                     'mean_PIR': float(rows_t[:, 4].nanmean()), 'mean_IR': float(rows_t[:, 5].nanmean()),
