@@ -62,6 +62,30 @@ def test_structure_embedding_table_size_and_argument_checks():
     assert lib.geob200_launch_count() == 0
 
 
+def test_entry_points_reject_bad_arguments_before_any_launch():
+    """error behaviour of the boundary (the reference raises through TORCH_CHECK, extensions/common/torch_helper.h:6-35): bad sizes /
+    empty clouds / non-positive voxel or radius give a negative return code and a message, checked BEFORE any CUDA call -- so this
+    runs without a GPU and the launch counter stays at zero"""
+    import numpy as np
+    lib = L.lib()
+    lens = np.array([5, 0], dtype=np.int64)
+    buf = ctypes.create_string_buffer(1 << 16)
+    p = ctypes.addressof(buf)
+
+    def err():
+        return lib.geob200_last_error().decode()
+
+    assert lib.geob200_grid_subsample(p, 0, lens.ctypes.data, 2, 0.1, p, p, p, 1 << 16, None) < 0 and 'empty input' in err()
+    assert lib.geob200_grid_subsample(p, 5, lens.ctypes.data, 2, 0.0, p, p, p, 1 << 16, None) < 0 and 'voxel' in err()
+    assert lib.geob200_grid_subsample(p, 5, lens.ctypes.data, 2, 0.1, p, p, p, 1 << 16, None) < 0 and 'cloud 1 is empty' in err()
+    assert lib.geob200_radius_search(p, 0, p, 5, p, p, 1, 0.1, 8, p, p, p, p, 1 << 16, None) < 0 and 'empty input' in err()
+    assert lib.geob200_radius_search(p, 5, p, 5, p, p, 1, -1.0, 8, p, p, p, p, 1 << 16, None) < 0 and 'radius' in err()
+    assert lib.geob200_neighbor_histogram(p, 0, 8, 5, 16, p, None) < 0 and 'empty input' in err()
+    assert lib.geob200_gse_indices(p, 0, 0.2, 3.8, 3, p, p, None) < 0 and 'empty cloud' in err()
+    assert lib.geob200_gse_indices(p, 10, 0.2, 3.8, 5, p, p, None) < 0 and 'angle_k' in err()
+    assert lib.geob200_launch_count() == 0
+
+
 def test_product_does_not_import_the_oracle():
     """the oracle is test infrastructure: nothing under geotransformer_b200/ may reference it"""
     pkg = os.path.join(ROOT, 'geotransformer_b200')
