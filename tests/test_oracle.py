@@ -180,3 +180,18 @@ def test_c_restatement_matches_reference_build_on_adversarial_small_inputs():
         assert torch.equal(G.canonical_neighbors(a, pts, nq), G.canonical_neighbors(a, pts, nr))
 
     check()
+
+
+def test_boundary_2_op_restatements_match_the_real_reference_live():
+    """oracle/pin_ops_live.py in its own process (it imports the unmodified reference package and patches Tensor.cuda): the oracle's
+    pairwise_distance / knn_partition / get_point_to_node_indices / point_to_node_partition / ball_query_partition / apply_transform
+    are bit-identical to geotransformer.modules.ops on seeded inputs.  Only where /root/reference exists (the build container)."""
+    import os
+    import subprocess
+    import sys
+    from oracle import ref_harness
+    if not (ref_harness.available() and ref_ext.available()):
+        pytest.skip('needs /root/reference and oracle/_ref (build container only)')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, '-m', 'oracle.pin_ops_live'], cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and 'pinned:' in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
