@@ -24,7 +24,7 @@ from geotransformer_b200.synth import make_pair                     # noqa: E402
 from geotransformer_b200.weights import synthetic_state_dict        # noqa: E402
 from oracle import fixture, geo_oracle, ref_ext, ref_harness        # noqa: E402
 
-GOLD = os.path.join(ROOT, 'tests', 'golden')
+GOLD = os.environ.get('GEOB200_GOLDEN_OUT') or os.path.join(ROOT, 'tests', 'golden')    # override: regenerate elsewhere and compare
 LIMITS = {'demo2k': [38, 36, 36, 38], 'modelnet717': [13, 21, 27], 'kitti4k': [27, 75, 147, 157, 119]}
 
 
