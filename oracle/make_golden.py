@@ -28,8 +28,9 @@ GOLD = os.environ.get('GEOB200_GOLDEN_OUT') or os.path.join(ROOT, 'tests', 'gold
 LIMITS = {'demo2k': [38, 36, 36, 38], 'modelnet717': [13, 21, 27], 'kitti4k': [27, 75, 147, 157, 119]}
 
 
-def run(workload):
-    pair = make_pair(workload, 0)
+def run(workload, index=0, write=True):
+    """reference run + restatement check on pair ``index`` of the workload; ``write``: pack the fixture (pair 0 is the committed one)"""
+    pair = make_pair(workload, index)
     cfg = make_cfg(pair['config'])
     limits = cfg.neighbor_limits or LIMITS[workload]
     torch.manual_seed(0)
@@ -97,6 +98,15 @@ def run(workload):
         a, b = o['matching_scores'][perm], ref_out['matching_scores']
         report['matching_scores'] = float((a - b).abs().max())
         report['ref_node_corr_indices'] = report['src_node_corr_indices'] = True
+        # the fine correspondences come out patch after patch, i.e. block-permuted with the coarse order: compare them as a SET
+        # (rows [ref point, src point, score] sorted lexicographically)
+
+        def rows(out):
+            r = torch.cat([out['ref_corr_points'], out['src_corr_points'], out['corr_scores'][:, None]], dim=1).double().numpy()
+            return r[np.lexsort(r.T[::-1])]
+        ra, rb = rows(o), rows(ref_out)
+        same = ra.shape == rb.shape and float(np.abs(ra - rb).max()) if ra.shape == rb.shape else 'SHAPE'
+        report['ref_corr_points'] = report['src_corr_points'] = report['corr_scores'] = same
     # ground-truth superpoint correspondences and the Evaluator (loss.py:95-159)
     report['gt_node_corr_indices'] = bool(torch.equal(o['gt_node_corr_indices'], ref_out['gt_node_corr_indices']))
     report['gt_node_corr_overlaps'] = float((o['gt_node_corr_overlaps'] - ref_out['gt_node_corr_overlaps']).abs().max())
@@ -126,6 +136,9 @@ def run(workload):
            (isinstance(v, float) and v > (1e-3 if k.endswith('RRE') else 1e-5))]   # RRE: acos of an fp32 3x3 product
     assert not bad, f'oracle restatement deviates from the reference: {bad}'
 
+    if not write:
+        print(f'[{workload}] pair {index}: restatement == reference (no fixture written)')
+        return
     # ---- fixtures
     g = fixture.pack(data, taps, ref_out, o['node_corr_scores'], limits)
     g['metric_names'] = np.array(sorted(ref_metrics))
@@ -161,5 +174,10 @@ def run_calibration():
 
 if __name__ == '__main__':
     assert ref_harness.available(), 'needs /root/reference'
+    # `check:<workload>:<pair index>` = compare the restatement with the reference on ANOTHER pair of the workload, write nothing
     for w in (sys.argv[1:] or ['demo2k', 'modelnet717', 'kitti4k', 'calibration']):
-        run_calibration() if w == 'calibration' else run(w)
+        if w.startswith('check:'):
+            _, name, idx = w.split(':')
+            run(name, int(idx), write=False)
+        else:
+            run_calibration() if w == 'calibration' else run(w)
