@@ -199,7 +199,7 @@ def test_boundary_2_op_restatements_match_the_real_reference_live():
 
 def test_golden_fixtures_regenerate_bit_identically_from_the_real_reference(tmp_path):
     """python -m oracle.make_golden (the REAL reference package imported from /root/reference, CPU) into a scratch directory gives,
-    array for array, the committed tests/golden/{demo2k,modelnet717}.npz -- and the script itself asserts that the restatement
+    array for array, ALL committed fixtures tests/golden/{demo2k,modelnet717,kitti4k,calibration}.npz -- and the script itself asserts that the restatement
     oracle/geo_oracle.py equals the reference run.  Only in the build container (the GPU box has no /root/reference)."""
     import os
     import subprocess
@@ -209,10 +209,10 @@ def test_golden_fixtures_regenerate_bit_identically_from_the_real_reference(tmp_
         pytest.skip('needs /root/reference and oracle/_ref (build container only)')
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ, GEOB200_GOLDEN_OUT=str(tmp_path))
-    r = subprocess.run([sys.executable, '-m', 'oracle.make_golden', 'demo2k', 'modelnet717'], cwd=root, env=env, capture_output=True, text=True,
-                       timeout=1200)
+    names = ('demo2k', 'modelnet717', 'kitti4k', 'calibration')
+    r = subprocess.run([sys.executable, '-m', 'oracle.make_golden'] + list(names), cwd=root, env=env, capture_output=True, text=True, timeout=1800)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    for w in ('demo2k', 'modelnet717'):
+    for w in names:
         new, old = np.load(tmp_path / f'{w}.npz'), np.load(os.path.join(root, 'tests', 'golden', f'{w}.npz'))
         assert sorted(new.files) == sorted(old.files)
         for k in new.files:
