@@ -471,12 +471,16 @@ def main():
     def segs():
         return torch.cuda.memory_stats(dev).get('segment.all.allocated', 0)
 
-    # One large block for torch's caching allocator to carve later requests from: the timed pairs are not the warm-up pairs, and a
-    # batch a few percent larger than any seen before regrows a scratch buffer -- without a cached block to split that is a
-    # cudaMalloc (a device-wide synchronisation) inside the first timed region (reported below as cuda_mallocs).
+    # One large cached block per lane for torch's caching allocator to carve later requests from (its free lists are per stream,
+    # the lanes allocate under their own streams): the timed pairs are not the warm-up pairs, and a batch a few percent larger than
+    # any seen before regrows a scratch buffer -- without a cached block to split that is a cudaMalloc (a device-wide
+    # synchronisation) inside the first timed region (reported below as cuda_mallocs).
     try:
-        pool = torch.empty(12 << 30, dtype=torch.uint8, device=dev)
-        del pool
+        for lane_stream in engine.streams:
+            with torch.cuda.stream(lane_stream):
+                pool = torch.empty(6 << 30, dtype=torch.uint8, device=dev)
+                del pool
+        torch.cuda.synchronize()
     except Exception:                      # not enough free memory: keep going, the counter will show the mallocs
         pass
     timed(resident, 0, W)
