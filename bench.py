@@ -180,7 +180,7 @@ def gse_contraction_roofline(dev, emb_mod, n_sp, clouds, peak_tf, peak_src, traf
     """Tensor roofline of the structure embedding IN ITS CONTRACTION FORM (tcgen05 3xFP16 kernel, GSE mode 3 -- the dense
     contraction north_star names), timed alone on a batch-sized problem after the timed regions: the default path does not run it
     any more (tabulated projections, roofline_gse_embed), the number stays in the line for comparison.  Same call sequence as
-    tools/gse_table_check.py."""
+    tests/gse_table_check.py."""
     try:
         from geotransformer_b200 import functional as GF
         C = emb_mod.proj_d.out_features

@@ -1,6 +1,7 @@
 """Tabulated structure embedding (GSE mode 5, csrc/gse_table.cu) on the GPU box: accuracy against the CPU oracle and the fp32 /
 tcgen05 kernels, the direct-evaluation path for arguments beyond the table, and the time of one batch-sized launch next to
-the tcgen05 3xFP16 kernel.  Prints one JSON line per check (test infrastructure: imports oracle/)."""
+the tcgen05 3xFP16 kernel.  Prints one JSON line per check.  A CHECKER (lives under tests/ because it imports oracle/), not a
+pytest module: ``python tests/gse_table_check.py`` (profiles/r02_gse_table_check.txt is its output, then still under tools/)."""
 import json
 import math
 import os

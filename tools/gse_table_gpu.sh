@@ -3,7 +3,7 @@
 # then the GPU tests that touch the embedding.  Everything lands in gpurun_out/ as it is produced.
 mkdir -p gpurun_out
 export GEOB200_GSE_MODE=5
-timeout 150 python tools/gse_table_check.py > gpurun_out/gse_table_check.txt 2>&1
+timeout 150 python tests/gse_table_check.py > gpurun_out/gse_table_check.txt 2>&1
 echo "check rc=$?" >> gpurun_out/gse_table_check.txt
 timeout 170 python bench.py --steps 6 --warmup 3 --no-cpu-baseline > gpurun_out/bench_gse_mode5.json 2> gpurun_out/bench_gse_mode5.err
 echo "bench rc=$?" >> gpurun_out/bench_gse_mode5.err
